@@ -1,0 +1,100 @@
+"""ctypes binding of include/asr_b200.h.  Fails loudly when libasr_b200.so is missing: no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
+
+ABI_VERSION = 1
+
+
+class AsrLibraryError(RuntimeError):
+    pass
+
+
+class AsrConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "sample_rate", "hop", "n_fft", "win", "n_mels", "segment_size", "context_size", "bias", "stride",
+        "d_model", "n_heads", "ffn_dim", "n_layers", "left_context", "ctc_hidden", "vocab", "precision", "max_sessions",
+        "max_batch")]
+
+
+class AsrStepOutC(C.Structure):
+    _fields_ = [("argmax_ids", C.c_void_p), ("new_tokens", C.c_void_p), ("n_new", C.c_void_p), ("blank_frames", C.c_void_p),
+                ("has_token", C.c_void_p), ("logprobs", C.c_void_p)]
+
+
+class AsrStatsC(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("stream_chunks", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("step_ms_p50", C.c_double), ("step_ms_p99", C.c_double), ("step_ms_max", C.c_double), ("step_ms_mean", C.c_double)]
+
+
+# name -> (restype, argtypes); must list every symbol include/asr_b200.h declares (tests check this).
+SIGNATURES = {
+    "asr_last_error": (C.c_char_p, []),
+    "asr_abi_version": (C.c_int, []),
+    "asr_default_config": (C.c_int, [C.POINTER(AsrConfigC), C.c_int]),
+    "asr_weights_count": (C.c_int, [C.POINTER(AsrConfigC), C.POINTER(C.c_uint64)]),
+    "asr_chunk_geometry": (C.c_int, [C.POINTER(AsrConfigC), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "asr_engine_create": (C.c_int, [C.POINTER(AsrConfigC), C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "asr_engine_destroy": (C.c_int, [C.c_void_p]),
+    "asr_session_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "asr_session_reset": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_session_close": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
+    "asr_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "asr_run_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "asr_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
+    "asr_sync": (C.c_int, [C.c_void_p]),
+    "asr_stream_handle": (C.c_void_p, [C.c_void_p]),
+    "asr_fbank": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "asr_fbank_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "asr_stage_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "asr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(AsrStatsC)]),
+    "asr_debug_step_partial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "asr_debug_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]),
+    "asr_debug_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "asr_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library(path: str = None) -> C.CDLL:
+    """dlopen libasr_b200.so and type every entry point.  Raises AsrLibraryError if it is missing or incomplete."""
+    global _lib
+    with _lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or os.environ.get("ASR_B200_LIB", LIB_PATH)
+        if not os.path.exists(p):
+            raise AsrLibraryError(
+                f"{p} not found: build it with `python -m asr_streaming_b200.build` (nvcc, sm_100a). "
+                "This package has no CPU fallback.")
+        try:
+            lib = C.CDLL(p)
+        except OSError as e:
+            raise AsrLibraryError(f"cannot load {p}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise AsrLibraryError(f"{p} does not export {name}; rebuild the library") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.asr_abi_version() != ABI_VERSION:
+            raise AsrLibraryError(f"ABI mismatch: library {lib.asr_abi_version()} vs binding {ABI_VERSION}")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def check(lib: C.CDLL, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.asr_last_error()
+        raise AsrLibraryError(f"{what} failed: {msg.decode('utf-8', 'replace') if msg else rc}")

@@ -1,0 +1,826 @@
+// Engine + C ABI (include/asr_b200.h): device-resident session state (K/V rings, greedy carry), weight
+// packing, the per-step kernel chain, and the host<->device staging of one ragged batch of stream-chunks.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <vector>
+
+#include "../../include/asr_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace asr {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n) {
+    bytes = n;
+    ASR_CUDA_OK(cudaMalloc(&p, n ? n : 16));
+    return 0;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct WeightMat {            // one nn.Linear weight as a tcgen05 B operand
+  bf16* w = nullptr;          // [N, ld]  (ld = K or 2K)
+  int N = 0, K = 0, ld = 0;
+  CUtensorMap tm[3];          // box rows 64 / 128 / 256
+};
+
+struct LayerW {
+  WeightMat qkv, o, w1, w2;
+  const float *bqkv, *bo, *ln_in_g, *ln_in_b, *ln_ff_g, *ln_ff_b, *b1, *b2, *ln_out_g, *ln_out_b;
+};
+
+struct FbankPlan {
+  int nc = 0, frame_len = 0, n_mels = 0;
+  DevBuf window, tw, w2, mel_start, mel_cnt, mel_off, mel_w;
+};
+
+struct Operand {              // a GEMM A operand buffer + its tensor map
+  DevBuf buf;
+  int rows = 0, K = 0, ld = 0, lo_off = 0;
+  CUtensorMap tm;
+};
+
+}  // namespace
+}  // namespace asr
+
+using namespace asr;
+
+struct AsrEngine {
+  AsrConfig cfg;
+  Geo geo;
+  int device = 0, num_sms = 148;
+  int simt_gemm = 0;
+  int staged_fmt = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+
+  DevBuf w_f32, w_bf16;
+  WeightMat w_in, ctc1, ctc2;
+  const float *ctc_b1 = nullptr, *ctc_b2 = nullptr;
+  std::vector<LayerW> layers;
+  FbankPlan mel128, kaldi80;
+
+  // per-step activations
+  DevBuf d_pcm, d_slots, x, x1, x2, q, rc_kv, logits, fb_f32;
+  Operand a_fb, a_ln, a_attn, a_h, a_enc, a_ctc;
+  // per-session state
+  DevBuf kv_cache, past_len, prev_id, n_frames, last_tok;
+  size_t slot_stride = 0;
+  std::vector<int> free_slots;
+  std::vector<uint8_t> slot_open;
+  // outputs
+  DevBuf d_argmax, d_newtok, d_nnew, d_blank, d_hastok, d_logprobs;
+  void* h_stage = nullptr;      // pinned: pcm + slots in, results out
+  size_t h_stage_bytes = 0;
+  size_t h_out_off = 0;
+
+  // stats
+  uint64_t steps = 0, stream_chunks = 0, launches = 0;
+  std::vector<float> step_ms;
+  size_t step_ms_pos = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ geometry
+int fill_geo(const AsrConfig& c, Geo* g) {
+  if (c.abi_version != ASR_B200_ABI_VERSION) { set_error("AsrConfig.abi_version %d != %d", c.abi_version, ASR_B200_ABI_VERSION); return -1; }
+  g->hop = c.hop; g->n_fft = c.n_fft; g->win = c.win; g->n_mels = c.n_mels;
+  g->chunk_len = (c.segment_size + c.context_size + c.bias) * c.hop;         // utils.py:18-22
+  g->frames = 1 + (g->chunk_len - c.n_fft) / c.hop;                          // torch.stft center=False
+  g->stride = c.stride; g->d_model = c.d_model; g->n_heads = c.n_heads; g->ffn = c.ffn_dim; g->n_layers = c.n_layers;
+  g->seg_rows = c.segment_size / c.stride; g->rc_rows = c.context_size / c.stride; g->rows = g->seg_rows + g->rc_rows;
+  g->left = c.left_context; g->ring = g->left + g->seg_rows;
+  g->ctc_hidden = c.ctc_hidden; g->vocab = c.vocab; g->split = c.precision == ASR_PRECISION_EXACT;
+  if (g->frames != g->rows * g->stride) { set_error("geometry: %d fbank frames != rows %d * stride %d (Emformer.infer size check)", g->frames, g->rows, g->stride); return -1; }
+  if (c.n_fft != 800 || c.win != 400 || (c.win & 1)) { set_error("fbank kernel is built for n_fft 800 / win 400"); return -1; }
+  if (c.d_model % c.stride || c.d_model != c.n_heads * 64) { set_error("d_model must be n_heads * 64 and divisible by stride"); return -1; }
+  if (c.n_mels % 64 || c.d_model % 64 || c.ffn_dim % 64 || c.ctc_hidden % 64) { set_error("GEMM K dims must be multiples of 64"); return -1; }
+  if (c.max_batch <= 0 || c.max_sessions <= 0) { set_error("max_batch / max_sessions must be positive"); return -1; }
+  return 0;
+}
+
+uint64_t weights_count(const Geo& g) {
+  const uint64_t d = g.d_model, f = g.ffn, din = d / g.stride;
+  uint64_t n = din * g.n_mels;
+  n += (uint64_t)g.n_layers * (3 * d * d + 3 * d + d * d + d + 4 * d + f * d + f + d * f + d + 2 * d);
+  n += (uint64_t)g.ctc_hidden * d + g.ctc_hidden + (uint64_t)g.vocab * g.ctc_hidden + g.vocab;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ fbank tables
+float linspace_f32(float start, float end, int steps, int i) {          // torch.linspace (fp32, symmetric evaluation)
+  const float step = (end - start) / (float)(steps - 1);
+  return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+
+int upload(DevBuf* b, const void* src, size_t bytes) {
+  if (b->alloc(bytes)) return -1;
+  ASR_CUDA_OK(cudaMemcpy(b->p, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int upload_sparse_mel(FbankPlan* pl, const std::vector<float>& fb /*[n_freqs][n_mels]*/, int n_freqs, int n_mels) {
+  std::vector<int> start(n_mels), cnt(n_mels), off(n_mels);
+  std::vector<float> w;
+  for (int m = 0; m < n_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < n_freqs; ++k)
+      if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    start[m] = lo < 0 ? 0 : lo; cnt[m] = lo < 0 ? 0 : hi - lo + 1; off[m] = (int)w.size();
+    for (int k = 0; k < cnt[m]; ++k) w.push_back(fb[(size_t)(start[m] + k) * n_mels + m]);
+  }
+  if (w.empty()) w.push_back(0.f);
+  pl->n_mels = n_mels;
+  return upload(&pl->mel_start, start.data(), 4 * n_mels) || upload(&pl->mel_cnt, cnt.data(), 4 * n_mels) ||
+         upload(&pl->mel_off, off.data(), 4 * n_mels) || upload(&pl->mel_w, w.data(), 4 * w.size());
+}
+
+int upload_twiddles(FbankPlan* pl, int nc) {
+  std::vector<float2> tw(nc), w2(nc + 2);
+  for (int i = 0; i < nc; ++i) { const double a = -2.0 * M_PI * i / nc; tw[i] = make_float2((float)cos(a), (float)sin(a)); }
+  for (int i = 0; i <= nc; ++i) { const double a = -2.0 * M_PI * i / (2.0 * nc); w2[i] = make_float2((float)cos(a), (float)sin(a)); }
+  w2[nc + 1] = make_float2(0.f, 0.f);
+  pl->nc = nc;
+  return upload(&pl->tw, tw.data(), sizeof(float2) * nc) || upload(&pl->w2, w2.data(), sizeof(float2) * (nc + 2));
+}
+
+// torchaudio.functional.melscale_fbanks(n_freqs, 0, sr/2, n_mels, sr, norm=None, mel_scale="htk")  (TA:functional.py:492-587)
+int build_melspec_plan(AsrEngine* e) {
+  const AsrConfig& c = e->cfg;
+  FbankPlan* pl = &e->mel128;
+  pl->frame_len = c.win;
+  std::vector<float> win(c.win);
+  for (int n = 0; n < c.win; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / c.win));        // hann periodic
+  const int n_freqs = c.n_fft / 2 + 1, n_mels = c.n_mels;
+  const float f_max = (float)(c.sample_rate / 2);
+  const double m_min = 2595.0 * log10(1.0 + 0.0 / 700.0), m_max = 2595.0 * log10(1.0 + (double)f_max / 700.0);
+  std::vector<float> f_pts(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    const float m = linspace_f32((float)m_min, (float)m_max, n_mels + 2, i);
+    f_pts[i] = 700.0f * (powf(10.0f, m / 2595.0f) - 1.0f);
+  }
+  std::vector<float> fb((size_t)n_freqs * n_mels);
+  for (int k = 0; k < n_freqs; ++k) {
+    const float fr = linspace_f32(0.f, f_max, n_freqs, k);
+    for (int m = 0; m < n_mels; ++m) {
+      const float down = (-1.0f * (f_pts[m] - fr)) / (f_pts[m + 1] - f_pts[m]);
+      const float up = (f_pts[m + 2] - fr) / (f_pts[m + 2] - f_pts[m + 1]);
+      fb[(size_t)k * n_mels + m] = fmaxf(0.f, fminf(down, up));
+    }
+  }
+  return upload(&pl->window, win.data(), 4 * c.win) || upload_twiddles(pl, c.n_fft / 2) || upload_sparse_mel(pl, fb, n_freqs, n_mels);
+}
+
+// torchaudio.compliance.kaldi.get_mel_banks / _feature_window_function (TA:compliance/kaldi.py:104-124, :374-449)
+int build_kaldi_plan(AsrEngine* e) {
+  FbankPlan* pl = &e->kaldi80;
+  const int frame_len = 400, padded = 512, n_mels = 80, n_bins = padded / 2;
+  pl->frame_len = frame_len;
+  std::vector<float> win(frame_len);
+  for (int n = 0; n < frame_len; ++n) win[n] = (float)pow(0.5 - 0.5 * cos(2.0 * M_PI * n / (frame_len - 1)), 0.85);   // povey
+  const float sr = (float)e->cfg.sample_rate, low = 20.f, high = 0.5f * sr;
+  const float bin_w = sr / (float)padded;
+  const float mel_low = 1127.0f * logf(1.0f + low / 700.0f), mel_high = 1127.0f * logf(1.0f + high / 700.0f);
+  const float delta = (mel_high - mel_low) / (float)(n_mels + 1);
+  std::vector<float> fb((size_t)(n_bins + 1) * n_mels, 0.f);
+  for (int m = 0; m < n_mels; ++m) {
+    const float left = mel_low + (float)m * delta, center = mel_low + (float)(m + 1) * delta, right = mel_low + (float)(m + 2) * delta;
+    for (int k = 0; k < n_bins; ++k) {
+      const float mel = 1127.0f * logf(1.0f + (bin_w * (float)k) / 700.0f);
+      const float up = (mel - left) / (center - left), down = (right - mel) / (right - center);
+      fb[(size_t)k * n_mels + m] = fmaxf(0.f, fminf(up, down));
+    }
+  }
+  return upload(&pl->window, win.data(), 4 * frame_len) || upload_twiddles(pl, padded / 2) || upload_sparse_mel(pl, fb, n_bins + 1, n_mels);
+}
+
+// ------------------------------------------------------------------------------------------ weights / operands
+int make_weight(AsrEngine* e, WeightMat* w, const float* src_f32_dev, bf16*& cursor, int N, int K) {
+  const int split = e->geo.split;
+  w->N = N; w->K = K; w->ld = split ? 2 * K : K;
+  w->w = cursor;
+  cursor += round_up((size_t)N * w->ld, 64);
+  if (convert_weight(src_f32_dev, w->w, N, K, w->ld, split ? K : 0, e->stream)) return -1;
+  const uint32_t boxes[3] = {64, 128, 256};
+  for (int i = 0; i < 3; ++i)
+    if (make_tmap_bf16_2d(&w->tm[i], w->w, (uint64_t)w->ld, (uint64_t)N, (uint64_t)w->ld, boxes[i])) return -1;
+  return 0;
+}
+
+int make_operand(AsrEngine* e, Operand* a, int rows, int K) {
+  const int split = e->geo.split;
+  a->rows = (int)round_up(rows, 128); a->K = K; a->ld = split ? 2 * K : K; a->lo_off = split ? K : 0;
+  if (a->buf.alloc((size_t)a->rows * a->ld * sizeof(bf16))) return -1;
+  ASR_CUDA_OK(cudaMemset(a->buf.p, 0, a->buf.bytes));
+  return make_tmap_bf16_2d(&a->tm, a->buf.p, (uint64_t)a->ld, (uint64_t)a->rows, (uint64_t)a->ld, 128);
+}
+
+int pick_bn(const AsrEngine* e, int M, int N) {
+  // Largest N tile that still gives every SM a tile; small problems (few streams) take the smallest tile so the
+  // chunk latency is spread over more SMs.  Ragged N (vocab 804) is fine: TMA zero-fills, the epilogue masks.
+  const int mt = (M + 127) / 128;
+  int last = 64;
+  for (int bn : {256, 128, 64}) {
+    if (bn > 64 && bn / 2 >= N) continue;
+    last = bn;
+    if (mt * ((N + bn - 1) / bn) >= e->num_sms) return bn;
+  }
+  return last;
+}
+
+template <class Epi>
+int run_gemm(AsrEngine* e, const Operand& a, const WeightMat& w, int M, const Epi& epi) {
+  const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
+  ++e->launches;
+  if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
+  const int bn = pick_bn(e, M, w.N);
+  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
+}
+
+// ------------------------------------------------------------------------------------------ the per-step kernel chain
+template <typename T>
+int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
+  const Geo& g = e->geo;
+  const int M = n * g.rows, d = g.d_model;
+  const int* slots = e->d_slots.as<int>();
+  for (int l = 0; l < n_layers_to_run; ++l) {
+    const LayerW& L = e->layers[l];
+    T* cache_layer = e->kv_cache.as<T>() + (size_t)l * 2 * g.ring * d;
+    EpiQKV<T> eq;
+    eq.q = e->q.as<float>(); eq.cache_layer = cache_layer; eq.slot_stride = e->slot_stride; eq.rc = e->rc_kv.as<T>();
+    eq.bias = L.bqkv; eq.slots = slots; eq.past_len = e->past_len.as<int>();
+    eq.rows = g.rows; eq.seg_rows = g.seg_rows; eq.rc_rows = g.rc_rows; eq.ring = g.ring; eq.d = d;
+    eq.qscale = 1.0f / sqrtf((float)(d / g.n_heads));                                   // TA:emformer.py:108
+    if (run_gemm(e, e->a_ln, L.qkv, M, eq)) return -1;
+
+    AttnParams<T> ap;
+    ap.q = e->q.as<float>(); ap.cache_layer = cache_layer; ap.slot_stride = e->slot_stride; ap.rc = e->rc_kv.as<T>();
+    ap.slots = slots; ap.past_len = e->past_len.as<int>(); ap.out = e->a_attn.buf.as<bf16>(); ap.ld = e->a_attn.ld; ap.lo_off = e->a_attn.lo_off;
+    ap.rows = g.rows; ap.seg_rows = g.seg_rows; ap.rc_rows = g.rc_rows; ap.ring = g.ring; ap.left = g.left; ap.d = d; ap.n_heads = g.n_heads;
+    ++e->launches;
+    if (attention_launch<T>(ap, n, e->stream)) return -1;
+
+    EpiF32 eo{e->x1.as<float>(), L.bo, e->x.as<float>(), d, d};                          // out_proj + residual (pre-LN input)
+    if (run_gemm(e, e->a_attn, L.o, M, eo)) return -1;
+    ++e->launches;
+    if (ln_to_operand(e->x1.as<float>(), L.ln_ff_g, L.ln_ff_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, d, e->stream)) return -1;
+    EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
+    if (run_gemm(e, e->a_ln, L.w1, M, e1)) return -1;
+    EpiF32 e2{e->x2.as<float>(), L.b2, e->x1.as<float>(), d, d};
+    if (run_gemm(e, e->a_h, L.w2, M, e2)) return -1;
+    ++e->launches;
+    const bool last = l == g.n_layers - 1;
+    if (last) {
+      if (ln_out_fused(e->x2.as<float>(), L.ln_out_g, L.ln_out_b, e->x.as<float>(), nullptr, nullptr, e->a_enc.buf.as<bf16>(), e->a_enc.ld,
+                       e->a_enc.lo_off, M, d, g.rows, g.seg_rows, e->stream)) return -1;
+    } else {
+      const LayerW& Nx = e->layers[l + 1];
+      if (ln_out_fused(e->x2.as<float>(), L.ln_out_g, L.ln_out_b, e->x.as<float>(), Nx.ln_in_g, Nx.ln_in_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld,
+                       e->a_ln.lo_off, M, d, g.rows, g.seg_rows, e->stream)) return -1;
+    }
+  }
+  return 0;
+}
+
+int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool to_operand) {
+  const Geo& g = e->geo;
+  const FbankPlan& pl = e->mel128;
+  FbankParams P;
+  memset(&P, 0, sizeof(P));
+  P.pcm = e->d_pcm.p; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
+  P.n_frames = g.frames; P.hop = g.hop; P.frame_len = g.win; P.frame_off = (g.n_fft - g.win) / 2; P.nc = pl.nc; P.kaldi = 0;
+  P.in_scale = P.pcm_is_f32 ? 1.0f : 1.0f / 32768.0f;                                  // streaming_server.py:362-363
+  P.preemph = 0.f; P.log_floor = 1e-5f;                                                // audio.py:25 clamp(1e-5)
+  P.window = pl.window.as<float>(); P.tw = pl.tw.as<float2>(); P.w2 = pl.w2.as<float2>();
+  P.mel_start = pl.mel_start.as<int>(); P.mel_cnt = pl.mel_cnt.as<int>(); P.mel_off = pl.mel_off.as<int>(); P.mel_w = pl.mel_w.as<float>();
+  P.n_mels = g.n_mels; P.out_f32 = out_f32;
+  P.out_op = to_operand ? e->a_fb.buf.as<bf16>() : nullptr; P.op_ld = e->a_fb.ld; P.op_lo_off = e->a_fb.lo_off;
+  ++e->launches;
+  return fbank_launch(P, n, e->stream);
+}
+
+int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool with_ctc, bool want_logprobs) {
+  const Geo& g = e->geo;
+  if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
+  // input_linear (encoder.py:142, no bias); its [n*frames, d/stride] output *is* the time-reduced [n*rows, d] (common.py:118-119)
+  EpiF32 ein{e->x.as<float>(), nullptr, nullptr, g.d_model / g.stride, g.d_model / g.stride};
+  if (run_gemm(e, e->a_fb, e->w_in, n * g.frames, ein)) return -1;
+  const int M = n * g.rows;
+  ++e->launches;
+  if (ln_to_operand(e->x.as<float>(), e->layers[0].ln_in_g, e->layers[0].ln_in_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, g.d_model,
+                    e->stream)) return -1;
+  if (g.split ? run_layers<float>(e, n, n_layers_to_run) : run_layers<bf16>(e, n, n_layers_to_run)) return -1;
+  if (!with_ctc) return 0;
+  const int Mc = n * g.seg_rows;
+  EpiOperand ec1{e->a_ctc.buf.as<bf16>(), e->ctc_b1, e->a_ctc.ld, e->a_ctc.lo_off, ACT_SILU};    // decoder.py:67
+  if (run_gemm(e, e->a_enc, e->ctc1, Mc, ec1)) return -1;
+  EpiF32 ec2{e->logits.as<float>(), e->ctc_b2, nullptr, g.vocab, g.vocab};                        // decoder.py:68
+  if (run_gemm(e, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
+  CtcParams cp;
+  cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->d_slots.as<int>();
+  cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
+  cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
+  cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>();
+  cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
+  ++e->launches;
+  return ctc_greedy_launch(cp, n, e->stream);
+}
+
+int check_step_args(AsrEngine* e, int n, const int32_t* slots) {
+  if (!e) { set_error("null engine"); return -1; }
+  if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch = %d]", n, e->cfg.max_batch); return -1; }
+  if (n && !slots) { set_error("null slots"); return -1; }
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_sessions || !e->slot_open[slots[i]]) { set_error("slot %d (index %d) is not an open session", slots[i], i); return -1; }
+  return 0;
+}
+
+size_t pcm_bytes(const AsrEngine* e, int n, int fmt) { return (size_t)n * e->geo.chunk_len * (fmt == ASR_PCM_F32 ? 4 : 2); }
+
+int stage_inputs(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int fmt) {
+  if (check_step_args(e, n, slots)) return -1;
+  if (n && !pcm) { set_error("null pcm"); return -1; }
+  if (fmt != ASR_PCM_I16 && fmt != ASR_PCM_F32) { set_error("bad pcm_format %d", fmt); return -1; }
+  if (!n) return 0;
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  const size_t pb = pcm_bytes(e, n, fmt);
+  uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_stage);
+  memcpy(hs, pcm, pb);
+  memcpy(hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), slots, 4 * (size_t)n);
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, hs, pb, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_slots.p, hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+int fetch_outputs(AsrEngine* e, int n, const AsrStepOut* out, bool sync_only) {
+  const Geo& g = e->geo;
+  uint8_t* ho = reinterpret_cast<uint8_t*>(e->h_stage) + e->h_out_off;
+  const size_t nS = (size_t)n * g.seg_rows;
+  size_t off = 0;
+  struct Item { void* dst; const void* src; size_t bytes; size_t hoff; };
+  std::vector<Item> items;
+  auto add = [&](void* dst, const DevBuf& src, size_t bytes) {
+    if (dst && bytes) { items.push_back({dst, src.p, bytes, off}); off += round_up(bytes, 256); }
+  };
+  if (out && !sync_only && n) {
+    add(out->argmax_ids, e->d_argmax, 4 * nS);
+    add(out->new_tokens, e->d_newtok, 4 * nS);
+    add(out->n_new, e->d_nnew, 4 * (size_t)n);
+    add(out->blank_frames, e->d_blank, 4 * (size_t)n);
+    add(out->has_token, e->d_hastok, 4 * (size_t)n);
+    add(out->logprobs, e->d_logprobs, 4 * nS * g.vocab);
+  }
+  for (auto& it : items) ASR_CUDA_OK(cudaMemcpyAsync(ho + it.hoff, it.src, it.bytes, cudaMemcpyDeviceToHost, e->stream));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (auto& it : items) memcpy(it.dst, ho + it.hoff, it.bytes);
+  return 0;
+}
+
+void record_step(AsrEngine* e, int n, double ms) {
+  ++e->steps; e->stream_chunks += n;
+  if (e->step_ms.size() < 4096) e->step_ms.push_back((float)ms);
+  else { e->step_ms[e->step_ms_pos] = (float)ms; e->step_ms_pos = (e->step_ms_pos + 1) % 4096; }
+}
+
+int reset_slot(AsrEngine* e, int slot) {
+  const int zero = 0, neg = -1;
+  ASR_CUDA_OK(cudaMemcpyAsync(e->past_len.as<int>() + slot, &zero, 4, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaMemcpyAsync(e->n_frames.as<int>() + slot, &zero, 4, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaMemcpyAsync(e->prev_id.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaMemcpyAsync(e->last_tok.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));     // the 4-byte host sources are stack variables
+  return 0;
+}
+
+void destroy_engine(AsrEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->d_pcm, &e->d_slots, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
+                    &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
+                    &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs};
+  for (DevBuf* b : bufs) b->free();
+  for (FbankPlan* pl : {&e->mel128, &e->kaldi80}) {
+    pl->window.free(); pl->tw.free(); pl->w2.free(); pl->mel_start.free(); pl->mel_cnt.free(); pl->mel_off.free(); pl->mel_w.free();
+  }
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats, int device, AsrEngine** out) {
+  if (!cfg || !weights || !out) { set_error("null argument"); return -1; }
+  Geo g;
+  if (fill_geo(*cfg, &g)) return -1;
+  if (weights_count(g) != n_floats) { set_error("weights blob has %llu floats, config needs %llu", (unsigned long long)n_floats, (unsigned long long)weights_count(g)); return -1; }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { set_error("no CUDA device: the B200 path has no CPU fallback"); return -1; }
+  if (device < 0 || device >= n_dev) { set_error("device %d out of range (%d devices)", device, n_dev); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return -1; }
+
+  AsrEngine* e = new AsrEngine();
+  e->cfg = *cfg; e->geo = g; e->device = device; e->num_sms = prop.multiProcessorCount;
+  const char* dbg = getenv("ASR_B200_DEBUG_SIMT_GEMM");
+  e->simt_gemm = dbg && dbg[0] == '1';
+  int rc = -1;
+  do {
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); break; }
+    if (e->w_f32.alloc(n_floats * 4)) break;
+    if (cudaMemcpy(e->w_f32.p, weights, n_floats * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("weights H2D failed"); break; }
+    // ---- carve the fp32 blob and convert the matrices to bf16 (hi|lo) B operands
+    const int d = g.d_model, f = g.ffn, din = d / g.stride, kmul = g.split ? 2 : 1;
+    size_t bf_elems = round_up((size_t)din * g.n_mels * kmul, 64);
+    bf_elems += (size_t)g.n_layers * (round_up((size_t)3 * d * d * kmul, 64) + round_up((size_t)d * d * kmul, 64) + 2 * round_up((size_t)f * d * kmul, 64));
+    bf_elems += round_up((size_t)g.ctc_hidden * d * kmul, 64) + round_up((size_t)g.vocab * g.ctc_hidden * kmul, 64);
+    if (e->w_bf16.alloc(bf_elems * sizeof(bf16))) break;
+    bf16* cur = e->w_bf16.as<bf16>();
+    const float* wp = e->w_f32.as<float>();
+    auto take = [&](size_t n) { const float* p = wp; wp += n; return p; };
+    bool ok = true;
+    ok = ok && !make_weight(e, &e->w_in, take((size_t)din * g.n_mels), cur, din, g.n_mels);
+    e->layers.resize(g.n_layers);
+    for (int l = 0; l < g.n_layers && ok; ++l) {
+      LayerW& L = e->layers[l];
+      ok = ok && !make_weight(e, &L.qkv, take((size_t)3 * d * d), cur, 3 * d, d);
+      L.bqkv = take(3 * d);
+      ok = ok && !make_weight(e, &L.o, take((size_t)d * d), cur, d, d);
+      L.bo = take(d);
+      L.ln_in_g = take(d); L.ln_in_b = take(d); L.ln_ff_g = take(d); L.ln_ff_b = take(d);
+      ok = ok && !make_weight(e, &L.w1, take((size_t)f * d), cur, f, d);
+      L.b1 = take(f);
+      ok = ok && !make_weight(e, &L.w2, take((size_t)d * f), cur, d, f);
+      L.b2 = take(d);
+      L.ln_out_g = take(d); L.ln_out_b = take(d);
+    }
+    ok = ok && !make_weight(e, &e->ctc1, take((size_t)g.ctc_hidden * d), cur, g.ctc_hidden, d);
+    e->ctc_b1 = take(g.ctc_hidden);
+    ok = ok && !make_weight(e, &e->ctc2, take((size_t)g.vocab * g.ctc_hidden), cur, g.vocab, g.ctc_hidden);
+    e->ctc_b2 = take(g.vocab);
+    if (!ok) break;
+    if (build_melspec_plan(e) || build_kaldi_plan(e)) break;
+
+    // ---- activations
+    const int B = cfg->max_batch, M = B * g.rows, Mc = B * g.seg_rows;
+    const size_t esz = g.split ? 4 : 2;
+    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
+        e->x2.alloc(4 * (size_t)M * d) || e->q.alloc(4 * (size_t)M * d) || e->rc_kv.alloc(esz * (size_t)B * 2 * g.rc_rows * d) ||
+        e->logits.alloc(4 * (size_t)Mc * g.vocab) || e->d_logprobs.alloc(4 * (size_t)Mc * g.vocab) || e->d_argmax.alloc(4 * (size_t)Mc) ||
+        e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B)) break;
+    if (make_operand(e, &e->a_fb, B * g.frames, g.n_mels) || make_operand(e, &e->a_ln, M, d) || make_operand(e, &e->a_attn, M, d) ||
+        make_operand(e, &e->a_h, M, f) || make_operand(e, &e->a_enc, Mc, d) || make_operand(e, &e->a_ctc, Mc, g.ctc_hidden)) break;
+    // ---- sessions
+    e->slot_stride = (size_t)g.n_layers * 2 * g.ring * d;
+    const size_t S = cfg->max_sessions;
+    if (e->kv_cache.alloc(esz * S * e->slot_stride) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S)) break;
+    if (cudaMemsetAsync(e->kv_cache.p, 0, e->kv_cache.bytes, e->stream) != cudaSuccess) { set_error("memset failed"); break; }
+    if (fill_i32(e->past_len.as<int>(), 0, S, e->stream) || fill_i32(e->n_frames.as<int>(), 0, S, e->stream) ||
+        fill_i32(e->prev_id.as<int>(), -1, S, e->stream) || fill_i32(e->last_tok.as<int>(), -1, S, e->stream)) break;
+    e->slot_open.assign(S, 0);
+    e->free_slots.resize(S);
+    for (size_t i = 0; i < S; ++i) e->free_slots[i] = (int)(S - 1 - i);
+    // ---- pinned staging: [pcm (f32 worst case) | slots | outputs]
+    const size_t in_bytes = round_up(pcm_bytes(e, B, ASR_PCM_F32), 256) + round_up(4 * (size_t)B, 256);
+    const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 3 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256);
+    e->h_out_off = in_bytes; e->h_stage_bytes = in_bytes + out_bytes;
+    if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", e->h_stage_bytes); break; }
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("engine init: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    rc = 0;
+  } while (0);
+  if (rc) { destroy_engine(e); return -1; }
+  *out = e;
+  return 0;
+}
+
+int run_fbank_kind(AsrEngine* e, int kind, int n, int fmt, int n_samples, int subtract_mean, float* d_out, int* n_frames_out) {
+  const Geo& g = e->geo;
+  if (kind == ASR_FBANK_MELSPEC128) {
+    if (n_samples != g.chunk_len) { set_error("melspec128 takes chunk_length = %d samples per stream", g.chunk_len); return -1; }
+    *n_frames_out = g.frames;
+    return run_fbank_melspec(e, n, fmt, d_out, false);
+  }
+  if (kind != ASR_FBANK_KALDI80) { set_error("unknown fbank kind %d", kind); return -1; }
+  const FbankPlan& pl = e->kaldi80;
+  if (n_samples < 400 || (size_t)n * n_samples * (fmt == ASR_PCM_F32 ? 4 : 2) > e->d_pcm.bytes || ((size_t)n_samples * (fmt == ASR_PCM_F32 ? 4 : 2)) % 16) {
+    set_error("kaldi80: n_samples %d unsupported (>= 400, 16-byte multiple, fits the staging buffer)", n_samples); return -1;
+  }
+  FbankParams P;
+  memset(&P, 0, sizeof(P));
+  P.pcm = e->d_pcm.p; P.pcm_is_f32 = fmt == ASR_PCM_F32; P.pcm_stride = n_samples; P.n_samples = n_samples;
+  P.n_frames = 1 + (n_samples - 400) / 160; P.hop = 160; P.frame_len = 400; P.frame_off = 0; P.nc = pl.nc; P.kaldi = 1;
+  P.in_scale = 1.0f; P.preemph = 0.97f; P.log_floor = 1.1920928955078125e-07f;
+  P.window = pl.window.as<float>(); P.tw = pl.tw.as<float2>(); P.w2 = pl.w2.as<float2>();
+  P.mel_start = pl.mel_start.as<int>(); P.mel_cnt = pl.mel_cnt.as<int>(); P.mel_off = pl.mel_off.as<int>(); P.mel_w = pl.mel_w.as<float>();
+  P.n_mels = pl.n_mels; P.out_f32 = d_out; P.out_op = nullptr;
+  *n_frames_out = P.n_frames;
+  if ((size_t)n * P.n_frames * P.n_mels * 4 > e->fb_f32.bytes) { set_error("kaldi80: output exceeds the feature buffer"); return -1; }
+  ++e->launches;
+  if (fbank_launch(P, n, e->stream)) return -1;
+  if (subtract_mean) {
+    ++e->launches;
+    if (subtract_mean_launch(d_out, n, P.n_frames, P.n_mels, e->stream)) return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* asr_last_error(void) { return g_err; }
+int asr_abi_version(void) { return ASR_B200_ABI_VERSION; }
+
+int asr_default_config(AsrConfig* c, int low_latency) {
+  if (!c) { set_error("null config"); return -1; }
+  memset(c, 0, sizeof(*c));
+  c->abi_version = ASR_B200_ABI_VERSION;
+  c->sample_rate = 16000; c->hop = 160; c->n_fft = 800; c->win = 400; c->n_mels = 128;
+  c->segment_size = low_latency ? 32 : 64; c->context_size = 16; c->bias = 4; c->stride = 4;
+  c->d_model = 512; c->n_heads = 8; c->ffn_dim = 2048; c->n_layers = 20; c->left_context = 32; c->ctc_hidden = 512; c->vocab = 804;
+  c->precision = ASR_PRECISION_FAST; c->max_sessions = 1024; c->max_batch = 256;
+  return 0;
+}
+
+int asr_weights_count(const AsrConfig* cfg, uint64_t* n) {
+  Geo g;
+  if (!cfg || !n) { set_error("null argument"); return -1; }
+  AsrConfig c = *cfg;
+  if (c.max_batch <= 0) c.max_batch = 1;
+  if (c.max_sessions <= 0) c.max_sessions = 1;
+  if (fill_geo(c, &g)) return -1;
+  *n = weights_count(g);
+  return 0;
+}
+
+int asr_chunk_geometry(const AsrConfig* cfg, int32_t* chunk_length, int32_t* segment_length, int32_t* seg_rows) {
+  Geo g;
+  if (!cfg) { set_error("null config"); return -1; }
+  AsrConfig c = *cfg;
+  if (c.max_batch <= 0) c.max_batch = 1;
+  if (c.max_sessions <= 0) c.max_sessions = 1;
+  if (fill_geo(c, &g)) return -1;
+  if (chunk_length) *chunk_length = g.chunk_len;
+  if (segment_length) *segment_length = cfg->segment_size * cfg->hop;
+  if (seg_rows) *seg_rows = g.seg_rows;
+  return 0;
+}
+
+int asr_engine_create(const AsrConfig* cfg, const float* weights, uint64_t n_floats, int device, AsrEngine** out) {
+  try { return create_engine(cfg, weights, n_floats, device, out); } catch (const std::exception& ex) { set_error("engine create: %s", ex.what()); return -1; }
+}
+
+int asr_engine_destroy(AsrEngine* e) { destroy_engine(e); return 0; }
+
+int asr_session_open(AsrEngine* e, int32_t* slot_out) {
+  if (!e || !slot_out) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->free_slots.empty()) { set_error("no free session slot (max_sessions = %d)", e->cfg.max_sessions); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  const int s = e->free_slots.back();
+  if (reset_slot(e, s)) return -1;
+  e->free_slots.pop_back();
+  e->slot_open[s] = 1;
+  *slot_out = s;
+  return 0;
+}
+
+int asr_session_reset(AsrEngine* e, int32_t slot) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (slot < 0 || slot >= e->cfg.max_sessions || !e->slot_open[slot]) { set_error("slot %d is not an open session", slot); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  return reset_slot(e, slot);
+}
+
+int asr_session_close(AsrEngine* e, int32_t slot) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (slot < 0 || slot >= e->cfg.max_sessions || !e->slot_open[slot]) { set_error("slot %d is not an open session", slot); return -1; }
+  e->slot_open[slot] = 0;
+  e->free_slots.push_back(slot);
+  return 0;
+}
+
+int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t fmt, const AsrStepOut* out) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (stage_inputs(e, n, slots, pcm, fmt)) return -1;
+  if (n == 0) return 0;
+  if (run_pipeline(e, n, fmt, e->geo.n_layers, true, out && out->logprobs)) return -1;
+  if (fetch_outputs(e, n, out, false)) return -1;
+  record_step(e, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
+}
+
+int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t fmt) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->staged_fmt = fmt;
+  return stage_inputs(e, n, slots, pcm, fmt);
+}
+
+int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n <= 0 || n > e->cfg.max_batch) { set_error("n = %d outside (0, max_batch]", n); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  if (run_pipeline(e, n, e->staged_fmt, e->geo.n_layers, true, want_logprobs != 0)) return -1;
+  ++e->steps; e->stream_chunks += n;
+  return 0;
+}
+
+int asr_fetch(AsrEngine* e, int32_t n, const AsrStepOut* out) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  return fetch_outputs(e, n, out, false);
+}
+
+int asr_sync(AsrEngine* e) {
+  if (!e) { set_error("null engine"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void* asr_stream_handle(AsrEngine* e) { return e ? (void*)e->stream : nullptr; }
+
+int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes) {
+  if (!e || !pcm) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (bytes > e->d_pcm.bytes) { set_error("asr_stage_raw: %llu bytes > staging capacity %zu", (unsigned long long)bytes, e->d_pcm.bytes); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  memcpy(e->h_stage, pcm, bytes);
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, e->h_stage, bytes, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+static int ensure_fb_buffer(AsrEngine* e, size_t bytes) {
+  if (e->fb_f32.bytes >= bytes && e->fb_f32.p) return 0;
+  e->fb_f32.free();
+  return e->fb_f32.alloc(bytes);
+}
+
+int asr_fbank_staged(AsrEngine* e, int32_t kind, int32_t n, int32_t fmt, int32_t n_samples) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  const int frames = kind == ASR_FBANK_MELSPEC128 ? e->geo.frames : 1 + (n_samples - 400) / 160;
+  const int mels = kind == ASR_FBANK_MELSPEC128 ? e->geo.n_mels : 80;
+  if (n <= 0 || frames <= 0) { set_error("asr_fbank_staged: bad sizes"); return -1; }
+  if (ensure_fb_buffer(e, (size_t)n * frames * mels * 4)) return -1;
+  int nf = 0;
+  return run_fbank_kind(e, kind, n, fmt, n_samples, 0, e->fb_f32.as<float>(), &nf);
+}
+
+int asr_fbank(AsrEngine* e, int32_t kind, int32_t n, const void* pcm, int32_t fmt, int32_t n_samples, int32_t subtract_mean, float* out) {
+  if (!e || !pcm || !out) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n <= 0) return 0;
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  const size_t in_bytes = (size_t)n * n_samples * (fmt == ASR_PCM_F32 ? 4 : 2);
+  if (in_bytes > e->d_pcm.bytes) { set_error("asr_fbank: input of %zu bytes exceeds staging capacity %zu (raise max_batch)", in_bytes, e->d_pcm.bytes); return -1; }
+  const int frames = kind == ASR_FBANK_MELSPEC128 ? e->geo.frames : 1 + (n_samples - 400) / 160;
+  const int mels = kind == ASR_FBANK_MELSPEC128 ? e->geo.n_mels : 80;
+  if (frames <= 0) { set_error("asr_fbank: too few samples"); return -1; }
+  const size_t out_bytes = (size_t)n * frames * mels * 4;
+  if (ensure_fb_buffer(e, out_bytes)) return -1;
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, pcm, in_bytes, cudaMemcpyHostToDevice, e->stream));
+  int nf = 0;
+  if (run_fbank_kind(e, kind, n, fmt, n_samples, subtract_mean, e->fb_f32.as<float>(), &nf)) return -1;
+  ASR_CUDA_OK(cudaMemcpyAsync(out, e->fb_f32.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int asr_get_stats(AsrEngine* e, AsrStats* out) {
+  if (!e || !out) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  memset(out, 0, sizeof(*out));
+  out->steps = e->steps; out->stream_chunks = e->stream_chunks; out->kernel_launches = e->launches;
+  if (!e->step_ms.empty()) {
+    std::vector<float> v = e->step_ms;
+    std::sort(v.begin(), v.end());
+    double s = 0; for (float x : v) s += x;
+    out->step_ms_mean = s / v.size();
+    out->step_ms_p50 = v[v.size() / 2];
+    out->step_ms_p99 = v[std::min(v.size() - 1, (size_t)(0.99 * v.size()))];
+    out->step_ms_max = v.back();
+  }
+  return 0;
+}
+
+int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t fmt, int32_t n_layers) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n_layers < 0 || n_layers > e->geo.n_layers) { set_error("n_layers out of range"); return -1; }
+  if (stage_inputs(e, n, slots, pcm, fmt)) return -1;
+  if (n == 0) return 0;
+  if (run_pipeline(e, n, fmt, n_layers, false, false)) return -1;
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int asr_debug_read(AsrEngine* e, int32_t which, float* out, uint64_t n_floats) {
+  if (!e || !out) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  const DevBuf* src = which == 0 ? &e->x : which == 1 ? &e->x1 : which == 2 ? &e->x2 : which == 3 ? &e->q : which == 4 ? &e->logits : nullptr;
+  if (!src || n_floats * 4 > src->bytes) { set_error("asr_debug_read: bad buffer id %d or size", which); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  ASR_CUDA_OK(cudaMemcpy(out, src->p, n_floats * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int32_t which, float* out, int32_t* past_length) {
+  if (!e || !out) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  const Geo& g = e->geo;
+  if (slot < 0 || slot >= e->cfg.max_sessions || layer < 0 || layer >= g.n_layers || (which != 0 && which != 1)) { set_error("asr_debug_read_state: bad index"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  int pl = 0;
+  ASR_CUDA_OK(cudaMemcpy(&pl, e->past_len.as<int>() + slot, 4, cudaMemcpyDeviceToHost));
+  if (past_length) *past_length = pl;
+  const size_t esz = g.split ? 4 : 2, d = g.d_model;
+  std::vector<uint8_t> ring((size_t)g.ring * d * esz);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(e->kv_cache.p) + ((size_t)slot * e->slot_stride + ((size_t)layer * 2 + which) * g.ring * d) * esz;
+  ASR_CUDA_OK(cudaMemcpy(ring.data(), base, ring.size(), cudaMemcpyDeviceToHost));
+  const int lv = std::min(pl, g.left);
+  memset(out, 0, sizeof(float) * g.left * d);
+  for (int i = 0; i < lv; ++i) {                       // reference layout: right-aligned, oldest first (TA:emformer.py:395-396)
+    const int rr = ((pl - lv + i) % g.ring + g.ring) % g.ring;
+    float* o = out + (size_t)(g.left - lv + i) * d;
+    if (g.split) memcpy(o, ring.data() + (size_t)rr * d * 4, d * 4);
+    else {
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(ring.data()) + (size_t)rr * d;
+      for (size_t c = 0; c < d; ++c) { uint32_t u = (uint32_t)h[c] << 16; memcpy(o + c, &u, 4); }
+    }
+  }
+  return 0;
+}
+
+int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, const float* A, const float* B, const float* bias,
+                   float* C, int device) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || K % 64) { set_error("asr_debug_gemm: bad arguments"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int ld = split ? 2 * K : K, lo = split ? K : 0;
+  const int Mp = (int)round_up(M, 128);
+  DevBuf dA32, dB32, dA, dB, dC, dbias;
+  int rc = -1;
+  do {
+    if (dA32.alloc(4 * (size_t)M * K) || dB32.alloc(4 * (size_t)N * K) || dA.alloc(2 * (size_t)Mp * ld) || dB.alloc(2 * (size_t)N * ld) ||
+        dC.alloc(4 * (size_t)M * N) || dbias.alloc(4 * (size_t)N)) break;
+    if (cudaMemcpy(dA32.p, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dB32.p, B, 4 * (size_t)N * K, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); break; }
+    if (bias && cudaMemcpy(dbias.p, bias, 4 * (size_t)N, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); break; }
+    cudaMemset(dA.p, 0, dA.bytes);
+    if (convert_weight(dA32.as<float>(), dA.as<bf16>(), M, K, ld, lo, 0) || convert_weight(dB32.as<float>(), dB.as<bf16>(), N, K, ld, lo, 0)) break;
+    const GemmProblem p = make_problem(M, N, K, split);
+    EpiF32 epi{dC.as<float>(), bias ? dbias.as<float>() : nullptr, nullptr, N, N};
+    if (impl == 1) {
+      if (gemm_simt<EpiF32>(dA.as<bf16>(), ld, dB.as<bf16>(), ld, p, epi, 0)) break;
+    } else {
+      CUtensorMap ta, tb;
+      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn)) break;
+      if (gemm_tc<EpiF32>(ta, tb, p, epi, bn, prop.multiProcessorCount, 0)) break;
+    }
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { set_error("asr_debug_gemm: kernel failed: %s", cudaGetErrorString(err)); break; }
+    if (cudaMemcpy(C, dC.p, 4 * (size_t)M * N, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); break; }
+    rc = 0;
+  } while (0);
+  dA32.free(); dB32.free(); dA.free(); dB.free(); dC.free(); dbias.free();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Launch interfaces of the memory-bound kernels (fbank, LayerNorm, chunk attention, CTC decode).
+#pragma once
+#include "common.cuh"
+
+namespace asr {
+
+// ---------------------------------------------------------------- fbank
+struct FbankParams {
+  const void* pcm;        // [n_streams, pcm_stride] int16 or float
+  int pcm_is_f32;
+  int pcm_stride;         // samples between consecutive streams
+  int n_samples;          // samples staged per stream
+  int n_frames, hop, frame_len, frame_off;
+  int nc;                 // complex FFT size: 400 (800-pt real) or 256 (512-pt real)
+  int kaldi;              // remove-DC + pre-emphasis path
+  float in_scale;         // 1/32768 for int16 -> [-1,1) (streaming_server.py:362-363), 1 otherwise
+  float preemph;
+  float log_floor;
+  const float* window;    // [frame_len]
+  const float2* tw;       // [nc]      exp(-2*pi*i*m/nc)
+  const float2* w2;       // [nc+1]    exp(-2*pi*i*k/(2*nc))
+  const int* mel_start;   // [n_mels]
+  const int* mel_cnt;     // [n_mels]
+  const int* mel_off;     // [n_mels]
+  const float* mel_w;     // packed triangle weights
+  int n_mels;
+  float* out_f32;         // nullable [n_streams, n_frames, n_mels]
+  bf16* out_op;           // nullable A operand [n_streams*n_frames, op_ld]
+  int op_ld, op_lo_off;
+};
+int fbank_launch(const FbankParams& P, int n_streams, cudaStream_t st);
+
+// ---------------------------------------------------------------- LayerNorm (d = 512)
+// y = LN(x; g, b)  ->  A operand (bf16 hi [+lo])                         (TA:emformer.py:427-434, pos_ff[0])
+int ln_to_operand(const float* x, const float* g, const float* b, bf16* out, int ld, int lo_off, int M, int d, cudaStream_t st);
+// y = LN(x2; g1, b1) -> fp32 y ; then (g2 != null) LN(y; g2, b2) -> A operand           (layer_norm_output + next layer_norm_input)
+// or (g2 == null) the segment rows of y -> compact A operand [B*seg_rows, ld]           (TA:emformer.py:803 drops rc rows)
+int ln_out_fused(const float* x2, const float* g1, const float* b1, float* y, const float* g2, const float* b2, bf16* out, int ld,
+                 int lo_off, int M, int d, int rows, int seg_rows, cudaStream_t st);
+
+// ---------------------------------------------------------------- chunk attention over the ring KV cache
+template <typename T>
+struct AttnParams {
+  const float* q;          // [M, d], already scaled
+  const T* cache_layer;    // cache + layer*(2*ring*d)
+  size_t slot_stride;
+  const T* rc;             // [B, 2, rc_rows, d]
+  const int* slots;        // [B]
+  const int* past_len;     // [n_slots]  (value before this step)
+  bf16* out;               // A operand [M, ld]
+  int ld, lo_off;
+  int rows, seg_rows, rc_rows, ring, left, d, n_heads;
+};
+template <typename T> int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st);
+
+// ---------------------------------------------------------------- CTC log-softmax + argmax + incremental greedy
+struct CtcParams {
+  const float* logits;     // [B*seg_rows, vocab]
+  int vocab, seg_rows;
+  const int* slots;        // [B]
+  // per-slot carry of greedy_search's unique_consecutive / last_blank across chunks (recognition.py:33-57)
+  int* prev_id;            // last argmax id of the segment so far (-1: none)
+  int* n_frames;           // frames accumulated in the current utterance segment
+  int* last_tok_frame;     // index of last frame with id > 1 (-1: none)
+  int* past_len;           // advanced by seg_rows here (end of step)
+  // outputs per stream
+  int* argmax_ids;         // [B*seg_rows]
+  int* new_tokens;         // [B*seg_rows] collapsed, blank-dropped ids appended this chunk
+  int* n_new;              // [B]
+  int* blank_frames;       // [B]  frames since last token (or all frames if none)
+  int* has_token;          // [B]
+  float* logprobs;         // nullable [B*seg_rows, vocab]
+};
+int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st);
+
+// fp32 [n] -> bf16 hi (+ lo) weight conversion at engine creation
+int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int lo_off, cudaStream_t st);
+int fill_i32(int* p, int v, size_t n, cudaStream_t st);
+// per-utterance CMVN over the frames of one call (TA:compliance/kaldi.py:603-606, subtract_mean)
+int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cudaStream_t st);
+
+}  // namespace asr

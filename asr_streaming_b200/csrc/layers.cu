@@ -1,0 +1,375 @@
+// Memory-bound fused kernels of the Emformer layer and the CTC decode.
+#include "kernels.cuh"
+
+namespace asr {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm(512): one warp per row, 16 values per lane held in registers, two-pass variance (matches
+// torch.nn.LayerNorm: biased variance, eps = 1e-5), fp32 statistics.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_D = 512;
+constexpr int LN_V = LN_D / 128;   // float4 per lane
+
+__device__ __forceinline__ void ln_load(const float* __restrict__ x, int lane, float (&v)[LN_V * 4]) {
+#pragma unroll
+  for (int i = 0; i < LN_V; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(x + i * 128 + lane * 4);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+__device__ __forceinline__ void ln_apply(float (&v)[LN_V * 4], const float* __restrict__ g, const float* __restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_V * 4; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / LN_D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_V * 4; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float var = warp_sum(q) * (1.0f / LN_D);
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < LN_V; ++i) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i * 128 + lane * 4);
+    const float4 bb = *reinterpret_cast<const float4*>(b + i * 128 + lane * 4);
+    v[4 * i] = (v[4 * i] - mean) * rstd * gg.x + bb.x;
+    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * gg.y + bb.y;
+    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * gg.z + bb.z;
+    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
+  }
+}
+
+__device__ __forceinline__ void ln_store_operand(bf16* __restrict__ o, int lo_off, int lane, const float (&v)[LN_V * 4]) {
+#pragma unroll
+  for (int i = 0; i < LN_V; ++i) {
+    const int c = i * 128 + lane * 4;
+    const bf16 h0 = __float2bfloat16_rn(v[4 * i]), h1 = __float2bfloat16_rn(v[4 * i + 1]);
+    const bf16 h2 = __float2bfloat16_rn(v[4 * i + 2]), h3 = __float2bfloat16_rn(v[4 * i + 3]);
+    uint2 h;
+    h.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    h.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    *reinterpret_cast<uint2*>(o + c) = h;
+    if (lo_off) {
+      uint2 l;
+      l.x = pack_bf16x2(v[4 * i] - __bfloat162float(h0), v[4 * i + 1] - __bfloat162float(h1));
+      l.y = pack_bf16x2(v[4 * i + 2] - __bfloat162float(h2), v[4 * i + 3] - __bfloat162float(h3));
+      *reinterpret_cast<uint2*>(o + lo_off + c) = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_to_operand_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                                            bf16* __restrict__ out, int ld, int lo_off, int M) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[LN_V * 4];
+  ln_load(x + (size_t)row * LN_D, lane, v);
+  ln_apply(v, g, b, lane);
+  ln_store_operand(out + (size_t)row * ld, lo_off, lane, v);
+}
+
+__global__ void __launch_bounds__(256) ln_out_fused_kernel(const float* __restrict__ x2, const float* __restrict__ g1, const float* __restrict__ b1,
+                                                           float* __restrict__ y, const float* __restrict__ g2, const float* __restrict__ b2,
+                                                           bf16* __restrict__ out, int ld, int lo_off, int M, int rows, int seg_rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[LN_V * 4];
+  ln_load(x2 + (size_t)row * LN_D, lane, v);
+  ln_apply(v, g1, b1, lane);
+#pragma unroll
+  for (int i = 0; i < LN_V; ++i)
+    *reinterpret_cast<float4*>(y + (size_t)row * LN_D + i * 128 + lane * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  if (g2) {
+    ln_apply(v, g2, b2, lane);
+    ln_store_operand(out + (size_t)row * ld, lo_off, lane, v);
+  } else {
+    const int b = row / rows, t = row - b * rows;
+    if (t < seg_rows) ln_store_operand(out + ((size_t)b * seg_rows + t) * ld, lo_off, lane, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Chunk attention (TA:emformer.py:184-204, :127-144) for one (stream, head) per warp.
+// Keys = [valid left context from the ring (oldest first), this chunk's segment rows (already in the ring,
+// written by the QKV epilogue), right-context rows (scratch)]; softmax in fp32 over exactly
+// lv + seg + rc keys — the reference slices the cache, it never attends to zero padding (:391-398).
+// ------------------------------------------------------------------------------------------
+constexpr int AT_DH = 64;
+constexpr int AT_MAXK = 64;
+constexpr int AT_KST = 68;     // padded fp32 row stride of the staged K / V tile (conflict-free LDS.128)
+constexpr int AT_WARPS = 4;
+
+template <typename T>
+__device__ __forceinline__ void stage_rows(const AttnParams<T>& P, const T* cache_slot, const T* rc_b, int which, int head, int lv, int pl,
+                                           int n_keys, float* __restrict__ dst, int lane) {
+  constexpr int VEC = 16 / (int)sizeof(T);              // elements per 16-byte load
+  constexpr int PER_ROW = AT_DH / VEC;
+  for (int i = lane; i < n_keys * PER_ROW; i += 32) {
+    const int j = i / PER_ROW, c = (i - j * PER_ROW) * VEC;
+    const T* src;
+    if (j < lv + P.seg_rows) {
+      const int rr = (pl - lv + j + P.ring) % P.ring;     // left rows: pl-lv+j ; segment rows: pl + (j-lv)
+      src = cache_slot + ((size_t)which * P.ring + rr) * P.d;
+    } else {
+      src = rc_b + ((size_t)which * P.rc_rows + (j - lv - P.seg_rows)) * P.d;
+    }
+    const int4 raw = *reinterpret_cast<const int4*>(src + head * AT_DH + c);
+    float* o = dst + j * AT_KST + c;
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<int4*>(o) = raw;
+    } else {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); o[2 * e] = f.x; o[2 * e + 1] = f.y; }
+    }
+  }
+}
+
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(AT_WARPS * 32) attention_kernel(AttnParams<T> P) {
+  extern __shared__ __align__(16) float at_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x, head = blockIdx.y * AT_WARPS + warp;
+  float* s_q = at_smem + warp * (ROWS * AT_DH + AT_MAXK * AT_KST + AT_MAXK * ROWS);
+  float* s_kv = s_q + ROWS * AT_DH;
+  float* s_p = s_kv + AT_MAXK * AT_KST;                   // pT[key][ROWS]
+
+  const int slot = P.slots[b];
+  const int pl = P.past_len[slot];
+  const int lv = pl < P.left ? pl : P.left;
+  const int n_keys = lv + P.seg_rows + P.rc_rows;
+  const T* cache_slot = P.cache_layer + (size_t)slot * P.slot_stride;
+  const T* rc_b = P.rc + (size_t)b * 2 * P.rc_rows * P.d;
+
+  for (int i = lane; i < ROWS * (AT_DH / 4); i += 32) {
+    const int r = i / (AT_DH / 4), c = (i - r * (AT_DH / 4)) * 4;
+    *reinterpret_cast<float4*>(s_q + r * AT_DH + c) = *reinterpret_cast<const float4*>(P.q + ((size_t)b * ROWS + r) * P.d + head * AT_DH + c);
+  }
+  stage_rows<T>(P, cache_slot, rc_b, 0, head, lv, pl, n_keys, s_kv, lane);
+  __syncwarp();
+
+  // ---- scores: lane owns keys (lane, lane + 32), all ROWS queries
+  float s0[ROWS], s1[ROWS];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+  const float* k0 = s_kv + lane * AT_KST;
+  const float* k1 = s_kv + (lane + 32) * AT_KST;
+  const bool v0 = lane < n_keys, v1 = lane + 32 < n_keys;
+#pragma unroll 2
+  for (int c = 0; c < AT_DH; c += 4) {
+    const float4 ka = v0 ? *reinterpret_cast<const float4*>(k0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 kb = v1 ? *reinterpret_cast<const float4*>(k1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const float4 qq = *reinterpret_cast<const float4*>(s_q + i * AT_DH + c);
+      s0[i] = fmaf(qq.x, ka.x, fmaf(qq.y, ka.y, fmaf(qq.z, ka.z, fmaf(qq.w, ka.w, s0[i]))));
+      s1[i] = fmaf(qq.x, kb.x, fmaf(qq.y, kb.y, fmaf(qq.z, kb.z, fmaf(qq.w, kb.w, s1[i]))));
+    }
+  }
+  // ---- softmax over keys (fp32), probabilities to smem transposed
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const float a = v0 ? s0[i] : -INFINITY, c = v1 ? s1[i] : -INFINITY;
+    const float m = warp_max(fmaxf(a, c));
+    const float e0 = v0 ? expf(a - m) : 0.f, e1 = v1 ? expf(c - m) : 0.f;
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    s_p[lane * ROWS + i] = e0 * inv;
+    s_p[(lane + 32) * ROWS + i] = e1 * inv;
+  }
+  __syncwarp();
+  stage_rows<T>(P, cache_slot, rc_b, 1, head, lv, pl, n_keys, s_kv, lane);   // V over the K tile
+  __syncwarp();
+  // ---- out[i][d] = sum_j p[i][j] * v[j][d]; lane owns d = lane, lane + 32
+  float o0[ROWS], o1[ROWS];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) { o0[i] = 0.f; o1[i] = 0.f; }
+  for (int j = 0; j < n_keys; ++j) {
+    const float va = s_kv[j * AT_KST + lane], vb = s_kv[j * AT_KST + lane + 32];
+#pragma unroll
+    for (int i = 0; i < ROWS; i += 4) {
+      const float4 pp = *reinterpret_cast<const float4*>(s_p + j * ROWS + i);
+      o0[i] = fmaf(pp.x, va, o0[i]); o1[i] = fmaf(pp.x, vb, o1[i]);
+      o0[i + 1] = fmaf(pp.y, va, o0[i + 1]); o1[i + 1] = fmaf(pp.y, vb, o1[i + 1]);
+      o0[i + 2] = fmaf(pp.z, va, o0[i + 2]); o1[i + 2] = fmaf(pp.z, vb, o1[i + 2]);
+      o0[i + 3] = fmaf(pp.w, va, o0[i + 3]); o1[i + 3] = fmaf(pp.w, vb, o1[i + 3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    bf16* o = P.out + ((size_t)b * ROWS + i) * P.ld + head * AT_DH;
+    const bf16 h0 = __float2bfloat16_rn(o0[i]), h1 = __float2bfloat16_rn(o1[i]);
+    o[lane] = h0; o[lane + 32] = h1;
+    if (P.lo_off) {
+      o[P.lo_off + lane] = __float2bfloat16_rn(o0[i] - __bfloat162float(h0));
+      o[P.lo_off + lane + 32] = __float2bfloat16_rn(o1[i] - __bfloat162float(h1));
+    }
+  }
+}
+
+template <typename T, int ROWS>
+int attention_launch_rows(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
+  static_assert(ROWS % 4 == 0, "ROWS must be a multiple of 4");
+  const size_t smem = sizeof(float) * AT_WARPS * (ROWS * AT_DH + AT_MAXK * AT_KST + AT_MAXK * ROWS);
+  static bool attr = false;
+  if (!attr) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(attention_kernel<T, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(n_streams, P.n_heads / AT_WARPS);
+  attention_kernel<T, ROWS><<<grid, AT_WARPS * 32, smem, st>>>(P);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CTC log-softmax + argmax + incremental greedy (decoder.py:69; recognition.py:33-57).  One CTA per stream.
+// The reference re-scans the whole accumulated emission every chunk; carrying (prev_id, n_frames,
+// last_tok_frame) per session gives the identical token sequence and last_blank incrementally.
+// ------------------------------------------------------------------------------------------
+constexpr int CTC_MAXV = 32;   // vocab <= 1024
+
+__global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
+  __shared__ int s_ids[64];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < P.seg_rows; r += 8) {
+    const size_t row = (size_t)b * P.seg_rows + r;
+    const float* z = P.logits + row * P.vocab;
+    float v[CTC_MAXV];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < CTC_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < P.vocab ? z[c] : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CTC_MAXV; ++i) s += (lane + 32 * i < P.vocab) ? expf(v[i] - m) : 0.f;
+    const float lse = logf(warp_sum(s));
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < CTC_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < P.vocab) {
+        const float lp = (v[i] - m) - lse;                       // log_softmax(dim=2)
+        if (P.logprobs) P.logprobs[row * P.vocab + c] = lp;
+        if (lp > best) { best = lp; bi = c; }                     // first max wins inside a lane (c increasing)
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                            // torch.argmax: lowest index among equal maxima
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_ids[r] = bi; P.argmax_ids[row] = bi; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int slot = P.slots[b];
+    int prev = P.prev_id[slot], nf = P.n_frames[slot], lt = P.last_tok_frame[slot], n_new = 0;
+    for (int r = 0; r < P.seg_rows; ++r) {
+      const int id = s_ids[r];
+      if (id != prev && id != 0) P.new_tokens[(size_t)b * P.seg_rows + n_new++] = id;   // unique_consecutive, then drop blank
+      if (id > 1) lt = nf;                                                              // tokens_idx = indices > 1
+      prev = id; ++nf;
+    }
+    P.prev_id[slot] = prev; P.n_frames[slot] = nf; P.last_tok_frame[slot] = lt;
+    P.n_new[b] = n_new;
+    P.has_token[b] = lt >= 0;
+    P.blank_frames[b] = lt >= 0 ? nf - 1 - lt : nf;
+    P.past_len[slot] += P.seg_rows;                                                     // TA:emformer.py:413 (state[3] + update_length)
+  }
+}
+
+__global__ void convert_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int cols, int ld, int lo_off) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    const float x = src[i];
+    const bf16 h = __float2bfloat16_rn(x);
+    dst[(size_t)r * ld + c] = h;
+    if (lo_off) dst[(size_t)r * ld + lo_off + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+__global__ void subtract_mean_kernel(float* __restrict__ x, int n_frames, int n_mels) {
+  // one CTA per stream, one thread per mel bin
+  float* p = x + (size_t)blockIdx.x * n_frames * n_mels;
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < n_frames; ++t) s += p[(size_t)t * n_mels + m];
+    const float mean = s / (float)n_frames;
+    for (int t = 0; t < n_frames; ++t) p[(size_t)t * n_mels + m] -= mean;
+  }
+}
+
+__global__ void fill_i32_kernel(int* p, int v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+int ln_to_operand(const float* x, const float* g, const float* b, bf16* out, int ld, int lo_off, int M, int d, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (d != LN_D) { set_error("layer norm kernels are built for d_model = %d (got %d)", LN_D, d); return -1; }
+  ln_to_operand_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, b, out, ld, lo_off, M);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ln_out_fused(const float* x2, const float* g1, const float* b1, float* y, const float* g2, const float* b2, bf16* out, int ld,
+                 int lo_off, int M, int d, int rows, int seg_rows, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (d != LN_D) { set_error("layer norm kernels are built for d_model = %d (got %d)", LN_D, d); return -1; }
+  ln_out_fused_kernel<<<(M + 7) / 8, 256, 0, st>>>(x2, g1, b1, y, g2, b2, out, ld, lo_off, M, rows, seg_rows);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
+  if (n_streams <= 0) return 0;
+  if (P.d != P.n_heads * AT_DH || P.n_heads % AT_WARPS != 0 || P.left + P.seg_rows + P.rc_rows > AT_MAXK) {
+    set_error("attention: unsupported geometry (d %d heads %d keys %d)", P.d, P.n_heads, P.left + P.seg_rows + P.rc_rows);
+    return -1;
+  }
+  if (P.rows == 20) return attention_launch_rows<T, 20>(P, n_streams, st);
+  if (P.rows == 12) return attention_launch_rows<T, 12>(P, n_streams, st);
+  set_error("attention: unsupported rows per chunk %d (built for 20 and 12)", P.rows);
+  return -1;
+}
+template int attention_launch<float>(const AttnParams<float>&, int, cudaStream_t);
+template int attention_launch<bf16>(const AttnParams<bf16>&, int, cudaStream_t);
+
+int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st) {
+  if (n_streams <= 0) return 0;
+  if (P.vocab > 32 * CTC_MAXV || P.seg_rows > 64) { set_error("ctc: vocab %d / seg_rows %d too large", P.vocab, P.seg_rows); return -1; }
+  ctc_greedy_kernel<<<n_streams, 256, 0, st>>>(P);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int lo_off, cudaStream_t st) {
+  convert_weight_kernel<<<296, 256, 0, st>>>(src, dst, rows, cols, ld, lo_off);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cudaStream_t st) {
+  subtract_mean_kernel<<<n_streams, 128, 0, st>>>(x, n_frames, n_mels);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fill_i32(int* p, int v, size_t n, cudaStream_t st) {
+  if (!n) return 0;
+  fill_i32_kernel<<<148, 256, 0, st>>>(p, v, n);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace asr

@@ -1,0 +1,210 @@
+"""Slot-based batched front of the C ABI: one Engine per GPU, device-resident K/V rings and greedy carry per session."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .config import ModelConfig
+
+FRAMERATE = 0.04            # recognition.py:30
+PCM_I16, PCM_F32 = 0, 1
+FBANK_MELSPEC128, FBANK_KALDI80 = 0, 1
+
+
+@dataclass
+class StepResult:
+    """Per-step outputs for n streams (S = segment rows)."""
+    argmax_ids: np.ndarray                 # [n, S] int32
+    new_tokens: List[np.ndarray]           # n arrays of the ids appended this chunk (collapsed, blank-free)
+    blank_frames: np.ndarray               # [n] int32
+    has_token: np.ndarray                  # [n] bool
+    logprobs: Optional[np.ndarray]         # [n, S, V] float32 or None
+
+    def last_blank(self, i: int) -> float:
+        """The reference's ``last_blank`` (recognition.py:38-43): python float 0.04*T when the segment has no
+        token yet, else the float32 product tensor(int64) * 0.04 -> .item()."""
+        if self.has_token[i]:
+            return float(np.float32(self.blank_frames[i]) * np.float32(FRAMERATE))
+        return FRAMERATE * int(self.blank_frames[i])
+
+
+def _cfg_to_c(cfg: ModelConfig) -> _lib.AsrConfigC:
+    c = _lib.AsrConfigC()
+    c.abi_version = _lib.ABI_VERSION
+    for name in ("sample_rate", "hop", "n_fft", "win", "n_mels", "segment_size", "context_size", "bias", "stride", "d_model",
+                 "n_heads", "ffn_dim", "n_layers", "left_context", "ctc_hidden", "vocab", "precision", "max_sessions", "max_batch"):
+        setattr(c, name, int(getattr(cfg, name)))
+    return c
+
+
+class Engine:
+    """Owns the device state of one GPU.  ``weights`` is the flat fp32 blob from ``pack_weights``."""
+
+    def __init__(self, cfg: ModelConfig, weights: np.ndarray, device: int = 0):
+        self.lib = _lib.load_library()
+        self.cfg = cfg
+        self.device = device
+        self._c = _cfg_to_c(cfg)
+        n = C.c_uint64()
+        _lib.check(self.lib, self.lib.asr_weights_count(C.byref(self._c), C.byref(n)), "asr_weights_count")
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(-1)
+        if w.size != n.value:
+            raise ValueError(f"weights blob has {w.size} floats, config needs {n.value}")
+        h = C.c_void_p()
+        _lib.check(self.lib, self.lib.asr_engine_create(C.byref(self._c), w.ctypes.data, w.size, device, C.byref(h)), "asr_engine_create")
+        self._h = h
+        self.S = cfg.seg_rows
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.asr_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ sessions
+    def open_session(self) -> int:
+        s = C.c_int32()
+        _lib.check(self.lib, self.lib.asr_session_open(self._h, C.byref(s)), "asr_session_open")
+        return s.value
+
+    def reset_session(self, slot: int) -> None:
+        _lib.check(self.lib, self.lib.asr_session_reset(self._h, slot), "asr_session_reset")
+
+    def close_session(self, slot: int) -> None:
+        _lib.check(self.lib, self.lib.asr_session_close(self._h, slot), "asr_session_close")
+
+    # ------------------------------------------------------------------ the hot path
+    def _pcm(self, pcm: np.ndarray, n: int):
+        a = np.ascontiguousarray(pcm)
+        if a.dtype == np.int16:
+            fmt = PCM_I16
+        elif a.dtype == np.float32:
+            fmt = PCM_F32
+        else:
+            raise TypeError(f"pcm must be int16 or float32, got {a.dtype}")
+        if a.size != n * self.cfg.chunk_length:
+            raise ValueError(f"pcm has {a.size} samples, expected {n} x chunk_length {self.cfg.chunk_length}")
+        return a, fmt
+
+    def _alloc_out(self, n: int, want_logprobs: bool):
+        S, V = self.S, self.cfg.vocab
+        bufs = dict(argmax=np.empty((n, S), np.int32), newtok=np.empty((n, S), np.int32), nnew=np.empty(n, np.int32),
+                    blank=np.empty(n, np.int32), hastok=np.empty(n, np.int32),
+                    logprobs=np.empty((n, S, V), np.float32) if want_logprobs else None)
+        o = _lib.AsrStepOutC(bufs["argmax"].ctypes.data, bufs["newtok"].ctypes.data, bufs["nnew"].ctypes.data, bufs["blank"].ctypes.data,
+                             bufs["hastok"].ctypes.data, bufs["logprobs"].ctypes.data if want_logprobs else None)
+        return bufs, o
+
+    @staticmethod
+    def _result(bufs, n) -> StepResult:
+        new = [bufs["newtok"][i, :bufs["nnew"][i]].copy() for i in range(n)]
+        return StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"])
+
+    def step(self, slots: Sequence[int], pcm: np.ndarray, want_logprobs: bool = False) -> StepResult:
+        """One chunk for each of ``slots`` (any mix of progress).  pcm: [n, chunk_length] int16 or float32."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        n = int(sl.size)
+        a, fmt = self._pcm(pcm, n)
+        bufs, o = self._alloc_out(n, want_logprobs)
+        _lib.check(self.lib, self.lib.asr_step(self._h, n, sl.ctypes.data, a.ctypes.data, fmt, C.byref(o)), "asr_step")
+        return self._result(bufs, n)
+
+    # split form (pipelining / device-resident timing)
+    def stage(self, slots: Sequence[int], pcm: np.ndarray) -> int:
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        a, fmt = self._pcm(pcm, int(sl.size))
+        _lib.check(self.lib, self.lib.asr_stage(self._h, int(sl.size), sl.ctypes.data, a.ctypes.data, fmt), "asr_stage")
+        return int(sl.size)
+
+    def run_staged(self, n: int, want_logprobs: bool = False) -> None:
+        _lib.check(self.lib, self.lib.asr_run_staged(self._h, n, int(want_logprobs)), "asr_run_staged")
+
+    def fetch(self, n: int, want_logprobs: bool = False) -> StepResult:
+        bufs, o = self._alloc_out(n, want_logprobs)
+        _lib.check(self.lib, self.lib.asr_fetch(self._h, n, C.byref(o)), "asr_fetch")
+        return self._result(bufs, n)
+
+    def sync(self) -> None:
+        _lib.check(self.lib, self.lib.asr_sync(self._h), "asr_sync")
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.lib.asr_stream_handle(self._h) or 0)
+
+    # ------------------------------------------------------------------ fbank
+    def fbank(self, pcm: np.ndarray, kind: int = FBANK_MELSPEC128, subtract_mean: bool = False) -> np.ndarray:
+        """pcm [n, n_samples] int16/float32 -> [n, frames, mels] float32 (extract_filterbank, audio.py:9-30 / Kaldi fbank)."""
+        a = np.ascontiguousarray(pcm)
+        if a.ndim != 2:
+            raise ValueError("pcm must be [n, n_samples]")
+        fmt = PCM_I16 if a.dtype == np.int16 else PCM_F32
+        if a.dtype not in (np.int16, np.float32):
+            raise TypeError("pcm must be int16 or float32")
+        n, ns = a.shape
+        if kind == FBANK_MELSPEC128:
+            frames, mels = self.cfg.frames, self.cfg.n_mels
+        else:
+            frames, mels = 1 + (ns - 400) // 160, 80
+        out = np.empty((n, frames, mels), np.float32)
+        _lib.check(self.lib, self.lib.asr_fbank(self._h, kind, n, a.ctypes.data, fmt, ns, int(subtract_mean), out.ctypes.data), "asr_fbank")
+        return out
+
+    def stage_raw(self, pcm: np.ndarray) -> None:
+        a = np.ascontiguousarray(pcm)
+        _lib.check(self.lib, self.lib.asr_stage_raw(self._h, a.ctypes.data, a.nbytes), "asr_stage_raw")
+
+    def fbank_staged(self, kind: int, n: int, fmt: int, n_samples: int) -> None:
+        _lib.check(self.lib, self.lib.asr_fbank_staged(self._h, kind, n, fmt, n_samples), "asr_fbank_staged")
+
+    # ------------------------------------------------------------------ stats / diagnostics
+    def stats(self) -> dict:
+        s = _lib.AsrStatsC()
+        _lib.check(self.lib, self.lib.asr_get_stats(self._h, C.byref(s)), "asr_get_stats")
+        return {k: getattr(s, k) for k, _ in _lib.AsrStatsC._fields_}
+
+    def debug_step_partial(self, slots: Sequence[int], pcm: np.ndarray, n_layers: int) -> None:
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        a, fmt = self._pcm(pcm, int(sl.size))
+        _lib.check(self.lib, self.lib.asr_debug_step_partial(self._h, int(sl.size), sl.ctypes.data, a.ctypes.data, fmt, n_layers), "asr_debug_step_partial")
+
+    def debug_read(self, which: int, shape) -> np.ndarray:
+        out = np.empty(shape, np.float32)
+        _lib.check(self.lib, self.lib.asr_debug_read(self._h, which, out.ctypes.data, out.size), "asr_debug_read")
+        return out
+
+    def debug_read_state(self, slot: int, layer: int, which: int):
+        out = np.empty((self.cfg.left_context, self.cfg.d_model), np.float32)
+        pl = C.c_int32()
+        _lib.check(self.lib, self.lib.asr_debug_read_state(self._h, slot, layer, which, out.ctypes.data, C.byref(pl)), "asr_debug_read_state")
+        return out, pl.value
+
+
+def debug_gemm(A: np.ndarray, B: np.ndarray, bias: Optional[np.ndarray] = None, impl: int = 0, split: int = 0, bn: int = 128,
+               device: int = 0) -> np.ndarray:
+    """C = A @ B.T (+bias) through the tcgen05 (impl 0) or CUDA-core (impl 1) GEMM."""
+    lib = _lib.load_library()
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = np.empty((M, N), np.float32)
+    b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
+    _lib.check(lib, lib.asr_debug_gemm(impl, M, N, K, split, bn, A.ctypes.data, B.ctypes.data, b.ctypes.data if b is not None else None,
+                                       Cm.ctypes.data, device), "asr_debug_gemm")
+    return Cm

@@ -1,0 +1,142 @@
+/* asr_b200.h — C ABI of the B200-native per-chunk compute path of Naiscorp-Robotics/ASR-streaming's
+ * "lightspeech" streaming decoder (PCM -> log-mel -> Emformer chunk forward with per-session K/V caches ->
+ * CTC log-softmax -> greedy / prefix-beam decode), batched across many websocket sessions.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference has no FFI of its own
+ * (it is pure Python); each entry point below names the reference Python interface it replaces, with file:line
+ * relative to the reference repo root.  The Python host mirror (asr_streaming_b200.recognition.LightningASR)
+ * binds these with ctypes; INTEGRATION.md shows the stub a maintainer adds on the reference side.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure, and never throws; the message of the
+ * last failure on the calling thread is asr_last_error().  One engine per GPU; calls on one engine are serialised
+ * by an internal mutex.  Device memory is owned by the engine; host buffers are owned by the caller and are only
+ * read / written during the call.
+ */
+#ifndef ASR_B200_H_
+#define ASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASR_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ASR_API __attribute__((visibility("default")))
+#else
+#define ASR_API
+#endif
+
+typedef struct AsrEngine AsrEngine;
+
+/* Precision of the dense projections.  FAST: bf16 operands, fp32 accumulate (north-star tolerance: max-abs <= 1e-2
+ * on log-probs).  EXACT: split-bf16 (hi + lo) operands, three tcgen05 products per GEMM, fp32 K/V cache
+ * (max-abs ~1e-5; used for the token-exact gate against the reference). */
+enum { ASR_PRECISION_FAST = 0, ASR_PRECISION_EXACT = 1 };
+enum { ASR_PCM_I16 = 0, ASR_PCM_F32 = 1 };
+enum { ASR_FBANK_MELSPEC128 = 0, ASR_FBANK_KALDI80 = 1 };
+
+/* Geometry = AudioConfig (streaming_decoder/utils.py:9-23, config/asr-online.yaml:112-118) + model hyper-parameters
+ * (lightspeech/modules/encoder.py:73-117, lightspeech/models/recognition.py:207-217). */
+typedef struct AsrConfig {
+  int32_t abi_version;     /* ASR_B200_ABI_VERSION */
+  int32_t sample_rate;     /* 16000 */
+  int32_t hop;             /* 160  samples */
+  int32_t n_fft;           /* 800 */
+  int32_t win;             /* 400 */
+  int32_t n_mels;          /* 128 */
+  int32_t segment_size;    /* 64 frames  (32 in the low-latency mode) */
+  int32_t context_size;    /* 16 frames */
+  int32_t bias;            /* 4 frames */
+  int32_t stride;          /* 4 */
+  int32_t d_model;         /* 512 */
+  int32_t n_heads;         /* 8 */
+  int32_t ffn_dim;         /* 2048 */
+  int32_t n_layers;        /* 20 */
+  int32_t left_context;    /* 32 rows */
+  int32_t ctc_hidden;      /* 512 */
+  int32_t vocab;           /* 804 */
+  int32_t precision;       /* ASR_PRECISION_* */
+  int32_t max_sessions;    /* K/V slots to allocate */
+  int32_t max_batch;       /* max stream-chunks per step */
+} AsrConfig;
+
+typedef struct AsrStepOut {     /* all pointers nullable, host memory, n = streams in the step, S = segment rows (16) */
+  int32_t* argmax_ids;          /* [n*S]  per-frame argmax of the log-probs (recognition.py:36)                       */
+  int32_t* new_tokens;          /* [n*S]  ids appended this chunk after unique_consecutive + blank drop (:44-45)     */
+  int32_t* n_new;               /* [n]                                                                                */
+  int32_t* blank_frames;        /* [n]    frames since the last id > 1, or all frames of the segment if none (:38-43) */
+  int32_t* has_token;           /* [n]                                                                                */
+  float* logprobs;              /* [n*S*vocab]  the reference's `emission` (recognition.py:203-204)                   */
+} AsrStepOut;
+
+typedef struct AsrStats {
+  uint64_t steps;               /* asr_step calls                                  */
+  uint64_t stream_chunks;       /* stream-chunks processed                         */
+  uint64_t kernel_launches;     /* CUDA kernels launched by this engine            */
+  double step_ms_p50, step_ms_p99, step_ms_max, step_ms_mean;   /* host wall time of asr_step, last <= 4096 steps */
+} AsrStats;
+
+ASR_API const char* asr_last_error(void);
+ASR_API int asr_abi_version(void);
+
+/* Fills *cfg with the canonical geometry of SURVEY.md §8a (chunk_size 16).  low_latency != 0 -> segment_size 32. */
+ASR_API int asr_default_config(AsrConfig* cfg, int low_latency);
+/* Number of fp32 values asr_engine_create expects in `weights` for this config (layout: see weights.py / DESIGN.md). */
+ASR_API int asr_weights_count(const AsrConfig* cfg, uint64_t* n_floats);
+/* Samples per stream-chunk (AudioConfig.chunk_length, utils.py:22) and output rows per chunk. */
+ASR_API int asr_chunk_geometry(const AsrConfig* cfg, int32_t* chunk_length, int32_t* segment_length, int32_t* seg_rows);
+
+/* Replaces LightningASR.__init__ / _load_checkpoint (recognition.py:137-159): weights are the fp32 tensors of the
+ * checkpoint's state_dict["encoder"|"decoder"], packed in the documented order. */
+ASR_API int asr_engine_create(const AsrConfig* cfg, const float* weights, uint64_t n_floats, int device, AsrEngine** out);
+ASR_API int asr_engine_destroy(AsrEngine* e);
+
+/* Replaces LightningASR.init_state (recognition.py:207-217) and `stream.state = state_init`
+ * (streaming_server.py:324-326, :530): a session owns one K/V ring slot + greedy carry. */
+ASR_API int asr_session_open(AsrEngine* e, int32_t* slot_out);
+ASR_API int asr_session_reset(AsrEngine* e, int32_t slot);           /* endpoint: state := init, emission := []  (:514-515, :530) */
+ASR_API int asr_session_close(AsrEngine* e, int32_t slot);
+
+/* Replaces LightningASR.stream (recognition.py:191-204) + greedy_search (recognition.py:33-57) for n sessions with
+ * arbitrary, different progress.  pcm: packed [n, chunk_length] int16 (as received from the websocket,
+ * streaming_server.py:362) or float32 in [-1,1).  A session may appear at most once per step. */
+ASR_API int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, const AsrStepOut* out);
+
+/* Same, split for pipelining / device-resident timing: stage = H2D of inputs; run = kernels only (async on the
+ * engine stream); fetch = D2H of results + synchronise. */
+ASR_API int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format);
+ASR_API int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs);
+ASR_API int asr_fetch(AsrEngine* e, int32_t n, const AsrStepOut* out);
+ASR_API int asr_sync(AsrEngine* e);
+ASR_API void* asr_stream_handle(AsrEngine* e);      /* cudaStream_t the engine launches on (for CUDA-event timing) */
+
+/* Replaces extract_filterbank (lightspeech/datas/audio.py:9-30) [MELSPEC128 -> out [n, frames, 128]] and provides the
+ * north-star Kaldi front-end (torchaudio.compliance.kaldi.fbank, 80 bins, dither 0) [KALDI80 -> out [n, frames, 80],
+ * frames = 1 + (n_samples - 400) / 160; subtract_mean != 0 applies per-utterance CMVN over the frames of the call]. */
+ASR_API int asr_fbank(AsrEngine* e, int32_t kind, int32_t n, const void* pcm, int32_t pcm_format, int32_t n_samples, int32_t subtract_mean,
+              float* out);
+ASR_API int asr_fbank_staged(AsrEngine* e, int32_t kind, int32_t n, int32_t pcm_format, int32_t n_samples);   /* kernels only, inputs from asr_stage_raw */
+ASR_API int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes);
+
+ASR_API int asr_get_stats(AsrEngine* e, AsrStats* out);
+
+/* ---- diagnostics used by tests (not part of the serving path) ---- */
+/* Runs the step but stops after `n_layers` encoder layers (no CTC, no state advance); buffers readable below. */
+ASR_API int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t n_layers);
+/* which: 0 = x (layer output / input_linear output) [n*rows, d]; 1 = x1; 2 = x2; 3 = q; 4 = logits [n*S, vocab] */
+ASR_API int asr_debug_read(AsrEngine* e, int32_t which, float* out, uint64_t n_floats);
+/* Reads the K (which=0) / V (which=1) left context of `layer` of a session in the reference's layout
+ * [left_context, d] (oldest row first, zero rows where past_length < left_context) and past_length. */
+ASR_API int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int32_t which, float* out, int32_t* past_length);
+/* Stand-alone GEMM C[M,N] = A[M,K] * B[N,K]^T (+bias): impl 0 = tcgen05 kernel, 1 = CUDA-core cross-check. */
+ASR_API int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, const float* A, const float* B, const float* bias,
+                   float* C, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H_ */

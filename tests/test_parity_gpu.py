@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C ABI) with the reference fixtures and the CPU oracle.
+
+Stated tolerances (derived in tests/test_oracle_golden.py::test_precision_models_meet_stated_tolerances):
+  fbank melspec128 : max-abs <= 2e-3 in the log domain on audio with signal, bins > clamp (fp32 FFT both sides)
+  EXACT precision  : log-probs max-abs <= 2e-4, greedy token ids bit-exact on every frame
+  FAST  precision  : log-probs max-abs <= 1e-2 (north-star), greedy ids exact on frames whose fp32 top-2 margin > 2e-2
+"""
+import numpy as np
+import pytest
+
+from oracle import lightspeech_oracle as O
+from tests.helpers import chunks_i16, margins, model_cfg, to_float
+
+pytestmark = pytest.mark.gpu
+
+EXACT_TOL, FAST_TOL = 2e-4, 1e-2
+
+
+@pytest.fixture(scope="module")
+def engines(packed_weights):
+    from asr_streaming_b200 import Engine, PRECISION_EXACT, PRECISION_FAST
+    made = {}
+
+    def get(precision, low_latency=False):
+        key = (precision, low_latency)
+        if key not in made:
+            made[key] = Engine(model_cfg(precision, low_latency), packed_weights)
+        return made[key]
+    get.EXACT, get.FAST = PRECISION_EXACT, PRECISION_FAST
+    yield get
+    for e in made.values():
+        e.close()
+
+
+# ------------------------------------------------------------------------------------------------ fbank
+def test_melspec128_vs_reference(engines, golden):
+    fb = golden("fbank")
+    e = engines(engines.FAST)
+    out_i16 = e.fbank(fb["melspec_pcm"][None, :])[0]
+    out_f32 = e.fbank(to_float(fb["melspec_pcm"])[None, :])[0]
+    assert out_i16.shape == (80, 128)
+    assert np.array_equal(out_i16, out_f32)                    # int16 and float inputs are the same samples
+    assert np.abs(out_i16 - fb["melspec128"]).max() < 2e-3
+    assert np.abs(out_i16 - O.melspec128(to_float(fb["melspec_pcm"]))).max() < 2e-3
+
+
+def test_melspec128_edge_inputs(engines):
+    e = engines(engines.FAST)
+    n = O.CANONICAL.chunk_length
+    sil = e.fbank(np.zeros((1, n), np.int16))[0]
+    assert np.all(sil == np.float32(np.log(np.float32(1e-5))))  # clamp(1e-5).log() exactly
+    fs = np.where((np.arange(n) // 37) % 2 == 0, 32767, -32768).astype(np.int16)
+    dc = np.full(n, 12000, np.int16)
+    for pcm in (fs, dc):
+        got = e.fbank(pcm[None])[0]
+        ref = O.melspec128(to_float(pcm))
+        big = ref > np.log(1e-3)                                # leakage bins far below the signal are fp32 noise on both sides
+        assert np.abs(got - ref)[big].max() < 5e-3
+        assert np.isfinite(got).all()
+
+
+def test_kaldi80_vs_torchaudio(engines, golden):
+    fb = golden("fbank")
+    e = engines(engines.FAST)
+    out = e.fbank(fb["kaldi_pcm"][None, :], kind=1)[0]
+    assert out.shape == fb["kaldi80"].shape == (64, 80)
+    assert np.abs(out - fb["kaldi80"]).max() < 2e-3
+    out_cmvn = e.fbank(fb["kaldi_pcm"][None, :], kind=1, subtract_mean=True)[0]
+    assert np.abs(out_cmvn - fb["kaldi80_cmvn"]).max() < 2e-3
+
+
+def test_fbank_batch_is_per_stream(engines):
+    e = engines(engines.FAST)
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-3000, 3000, size=(37, O.CANONICAL.chunk_length)).astype(np.int16)
+    out = e.fbank(pcm)
+    for i in (0, 17, 36):
+        assert np.array_equal(out[i], e.fbank(pcm[i:i + 1])[0])
+
+
+# ------------------------------------------------------------------------------------------------ full path vs reference fixtures
+def _run_case(e, case, mc, geo=O.CANONICAL):
+    slot = e.open_session()
+    ems, toks, blanks, texts_ids = [], [], [], []
+    acc = []
+    for k, ch in enumerate(chunks_i16(case["pcm"], geo)):
+        if k in mc["reset_before"]:
+            e.reset_session(slot)
+            acc = []
+        if k in mc["skip"]:
+            continue
+        r = e.step([slot], ch[None, :], want_logprobs=True)
+        ems.append(r.logprobs[0])
+        acc.extend(int(t) for t in r.new_tokens[0])
+        texts_ids.append(list(acc))
+        blanks.append(r.last_blank(0))
+    e.close_session(slot)
+    return np.stack(ems), texts_ids, blanks
+
+
+@pytest.mark.parametrize("name", ["synth_noise", "synth_tone", "testwav", "edge_silence", "edge_fullscale", "edge_dc", "seq_reset_skip"])
+def test_exact_mode_matches_reference(name, engines, golden, meta):
+    from asr_streaming_b200 import ids_to_text
+    case, mc = golden(name), meta["cases"][name]
+    em, ids, blanks = _run_case(engines(engines.EXACT), case, mc)
+    ref = case["emission"]
+    assert em.shape == ref.shape
+    assert np.abs(em - ref).max() < EXACT_TOL
+    assert np.array_equal(em.argmax(2), case["argmax"])                       # bit-exact greedy ids, every frame
+    for j in range(len(ids)):
+        assert ids_to_text(ids[j], meta["vocab"]) == mc["texts"][j]            # incremental greedy == reference rescans
+        assert abs(blanks[j] - case["last_blank"][j]) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["synth_noise", "testwav", "seq_reset_skip"])
+def test_fast_mode_within_tolerance(name, engines, golden, meta):
+    case, mc = golden(name), meta["cases"][name]
+    em, _, _ = _run_case(engines(engines.FAST), case, mc)
+    ref = case["emission"]
+    err = np.abs(em - ref).max()
+    assert err < FAST_TOL, f"bf16 path max-abs {err}"
+    safe = margins(ref) > 2 * FAST_TOL
+    assert safe.mean() > 0.3
+    assert np.array_equal(em.argmax(2)[safe], case["argmax"][safe])
+
+
+def test_low_latency_geometry(engines, golden, meta):
+    case, mc = golden("lowlat_noise"), meta["cases"]["lowlat_noise"]
+    em, _, _ = _run_case(engines(engines.EXACT, True), case, mc, O.LOW_LATENCY)
+    assert em.shape == case["emission"].shape
+    assert np.abs(em - case["emission"]).max() < EXACT_TOL
+    assert np.array_equal(em.argmax(2), case["argmax"])
+
+
+def test_kv_state_matches_reference(engines, golden, meta):
+    case, mc = golden("synth_noise"), meta["cases"]["synth_noise"]
+    e = engines(engines.EXACT)
+    slot = e.open_session()
+    for ch in chunks_i16(case["pcm"]):
+        e.step([slot], ch[None, :])
+    k0, pl = e.debug_read_state(slot, 0, 0)
+    v19, _ = e.debug_read_state(slot, 19, 1)
+    e.close_session(slot)
+    assert pl == mc["past_length"]
+    assert np.abs(k0 - case["state_k_l0"]).max() < EXACT_TOL       # ring overwrite == cat + slice (TA:emformer.py:400-414)
+    assert np.abs(v19 - case["state_v_l19"]).max() < EXACT_TOL
+
+
+# ------------------------------------------------------------------------------------------------ ragged batching
+def test_ragged_batch_equals_batch1(engines, golden, meta):
+    """Streams at different progress (fresh / 1 chunk / steady state / just reset) in ONE step must each equal their
+    own batch-1 run — the property torchaudio's batched infer violates (TA:emformer.py:392)."""
+    e = engines(engines.EXACT)
+    names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale"]
+    cases = [golden(n) for n in names]
+    chunks = [chunks_i16(c["pcm"]) for c in cases]
+    starts = [0, 2, 1, 3]                        # stream i joins at global tick starts[i]
+    slots = [e.open_session() for _ in names]
+    got = [[] for _ in names]
+    for tick in range(6):
+        idx = [i for i in range(len(names)) if 0 <= tick - starts[i] < len(chunks[i])]
+        if not idx:
+            continue
+        pcm = np.stack([chunks[i][tick - starts[i]] for i in idx])
+        r = e.step([slots[i] for i in idx], pcm, want_logprobs=True)
+        for j, i in enumerate(idx):
+            got[i].append(r.logprobs[j])
+    for i, c in enumerate(cases):
+        g = np.stack(got[i])
+        ref = c["emission"][:g.shape[0]]
+        assert np.abs(g - ref).max() < EXACT_TOL, names[i]
+        assert np.array_equal(g.argmax(2), c["argmax"][:g.shape[0]])
+    for s in slots:
+        e.close_session(s)
+
+
+def test_batch_order_and_duplicates_of_audio(engines):
+    """Permuting the batch permutes the outputs bit-exactly; identical audio in different slots gives identical rows."""
+    e = engines(engines.FAST)
+    rng = np.random.default_rng(11)
+    n = 24
+    pcm = rng.integers(-4000, 4000, size=(n, O.CANONICAL.chunk_length)).astype(np.int16)
+    pcm[5] = pcm[3]
+    a = [e.open_session() for _ in range(n)]
+    b = [e.open_session() for _ in range(n)]
+    perm = rng.permutation(n)
+    for _ in range(3):                           # through L_valid = 0, 16, 32
+        ra = e.step(a, pcm, want_logprobs=True)
+        rb = e.step([b[i] for i in perm], pcm[perm], want_logprobs=True)
+        assert np.array_equal(ra.logprobs[perm], rb.logprobs)
+        assert np.array_equal(ra.logprobs[3], ra.logprobs[5])
+    for s in a + b:
+        e.close_session(s)
+
+
+def test_full_batch_steady_state_property(engines):
+    """max_batch streams at once (size-independent property): every stream fed the same audio must produce the same
+    tokens as stream 0, in both precisions."""
+    for prec in (engines.FAST, engines.EXACT):
+        e = engines(prec)
+        n = e.cfg.max_batch
+        rng = np.random.default_rng(2)
+        one = rng.integers(-3000, 3000, size=(4, O.CANONICAL.chunk_length)).astype(np.int16)
+        slots = [e.open_session() for _ in range(n)]
+        for t in range(4):
+            r = e.step(slots, np.repeat(one[t][None], n, 0))
+            assert (r.argmax_ids == r.argmax_ids[0]).all()
+        for s in slots:
+            e.close_session(s)
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_error_paths(engines):
+    from asr_streaming_b200 import AsrLibraryError
+    e = engines(engines.FAST)
+    n = O.CANONICAL.chunk_length
+    with pytest.raises(AsrLibraryError):
+        e.step([12345], np.zeros((1, n), np.int16))                     # not an open session
+    with pytest.raises(ValueError):
+        e.step([0], np.zeros((1, n - 1), np.int16))                     # wrong chunk length
+    s = e.open_session()
+    e.close_session(s)
+    with pytest.raises(AsrLibraryError):
+        e.step([s], np.zeros((1, n), np.int16))                         # closed session
+    r = e.step([], np.zeros((0, n), np.int16))                          # empty batch is a no-op
+    assert r.argmax_ids.shape[0] == 0
+
+
+def test_lightning_asr_dropin(packed_weights, golden, meta):
+    """The reference call pattern (streaming_server.py:324-326, :420-435, :514-515, :530) on the shim."""
+    import torch
+    from asr_streaming_b200 import LightningASR, PRECISION_EXACT, greedy_search
+    case, mc = golden("seq_reset_skip"), meta["cases"]["seq_reset_skip"]
+    model = LightningASR(weights=packed_weights, cfg=model_cfg(PRECISION_EXACT, max_batch=4, max_sessions=8), vocab=meta["vocab"])
+    state_init = model.init_state()
+    state, emission = state_init, torch.Tensor([])
+    audio = torch.cat([torch.zeros(3200), torch.from_numpy(to_float(case["pcm"]))])
+    k = j = 0
+    while audio.numel() >= 13440:
+        if k in mc["reset_before"]:
+            emission, state = torch.Tensor([]), state_init
+        if k not in mc["skip"]:
+            em, length, states = model.stream([audio[None, :13440]], 16000, [state])
+            state = states[0]
+            assert int(length[0]) == 16
+            emission = torch.cat((emission, em[0]))
+            text, last_blank = greedy_search(emission)
+            assert text == mc["texts"][j]
+            assert abs(last_blank - case["last_blank"][j]) < 1e-7
+            assert np.abs(em[0].numpy() - case["emission"][j]).max() < EXACT_TOL
+            j += 1
+        audio = audio[10240:]
+        k += 1
+    assert j == mc["n_chunks"]

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import lightspeech_oracle as O
-from tests.helpers import chunks_i16, margins, model_cfg, to_float
+from helpers import chunks_i16, margins, model_cfg, to_float
 
 pytestmark = pytest.mark.gpu
 

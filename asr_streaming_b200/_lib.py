@@ -54,6 +54,8 @@ SIGNATURES = {
     "asr_fbank_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "asr_stage_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "asr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(AsrStatsC)]),
+    "asr_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "asr_debug_step_partial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "asr_debug_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]),
     "asr_debug_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),

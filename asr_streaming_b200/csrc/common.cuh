@@ -146,7 +146,7 @@ struct EpiOperand {
 // K/V of right-context rows -> per-step scratch (never cached, :314-315).
 template <typename T>
 struct EpiQKV {
-  float* q;              // [M, d]
+  T* q;                  // [M, d]  (same element type as the K/V cache: bf16 in FAST, fp32 in EXACT)
   T* cache_layer;        // cache + layer * (2 * ring * d)
   size_t slot_stride;    // elements per session slot
   T* rc;                 // [B, 2, rc_rows, d]
@@ -158,23 +158,22 @@ struct EpiQKV {
   __device__ __forceinline__ void store(int row, int col0, float (&v)[32]) const {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += bias[col0 + j];
+    T* dst;
     if (col0 < d) {
-      float* o = q + (size_t)row * d + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(v[j] * qscale, v[j + 1] * qscale, v[j + 2] * qscale, v[j + 3] * qscale);
-      return;
-    }
+      for (int j = 0; j < 32; ++j) v[j] *= qscale;
+      dst = q + (size_t)row * d + col0;
+    } else {
     const int which = col0 >= 2 * d;
     const int c = col0 - d - which * d;
     const int b = row / rows, t = row - b * rows;
-    T* dst;
     if (t < seg_rows) {
       const int slot = slots[b];
       const int rr = (past_len[slot] + t) % ring;
       dst = cache_layer + (size_t)slot * slot_stride + ((size_t)which * ring + rr) * d + c;
     } else {
       dst = rc + (((size_t)b * 2 + which) * rc_rows + (t - seg_rows)) * d + c;
+    }
     }
     if (sizeof(T) == 4) {
 #pragma unroll

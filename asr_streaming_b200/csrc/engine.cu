@@ -97,6 +97,14 @@ struct AsrEngine {
   size_t h_stage_bytes = 0;
   size_t h_out_off = 0;
 
+  // per-kernel-family CUDA-event profiling (bench.py roofline): pairs recorded on the launching stream
+  int prof_on = 0;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[ASR_PROF_COUNT] = {0};
+  uint64_t prof_n[ASR_PROF_COUNT] = {0};
+
   // stats
   uint64_t steps = 0, stream_chunks = 0, launches = 0;
   std::vector<float> step_ms;
@@ -252,10 +260,28 @@ int pick_bn(const AsrEngine* e, int M, int N) {
   return last;
 }
 
+cudaEvent_t prof_event(AsrEngine* e) {
+  if (!e->prof_pool.empty()) { cudaEvent_t ev = e->prof_pool.back(); e->prof_pool.pop_back(); return ev; }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+struct ProfScope {       // brackets one kernel launch with events when profiling is on; counts the launch always
+  AsrEngine* e; int cat; cudaEvent_t a = nullptr;
+  ProfScope(AsrEngine* e_, int cat_) : e(e_), cat(cat_) {
+    ++e->launches;
+    if (e->prof_on) { a = prof_event(e); cudaEventRecord(a, e->stream); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEvent_t b = prof_event(e); cudaEventRecord(b, e->stream); e->prof_recs.push_back({cat, a, b}); }
+  }
+};
+
 template <class Epi>
-int run_gemm(AsrEngine* e, const Operand& a, const WeightMat& w, int M, const Epi& epi) {
+int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const Epi& epi) {
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
-  ++e->launches;
+  ProfScope ps(e, cat);
   if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
   const int bn = pick_bn(e, M, w.N);
   return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
@@ -271,28 +297,26 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     const LayerW& L = e->layers[l];
     T* cache_layer = e->kv_cache.as<T>() + (size_t)l * 2 * g.ring * d;
     EpiQKV<T> eq;
-    eq.q = e->q.as<float>(); eq.cache_layer = cache_layer; eq.slot_stride = e->slot_stride; eq.rc = e->rc_kv.as<T>();
+    eq.q = e->q.as<T>(); eq.cache_layer = cache_layer; eq.slot_stride = e->slot_stride; eq.rc = e->rc_kv.as<T>();
     eq.bias = L.bqkv; eq.slots = slots; eq.past_len = e->past_len.as<int>();
     eq.rows = g.rows; eq.seg_rows = g.seg_rows; eq.rc_rows = g.rc_rows; eq.ring = g.ring; eq.d = d;
     eq.qscale = 1.0f / sqrtf((float)(d / g.n_heads));                                   // TA:emformer.py:108
-    if (run_gemm(e, e->a_ln, L.qkv, M, eq)) return -1;
+    if (run_gemm(e, ASR_PROF_GEMM_QKV, e->a_ln, L.qkv, M, eq)) return -1;
 
     AttnParams<T> ap;
-    ap.q = e->q.as<float>(); ap.cache_layer = cache_layer; ap.slot_stride = e->slot_stride; ap.rc = e->rc_kv.as<T>();
+    ap.q = e->q.as<T>(); ap.cache_layer = cache_layer; ap.slot_stride = e->slot_stride; ap.rc = e->rc_kv.as<T>();
     ap.slots = slots; ap.past_len = e->past_len.as<int>(); ap.out = e->a_attn.buf.as<bf16>(); ap.ld = e->a_attn.ld; ap.lo_off = e->a_attn.lo_off;
     ap.rows = g.rows; ap.seg_rows = g.seg_rows; ap.rc_rows = g.rc_rows; ap.ring = g.ring; ap.left = g.left; ap.d = d; ap.n_heads = g.n_heads;
-    ++e->launches;
-    if (attention_launch<T>(ap, n, e->stream)) return -1;
+    { ProfScope ps(e, ASR_PROF_ATTN); if (attention_launch<T>(ap, n, e->stream)) return -1; }
 
     EpiF32 eo{e->x1.as<float>(), L.bo, e->x.as<float>(), d, d};                          // out_proj + residual (pre-LN input)
-    if (run_gemm(e, e->a_attn, L.o, M, eo)) return -1;
-    ++e->launches;
-    if (ln_to_operand(e->x1.as<float>(), L.ln_ff_g, L.ln_ff_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, d, e->stream)) return -1;
+    if (run_gemm(e, ASR_PROF_GEMM_OUT, e->a_attn, L.o, M, eo)) return -1;
+    { ProfScope ps(e, ASR_PROF_LN); if (ln_to_operand(e->x1.as<float>(), L.ln_ff_g, L.ln_ff_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, d, e->stream)) return -1; }
     EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
-    if (run_gemm(e, e->a_ln, L.w1, M, e1)) return -1;
+    if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1)) return -1;
     EpiF32 e2{e->x2.as<float>(), L.b2, e->x1.as<float>(), d, d};
-    if (run_gemm(e, e->a_h, L.w2, M, e2)) return -1;
-    ++e->launches;
+    if (run_gemm(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
+    ProfScope ps_ln(e, ASR_PROF_LN);
     const bool last = l == g.n_layers - 1;
     if (last) {
       if (ln_out_fused(e->x2.as<float>(), L.ln_out_g, L.ln_out_b, e->x.as<float>(), nullptr, nullptr, e->a_enc.buf.as<bf16>(), e->a_enc.ld,
@@ -319,7 +343,7 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
   P.mel_start = pl.mel_start.as<int>(); P.mel_cnt = pl.mel_cnt.as<int>(); P.mel_off = pl.mel_off.as<int>(); P.mel_w = pl.mel_w.as<float>();
   P.n_mels = g.n_mels; P.out_f32 = out_f32;
   P.out_op = to_operand ? e->a_fb.buf.as<bf16>() : nullptr; P.op_ld = e->a_fb.ld; P.op_lo_off = e->a_fb.lo_off;
-  ++e->launches;
+  ProfScope ps(e, ASR_PROF_FBANK);
   return fbank_launch(P, n, e->stream);
 }
 
@@ -328,25 +352,25 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
   // input_linear (encoder.py:142, no bias); its [n*frames, d/stride] output *is* the time-reduced [n*rows, d] (common.py:118-119)
   EpiF32 ein{e->x.as<float>(), nullptr, nullptr, g.d_model / g.stride, g.d_model / g.stride};
-  if (run_gemm(e, e->a_fb, e->w_in, n * g.frames, ein)) return -1;
+  if (run_gemm(e, ASR_PROF_GEMM_IN, e->a_fb, e->w_in, n * g.frames, ein)) return -1;
   const int M = n * g.rows;
-  ++e->launches;
-  if (ln_to_operand(e->x.as<float>(), e->layers[0].ln_in_g, e->layers[0].ln_in_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, g.d_model,
-                    e->stream)) return -1;
+  { ProfScope ps(e, ASR_PROF_LN);
+    if (ln_to_operand(e->x.as<float>(), e->layers[0].ln_in_g, e->layers[0].ln_in_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, g.d_model,
+                      e->stream)) return -1; }
   if (g.split ? run_layers<float>(e, n, n_layers_to_run) : run_layers<bf16>(e, n, n_layers_to_run)) return -1;
   if (!with_ctc) return 0;
   const int Mc = n * g.seg_rows;
   EpiOperand ec1{e->a_ctc.buf.as<bf16>(), e->ctc_b1, e->a_ctc.ld, e->a_ctc.lo_off, ACT_SILU};    // decoder.py:67
-  if (run_gemm(e, e->a_enc, e->ctc1, Mc, ec1)) return -1;
+  if (run_gemm(e, ASR_PROF_GEMM_CTC1, e->a_enc, e->ctc1, Mc, ec1)) return -1;
   EpiF32 ec2{e->logits.as<float>(), e->ctc_b2, nullptr, g.vocab, g.vocab};                        // decoder.py:68
-  if (run_gemm(e, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
+  if (run_gemm(e, ASR_PROF_GEMM_CTC2, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
   CtcParams cp;
   cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->d_slots.as<int>();
   cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
   cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
   cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>();
   cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
-  ++e->launches;
+  ProfScope ps(e, ASR_PROF_CTC);
   return ctc_greedy_launch(cp, n, e->stream);
 }
 
@@ -427,6 +451,8 @@ void destroy_engine(AsrEngine* e) {
   for (FbankPlan* pl : {&e->mel128, &e->kaldi80}) {
     pl->window.free(); pl->tw.free(); pl->w2.free(); pl->mel_start.free(); pl->mel_cnt.free(); pl->mel_off.free(); pl->mel_w.free();
   }
+  for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -540,10 +566,9 @@ int run_fbank_kind(AsrEngine* e, int kind, int n, int fmt, int n_samples, int su
   P.n_mels = pl.n_mels; P.out_f32 = d_out; P.out_op = nullptr;
   *n_frames_out = P.n_frames;
   if ((size_t)n * P.n_frames * P.n_mels * 4 > e->fb_f32.bytes) { set_error("kaldi80: output exceeds the feature buffer"); return -1; }
-  ++e->launches;
-  if (fbank_launch(P, n, e->stream)) return -1;
+  { ProfScope ps(e, ASR_PROF_FBANK); if (fbank_launch(P, n, e->stream)) return -1; }
   if (subtract_mean) {
-    ++e->launches;
+    ProfScope ps(e, ASR_PROF_FBANK);
     if (subtract_mean_launch(d_out, n, P.n_frames, P.n_mels, e->stream)) return -1;
   }
   return 0;
@@ -734,6 +759,32 @@ int asr_get_stats(AsrEngine* e, AsrStats* out) {
     out->step_ms_p50 = v[v.size() / 2];
     out->step_ms_p99 = v[std::min(v.size() - 1, (size_t)(0.99 * v.size()))];
     out->step_ms_max = v.back();
+  }
+  return 0;
+}
+
+int asr_profile_enable(AsrEngine* e, int32_t on) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->prof_on = on != 0;
+  return 0;
+}
+
+int asr_profile_read(AsrEngine* e, double* ms, uint64_t* launches) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (auto& r : e->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { e->prof_ms[r.cat] += t; ++e->prof_n[r.cat]; }
+    e->prof_pool.push_back(r.a); e->prof_pool.push_back(r.b);
+  }
+  e->prof_recs.clear();
+  for (int i = 0; i < ASR_PROF_COUNT; ++i) {
+    if (ms) ms[i] = e->prof_ms[i];
+    if (launches) launches[i] = e->prof_n[i];
+    e->prof_ms[i] = 0; e->prof_n[i] = 0;
   }
   return 0;
 }

@@ -41,7 +41,7 @@ int ln_out_fused(const float* x2, const float* g1, const float* b1, float* y, co
 // ---------------------------------------------------------------- chunk attention over the ring KV cache
 template <typename T>
 struct AttnParams {
-  const float* q;          // [M, d], already scaled
+  const T* q;              // [M, d], already scaled by d_h^-0.5
   const T* cache_layer;    // cache + layer*(2*ring*d)
   size_t slot_stride;
   const T* rc;             // [B, 2, rc_rows, d]

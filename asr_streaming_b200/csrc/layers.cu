@@ -1,4 +1,6 @@
 // Memory-bound fused kernels of the Emformer layer and the CTC decode.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace asr {
@@ -145,7 +147,8 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_kernel(AttnParams<T> 
 
   for (int i = lane; i < ROWS * (AT_DH / 4); i += 32) {
     const int r = i / (AT_DH / 4), c = (i - r * (AT_DH / 4)) * 4;
-    *reinterpret_cast<float4*>(s_q + r * AT_DH + c) = *reinterpret_cast<const float4*>(P.q + ((size_t)b * ROWS + r) * P.d + head * AT_DH + c);
+    const T* qs = P.q + ((size_t)b * ROWS + r) * P.d + head * AT_DH + c;
+    *reinterpret_cast<float4*>(s_q + r * AT_DH + c) = make_float4(to_f32<T>(qs[0]), to_f32<T>(qs[1]), to_f32<T>(qs[2]), to_f32<T>(qs[3]));
   }
   stage_rows<T>(P, cache_slot, rc_b, 0, head, lv, pl, n_keys, s_kv, lane);
   __syncwarp();
@@ -206,6 +209,200 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_kernel(AttnParams<T> 
       o[P.lo_off + lane + 32] = __float2bfloat16_rn(o1[i] - __bfloat162float(h1));
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// FAST-mode chunk attention on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate).
+// One CTA per stream, one warp per head.  The whole K and V row set of the stream (valid left context +
+// segment rows from the ring, right-context rows from scratch; full 512-wide rows = 1 KB each) is brought into
+// shared memory with 16-byte cp.async in one go, so the ~105 KB per stream is in flight at once and each byte of
+// the K/V ring is read from HBM exactly once per layer.  Rows are padded to 1040 B: bank = (4*key + word) % 32,
+// conflict-free for the B-fragment loads of QK^T and for ldmatrix.trans of V.  S = QK^T lives in registers
+// (2 m-tiles x 8 n-tiles), softmax in fp32 on the fragments, P re-used as the A fragments of P*V.
+// ------------------------------------------------------------------------------------------
+constexpr int AM_ROWB = 1040;                 // bytes per staged K/V row (512 bf16 + 16 B pad)
+constexpr int AM_WARPS = 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(AM_WARPS * 32, 2) attention_mma_kernel(AttnParams<bf16> P) {
+  extern __shared__ __align__(16) uint8_t am_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int b = blockIdx.x, head = warp;
+  const int slot = P.slots[b];
+  const int pl = P.past_len[slot];
+  const int lv = pl < P.left ? pl : P.left;
+  const int n_keys = lv + P.seg_rows + P.rc_rows;            // <= 64
+  const int kmax = P.left + P.seg_rows + P.rc_rows;
+  uint8_t* s_k = am_smem;                                     // [kmax][1040]
+  uint8_t* s_v = s_k + (size_t)kmax * AM_ROWB;                // [kmax][1040]
+  uint8_t* s_zero = s_v + (size_t)kmax * AM_ROWB;             // one zero row for keys >= n_keys
+  const bf16* cache_slot = P.cache_layer + (size_t)slot * P.slot_stride;
+  const bf16* rc_b = P.rc + (size_t)b * 2 * P.rc_rows * P.d;
+
+  // ---- stage K and V rows: n_keys rows x 64 chunks of 16 B each, for K then V
+  const int chunks = n_keys * 64;
+  for (int i = tid; i < 2 * chunks; i += AM_WARPS * 32) {
+    const int which = i >= chunks;
+    const int r = (i - which * chunks) >> 6, c = (i & 63);
+    const bf16* src;
+    if (r < lv + P.seg_rows) {
+      const int rr = (pl - lv + r + P.ring) % P.ring;
+      src = cache_slot + ((size_t)which * P.ring + rr) * P.d;
+    } else {
+      src = rc_b + ((size_t)which * P.rc_rows + (r - lv - P.seg_rows)) * P.d;
+    }
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared((which ? s_v : s_k) + (size_t)r * AM_ROWB + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + c * 8) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < AM_ROWB / 16; i += AM_WARPS * 32) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
+
+  // ---- Q fragments straight from global (bf16, already scaled): rows >= ROWS are zero padding
+  uint32_t qa[2][4][4];                                       // [m-tile][k-step][reg]
+  const bf16* qb = P.q + (size_t)b * ROWS * P.d + head * AT_DH;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8, c0 = ks * 16 + 2 * tig;
+      qa[mt][ks][0] = r0 < ROWS ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * P.d + c0) : 0u;
+      qa[mt][ks][1] = r1 < ROWS ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * P.d + c0) : 0u;
+      qa[mt][ks][2] = r0 < ROWS ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * P.d + c0 + 8) : 0u;
+      qa[mt][ks][3] = r1 < ROWS ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * P.d + c0 + 8) : 0u;
+    }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- S = Q K^T
+  float sc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (nt * 8 < n_keys) {                                     // warp-uniform
+      int key = nt * 8 + g;
+      key = key < n_keys ? key : n_keys - 1;                    // clamp: garbage columns are masked below
+      const uint8_t* kr = s_k + (size_t)key * AM_ROWB + head * (AT_DH * 2) + tig * 4;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
+        mma_bf16_16816(sc[0][nt], qa[0][ks], b0, b1);
+        mma_bf16_16816(sc[1][nt], qa[1][ks], b0, b1);
+      }
+    }
+  }
+  // ---- softmax over keys, fp32, per query row (rows g and g+8 of each m-tile); 4 lanes share a row
+  uint32_t pa[2][4][4];                                        // P as A fragments: [m-tile][k-step of 16 keys][reg]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {                           // hr = 0: row g (regs 0,1), hr = 1: row g+8 (regs 2,3)
+      float m = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool valid = nt * 8 + 2 * tig + e < n_keys;
+          float& x = sc[mt][nt][2 * hr + e];
+          x = valid ? x : -INFINITY;
+          m = fmaxf(m, x);
+        }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& x = sc[mt][nt][2 * hr + e];
+          x = __expf(x - m);                                   // exp(-inf) = 0 for masked keys
+          sum += x;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[mt][nt][2 * hr] *= inv;
+        sc[mt][nt][2 * hr + 1] *= inv;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      pa[mt][kk][0] = pack_bf16x2(sc[mt][2 * kk][0], sc[mt][2 * kk][1]);
+      pa[mt][kk][1] = pack_bf16x2(sc[mt][2 * kk][2], sc[mt][2 * kk][3]);
+      pa[mt][kk][2] = pack_bf16x2(sc[mt][2 * kk + 1][0], sc[mt][2 * kk + 1][1]);
+      pa[mt][kk][3] = pack_bf16x2(sc[mt][2 * kk + 1][2], sc[mt][2 * kk + 1][3]);
+    }
+  }
+  // ---- O = P V : B fragments of V via ldmatrix.x4.trans (two 8-dim n-tiles per instruction)
+  float oc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oc[mt][dn][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    if (kk * 16 < n_keys) {                                     // warp-uniform
+      // lane -> (matrix id = lane/8, row in matrix = lane%8): matrices 0,1 = keys +0..7, +8..15 at dims dn; 2,3 = same keys at dims dn+1
+      const int mi = lane >> 3, ri = lane & 7;
+      const int key = kk * 16 + (mi & 1) * 8 + ri;
+      const uint8_t* row = key < n_keys ? s_v + (size_t)key * AM_ROWB : s_zero - head * (AT_DH * 2);   // zero row for padded keys
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {                          // pairs of 8-dim tiles
+        const uint8_t* src = (key < n_keys ? row + head * (AT_DH * 2) : s_zero) + (key < n_keys ? (dp * 2 + (mi >> 1)) * 16 : 0);
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(src);
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+        mma_bf16_16816(oc[0][2 * dp], pa[0][kk], v0, v1);
+        mma_bf16_16816(oc[1][2 * dp], pa[1][kk], v0, v1);
+        mma_bf16_16816(oc[0][2 * dp + 1], pa[0][kk], v2, v3);
+        mma_bf16_16816(oc[1][2 * dp + 1], pa[1][kk], v2, v3);
+      }
+    }
+  }
+  // ---- write the A operand of out_proj (bf16; FAST mode has no lo half)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r = mt * 16 + hr * 8 + g;
+      if (r < ROWS) {
+        bf16* o = P.out + ((size_t)b * ROWS + r) * P.ld + head * AT_DH + 2 * tig;
+#pragma unroll
+        for (int dn = 0; dn < 8; ++dn)
+          *reinterpret_cast<uint32_t*>(o + dn * 8) = pack_bf16x2(oc[mt][dn][2 * hr], oc[mt][dn][2 * hr + 1]);
+      }
+    }
+}
+
+template <int ROWS>
+int attention_mma_launch(const AttnParams<bf16>& P, int n_streams, cudaStream_t st) {
+  const int kmax = P.left + P.seg_rows + P.rc_rows;
+  const size_t smem = (size_t)(2 * kmax + 1) * AM_ROWB;
+  static size_t attr = 0;
+  if (smem > attr) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  attention_mma_kernel<ROWS><<<n_streams, AM_WARPS * 32, smem, st>>>(P);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 template <typename T, int ROWS>
@@ -336,6 +533,12 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
   if (P.d != P.n_heads * AT_DH || P.n_heads % AT_WARPS != 0 || P.left + P.seg_rows + P.rc_rows > AT_MAXK) {
     set_error("attention: unsupported geometry (d %d heads %d keys %d)", P.d, P.n_heads, P.left + P.seg_rows + P.rc_rows);
     return -1;
+  }
+  if constexpr (sizeof(T) == 2) {
+    if (P.n_heads == AM_WARPS && P.d == 512 && P.lo_off == 0 && !getenv("ASR_B200_DEBUG_SIMT_ATTENTION")) {
+      if (P.rows == 20) return attention_mma_launch<20>(P, n_streams, st);
+      if (P.rows == 12) return attention_mma_launch<12>(P, n_streams, st);
+    }
   }
   if (P.rows == 20) return attention_launch_rows<T, 20>(P, n_streams, st);
   if (P.rows == 12) return attention_launch_rows<T, 12>(P, n_streams, st);

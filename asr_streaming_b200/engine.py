@@ -178,6 +178,20 @@ class Engine:
         _lib.check(self.lib, self.lib.asr_get_stats(self._h, C.byref(s)), "asr_get_stats")
         return {k: getattr(s, k) for k, _ in _lib.AsrStatsC._fields_}
 
+    PROF_NAMES = ("fbank", "gemm_input_linear", "layernorm", "gemm_qkv", "attention", "gemm_out_proj", "gemm_ffn1", "gemm_ffn2",
+                  "gemm_ctc1", "gemm_ctc2", "ctc_greedy", "beam")
+
+    def profile_enable(self, on: bool) -> None:
+        _lib.check(self.lib, self.lib.asr_profile_enable(self._h, int(on)), "asr_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{family: (total_ms, launches)} accumulated since the last read (device time, CUDA events on the engine stream)."""
+        n = len(self.PROF_NAMES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        _lib.check(self.lib, self.lib.asr_profile_read(self._h, ms, cnt), "asr_profile_read")
+        return {self.PROF_NAMES[i]: (ms[i], int(cnt[i])) for i in range(n)}
+
     def debug_step_partial(self, slots: Sequence[int], pcm: np.ndarray, n_layers: int) -> None:
         sl = np.ascontiguousarray(slots, dtype=np.int32)
         a, fmt = self._pcm(pcm, int(sl.size))

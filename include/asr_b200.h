@@ -124,6 +124,14 @@ ASR_API int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes);
 
 ASR_API int asr_get_stats(AsrEngine* e, AsrStats* out);
 
+/* Per-kernel-family device time, measured with CUDA events recorded on the engine stream around every launch while
+ * enabled.  asr_profile_read synchronises, returns accumulated milliseconds / launch counts per family since the last
+ * read, and clears them.  (bench.py's roofline leg; off by default.) */
+enum { ASR_PROF_FBANK = 0, ASR_PROF_GEMM_IN, ASR_PROF_LN, ASR_PROF_GEMM_QKV, ASR_PROF_ATTN, ASR_PROF_GEMM_OUT, ASR_PROF_GEMM_FFN1,
+       ASR_PROF_GEMM_FFN2, ASR_PROF_GEMM_CTC1, ASR_PROF_GEMM_CTC2, ASR_PROF_CTC, ASR_PROF_BEAM, ASR_PROF_COUNT };
+ASR_API int asr_profile_enable(AsrEngine* e, int32_t on);
+ASR_API int asr_profile_read(AsrEngine* e, double* ms, uint64_t* launches);
+
 /* ---- diagnostics used by tests (not part of the serving path) ---- */
 /* Runs the step but stops after `n_layers` encoder layers (no CTC, no state advance); buffers readable below. */
 ASR_API int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t n_layers);

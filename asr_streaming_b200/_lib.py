@@ -50,6 +50,7 @@ SIGNATURES = {
     "asr_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
     "asr_sync": (C.c_int, [C.c_void_p]),
     "asr_stream_handle": (C.c_void_p, [C.c_void_p]),
+    "asr_pinned_pcm": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "asr_fbank": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "asr_fbank_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "asr_stage_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -87,12 +87,28 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA, branch-free.
+// The GELU epilogue of FFN1 runs once per output of a K=512 GEMM, i.e. it has ~16 issue slots per element before it,
+// not the tensor pipe, bounds the kernel; libdevice erff costs about twice this.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------
-// GEMM epilogues.  Each gets one accumulator row fragment of 32 consecutive columns
-// (row < M guaranteed by the caller) — the shape a tcgen05.ld 32x32b.x32 delivers per thread.
+// GEMM epilogues.  One thread owns one accumulator row (the shape tcgen05.ld 32x32b delivers) and gets it in
+// fragments of 32 consecutive columns; every global access is a 16-byte vector.  Anything that depends only on
+// the row (destination of a K/V row in the session ring) is computed once per tile (RowCtx).
+// (Measured on B200: a shared-memory transpose to lane = column with 4-byte accesses doubles the epilogue time;
+//  profiles/r01_notes.md.)
 // ------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
@@ -103,16 +119,23 @@ struct EpiF32 {
   const float* res;    // nullable, same ld as out
   int ld;
   int n_valid;
-  __device__ __forceinline__ void store(int row, int col0, float (&v)[32]) const {
+  typedef int RowCtx;
+  __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
+  __device__ __forceinline__ void store(int row, int col0, float (&v)[32], RowCtx) const {
     float* o = out + (size_t)row * ld + col0;
     const float* r = res ? res + (size_t)row * ld + col0 : nullptr;
     if (col0 + 32 <= n_valid) {
+      float4 rr[8];
+      if (r) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (bias) { float4 b = *reinterpret_cast<const float4*>(bias + col0 + j); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
-        if (r) { float4 q = *reinterpret_cast<const float4*>(r + j); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
-        *reinterpret_cast<float4*>(o + j) = t;
+        for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(r + 4 * j);      // all loads in flight first
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
+        if (r) { t.x += rr[j].x; t.y += rr[j].y; t.z += rr[j].z; t.w += rr[j].w; }
+        *reinterpret_cast<float4*>(o + 4 * j) = t;
       }
     } else {
 #pragma unroll
@@ -129,21 +152,31 @@ struct EpiOperand {
   int ld;       // elements per row (N, or 2N when split)
   int lo_off;   // 0 or N
   int act;
-  __device__ __forceinline__ void store(int row, int col0, float (&v)[32]) const {
+  typedef int RowCtx;
+  __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
+  __device__ __forceinline__ void store(int row, int col0, float (&v)[32], RowCtx) const {
     bf16* o = out + (size_t)row * ld;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = v[j] + bias[col0 + j];
-      v[j] = act == ACT_GELU ? gelu_erf(x) : (act == ACT_SILU ? silu(x) : x);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (act == ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
     }
 #pragma unroll
     for (int j = 0; j < 32; j += 8) store_operand8(o, col0 + j, lo_off, &v[j]);
   }
 };
 
-// Fused Q | K | V projection (TA:emformer.py:161,:164): q scaled by d_h^-0.5 (:188) -> fp32 buffer;
+// Fused Q | K | V projection (TA:emformer.py:161,:164): q scaled by d_h^-0.5 (:188);
 // K/V of the segment rows -> the session's ring slot (replaces _pack_state cat+slice, :400-414);
-// K/V of right-context rows -> per-step scratch (never cached, :314-315).
+// K/V of right-context rows -> per-step scratch (never cached, :314-315).  A tile never straddles the q|k|v
+// sections (d % BN == 0), so the destination row pointer is a per-tile, per-row constant.
 template <typename T>
 struct EpiQKV {
   T* q;                  // [M, d]  (same element type as the K/V cache: bf16 in FAST, fp32 in EXACT)
@@ -155,26 +188,28 @@ struct EpiQKV {
   const int* past_len;   // [n_slots]
   int rows, seg_rows, rc_rows, ring, d;
   float qscale;
-  __device__ __forceinline__ void store(int row, int col0, float (&v)[32]) const {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += bias[col0 + j];
-    T* dst;
-    if (col0 < d) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= qscale;
-      dst = q + (size_t)row * d + col0;
-    } else {
-    const int which = col0 >= 2 * d;
-    const int c = col0 - d - which * d;
+  typedef T* RowCtx;                          // column 0 of this tile's section (q | k | v) in the destination row
+  __device__ __forceinline__ RowCtx row_ctx(int row, int tile_col0) const {
+    const int sec = tile_col0 / d;            // 0: q, 1: k, 2: v
+    if (sec == 0) return q + (size_t)row * d;
+    const int which = sec - 1;
     const int b = row / rows, t = row - b * rows;
     if (t < seg_rows) {
       const int slot = slots[b];
       const int rr = (past_len[slot] + t) % ring;
-      dst = cache_layer + (size_t)slot * slot_stride + ((size_t)which * ring + rr) * d + c;
-    } else {
-      dst = rc + (((size_t)b * 2 + which) * rc_rows + (t - seg_rows)) * d + c;
+      return cache_layer + (size_t)slot * slot_stride + ((size_t)which * ring + rr) * d;
     }
+    return rc + (((size_t)b * 2 + which) * rc_rows + (t - seg_rows)) * d;
+  }
+  __device__ __forceinline__ void store(int, int col0, float (&v)[32], RowCtx dst_row) const {
+    const int sec = col0 / d;
+    const float sc = sec == 0 ? qscale : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+      v[j] = (v[j] + b.x) * sc; v[j + 1] = (v[j + 1] + b.y) * sc; v[j + 2] = (v[j + 2] + b.z) * sc; v[j + 3] = (v[j + 3] + b.w) * sc;
     }
+    T* dst = dst_row + (col0 - sec * d);
     if (sizeof(T) == 4) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)

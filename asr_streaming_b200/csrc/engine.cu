@@ -393,7 +393,7 @@ int stage_inputs(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int
   ASR_CUDA_OK(cudaSetDevice(e->device));
   const size_t pb = pcm_bytes(e, n, fmt);
   uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_stage);
-  memcpy(hs, pcm, pb);
+  if (pcm != hs) memcpy(hs, pcm, pb);                      // asr_pinned_pcm callers filled the staging buffer themselves
   memcpy(hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), slots, 4 * (size_t)n);
   ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, hs, pb, cudaMemcpyHostToDevice, e->stream));
   ASR_CUDA_OK(cudaMemcpyAsync(e->d_slots.p, hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
@@ -697,6 +697,12 @@ int asr_sync(AsrEngine* e) {
 }
 
 void* asr_stream_handle(AsrEngine* e) { return e ? (void*)e->stream : nullptr; }
+
+void* asr_pinned_pcm(AsrEngine* e, uint64_t* capacity_bytes) {
+  if (!e) return nullptr;
+  if (capacity_bytes) *capacity_bytes = pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32);
+  return e->h_stage;
+}
 
 int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes) {
   if (!e || !pcm) { set_error("null argument"); return -1; }

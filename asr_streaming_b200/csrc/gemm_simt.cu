@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const bf16* __restrict__
       }
     }
   }
-  if (row < p.M) epi.store(row, col0, acc);
+  if (row < p.M) epi.store(row, col0, acc, epi.row_ctx(row, col0));
 }
 
 }  // namespace

@@ -8,8 +8,10 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN,
 //               K=16 per instruction), fp32 accumulators in TMEM, double-buffered (2 x BN columns);
 //               tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused
-//               bias / residual / GELU / SiLU / Q-scaling / KV-ring scatter, direct global stores.
+//   warps 2..9  epilogue, two warps per TMEM lane quarter alternating 32-column blocks (a single warp per SM
+//               sub-partition cannot hide the tcgen05.ld / residual-load latency: measured 2x): tcgen05.ld
+//               32x32b.x32 (one accumulator row per thread), fused bias / residual / GELU / SiLU / Q-scaling /
+//               KV-ring scatter, 16-byte global accesses.
 #include "gemm.cuh"
 
 namespace asr {
@@ -19,7 +21,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStagingBytes = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,7 +115,7 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;   // power of two for BN in {64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, class Epi>
@@ -120,7 +124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024B alignment
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + kStagingBytes;
   // barrier layout (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
@@ -139,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -200,21 +205,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int quarter = warp & 3;                           // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                               // which of the two warps sharing the quarter
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const typename Epi::RowCtx ctx = epi.row_ctx(row_ok ? row : p.M - 1, n_blk * BN);   // before the wait: overlaps the MMA
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N) epi.store(row, col0, v);
+        if (row_ok && col0 < p.N) epi.store(row, col0, v, ctx);
       }
       tc_fence_before();
       __syncwarp();

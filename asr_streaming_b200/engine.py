@@ -143,6 +143,17 @@ class Engine:
     def sync(self) -> None:
         _lib.check(self.lib, self.lib.asr_sync(self._h), "asr_sync")
 
+    def pinned_pcm(self, dtype=np.int16) -> np.ndarray:
+        """numpy view [max_batch, chunk_length] of the engine's pinned staging buffer: fill rows [0, n) in place and pass
+        ``view[:n]`` to step()/stage() — the host copy is skipped and the H2D DMA reads what the caller wrote."""
+        cap = C.c_uint64()
+        ptr = self.lib.asr_pinned_pcm(self._h, C.byref(cap))
+        if not ptr:
+            raise _lib.AsrLibraryError("asr_pinned_pcm failed")
+        n = self.cfg.max_batch * self.cfg.chunk_length
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(self.cfg.max_batch, self.cfg.chunk_length)
+
     @property
     def cuda_stream(self) -> int:
         return int(self.lib.asr_stream_handle(self._h) or 0)

@@ -67,7 +67,8 @@ class SessionScheduler:
         self.sessions: Dict[int, StreamSession] = {}
         self._next_id = 0
         self._rr: Deque[int] = deque()            # round-robin order so a backlog cannot starve old sessions
-        self._pack = np.empty((self.cfg.max_batch, self.cfg.chunk_length), np.int16)
+        # batch assembly happens directly in the engine's pinned staging buffer (no second host copy)
+        self._pack = engine.pinned_pcm(np.int16) if hasattr(engine, "pinned_pcm") else np.empty((self.cfg.max_batch, self.cfg.chunk_length), np.int16)
 
     def open(self) -> StreamSession:
         s = StreamSession(self._next_id, self.engine.open_session(), self.cfg)

@@ -112,6 +112,10 @@ ASR_API int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void*
 ASR_API int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs);
 ASR_API int asr_fetch(AsrEngine* e, int32_t n, const AsrStepOut* out);
 ASR_API int asr_sync(AsrEngine* e);
+/* Zero-copy input: the engine's pinned host staging buffer for PCM (capacity max_batch * chunk_length * 4 bytes).  A caller
+ * that assembles its batch directly in this buffer passes the returned pointer as `pcm` to asr_step / asr_stage and the
+ * host-side copy is skipped (the websocket receive path can write chunks straight into pinned memory). */
+ASR_API void* asr_pinned_pcm(AsrEngine* e, uint64_t* capacity_bytes);
 ASR_API void* asr_stream_handle(AsrEngine* e);      /* cudaStream_t the engine launches on (for CUDA-event timing) */
 
 /* Replaces extract_filterbank (lightspeech/datas/audio.py:9-30) [MELSPEC128 -> out [n, frames, 128]] and provides the

@@ -20,3 +20,15 @@ def model_cfg(precision, low_latency=False, max_batch=64, max_sessions=128):
 def margins(emission):
     s = np.sort(emission, axis=-1)
     return s[..., -1] - s[..., -2]
+
+
+def report(line):
+    """Appends a measured-error line to gpurun_out/parity_report.txt (kept as evidence under profiles/)."""
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.txt"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import lightspeech_oracle as O
-from helpers import chunks_i16, margins, model_cfg, to_float
+from helpers import chunks_i16, margins, model_cfg, report, to_float
 
 pytestmark = pytest.mark.gpu
 
@@ -39,6 +39,7 @@ def test_melspec128_vs_reference(engines, golden):
     out_i16 = e.fbank(fb["melspec_pcm"][None, :])[0]
     out_f32 = e.fbank(to_float(fb["melspec_pcm"])[None, :])[0]
     assert out_i16.shape == (80, 128)
+    report(f"melspec128 vs reference extract_filterbank: max-abs {np.abs(out_i16 - fb['melspec128']).max():.3e}; vs float64 oracle {np.abs(out_i16 - O.melspec128(to_float(fb['melspec_pcm']))).max():.3e}")
     assert np.array_equal(out_i16, out_f32)                    # int16 and float inputs are the same samples
     assert np.abs(out_i16 - fb["melspec128"]).max() < 2e-3
     assert np.abs(out_i16 - O.melspec128(to_float(fb["melspec_pcm"]))).max() < 2e-3
@@ -64,6 +65,7 @@ def test_kaldi80_vs_torchaudio(engines, golden):
     e = engines(engines.FAST)
     out = e.fbank(fb["kaldi_pcm"][None, :], kind=1)[0]
     assert out.shape == fb["kaldi80"].shape == (64, 80)
+    report(f"kaldi80 vs torchaudio.compliance.kaldi.fbank: max-abs {np.abs(out - fb['kaldi80']).max():.3e}")
     assert np.abs(out - fb["kaldi80"]).max() < 2e-3
     out_cmvn = e.fbank(fb["kaldi_pcm"][None, :], kind=1, subtract_mean=True)[0]
     assert np.abs(out_cmvn - fb["kaldi80_cmvn"]).max() < 2e-3
@@ -105,6 +107,7 @@ def test_exact_mode_matches_reference(name, engines, golden, meta):
     em, ids, blanks = _run_case(engines(engines.EXACT), case, mc)
     ref = case["emission"]
     assert em.shape == ref.shape
+    report(f"EXACT {name}: logprob max-abs {np.abs(em - ref).max():.3e}, argmax equal {int((em.argmax(2) == case['argmax']).sum())}/{case['argmax'].size}")
     assert np.abs(em - ref).max() < EXACT_TOL
     assert np.array_equal(em.argmax(2), case["argmax"])                       # bit-exact greedy ids, every frame
     for j in range(len(ids)):
@@ -118,6 +121,7 @@ def test_fast_mode_within_tolerance(name, engines, golden, meta):
     em, _, _ = _run_case(engines(engines.FAST), case, mc)
     ref = case["emission"]
     err = np.abs(em - ref).max()
+    report(f"FAST {name}: logprob max-abs {err:.3e}, argmax equal {int((em.argmax(2) == case['argmax']).sum())}/{case['argmax'].size}")
     assert err < FAST_TOL, f"bf16 path max-abs {err}"
     safe = margins(ref) > 2 * FAST_TOL
     assert safe.mean() > 0.3

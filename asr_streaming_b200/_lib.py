@@ -24,7 +24,8 @@ class AsrConfigC(C.Structure):
 
 class AsrStepOutC(C.Structure):
     _fields_ = [("argmax_ids", C.c_void_p), ("new_tokens", C.c_void_p), ("n_new", C.c_void_p), ("blank_frames", C.c_void_p),
-                ("has_token", C.c_void_p), ("logprobs", C.c_void_p)]
+                ("has_token", C.c_void_p), ("logprobs", C.c_void_p), ("beam_tokens", C.c_void_p), ("beam_len", C.c_void_p),
+                ("beam_score", C.c_void_p)]
 
 
 class AsrStatsC(C.Structure):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "asr_fbank": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "asr_fbank_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "asr_stage_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "asr_set_beam": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "asr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(AsrStatsC)]),
     "asr_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -93,6 +93,9 @@ struct AsrEngine {
   std::vector<uint8_t> slot_open;
   // outputs
   DevBuf d_argmax, d_newtok, d_nnew, d_blank, d_hastok, d_logprobs;
+  // prefix beam search (optional)
+  int beam = 0, cand_k = 0;
+  DevBuf bm_n, bm_cur, bm_len, bm_last, bm_pb, bm_pnb, bm_hash, bm_tokens, d_beam_tok, d_beam_len, d_beam_score;
   void* h_stage = nullptr;      // pinned: pcm + slots in, results out
   size_t h_stage_bytes = 0;
   size_t h_out_off = 0;
@@ -347,7 +350,18 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
   return fbank_launch(P, n, e->stream);
 }
 
+BeamParams beam_params(AsrEngine* e, int n) {
+  BeamParams P;
+  P.logprobs = e->d_logprobs.as<float>(); P.slots = e->d_slots.as<int>();
+  P.n = n; P.seg_rows = e->geo.seg_rows; P.vocab = e->geo.vocab; P.beam = e->beam; P.cand_k = e->cand_k; P.max_len = BEAM_MAX_LEN - 1;
+  P.n_beam = e->bm_n.as<int>(); P.cur = e->bm_cur.as<int>(); P.len = e->bm_len.as<int>(); P.last = e->bm_last.as<int>();
+  P.pb = e->bm_pb.as<float>(); P.pnb = e->bm_pnb.as<float>(); P.hash = e->bm_hash.as<unsigned long long>(); P.tokens = e->bm_tokens.as<int16_t>();
+  P.out_tokens = e->d_beam_tok.as<int>(); P.out_len = e->d_beam_len.as<int>(); P.out_score = e->d_beam_score.as<float>();
+  return P;
+}
+
 int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool with_ctc, bool want_logprobs) {
+  if (e->beam > 0) want_logprobs = true;
   const Geo& g = e->geo;
   if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
   // input_linear (encoder.py:142, no bias); its [n*frames, d/stride] output *is* the time-reduced [n*rows, d] (common.py:118-119)
@@ -370,8 +384,9 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
   cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>();
   cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
-  ProfScope ps(e, ASR_PROF_CTC);
-  return ctc_greedy_launch(cp, n, e->stream);
+  { ProfScope ps(e, ASR_PROF_CTC); if (ctc_greedy_launch(cp, n, e->stream)) return -1; }
+  if (e->beam > 0) { ProfScope ps(e, ASR_PROF_BEAM); if (beam_launch(beam_params(e, n), e->stream)) return -1; }
+  return 0;
 }
 
 int check_step_args(AsrEngine* e, int n, const int32_t* slots) {
@@ -417,6 +432,11 @@ int fetch_outputs(AsrEngine* e, int n, const AsrStepOut* out, bool sync_only) {
     add(out->blank_frames, e->d_blank, 4 * (size_t)n);
     add(out->has_token, e->d_hastok, 4 * (size_t)n);
     add(out->logprobs, e->d_logprobs, 4 * nS * g.vocab);
+    if (e->beam > 0) {
+      add(out->beam_tokens, e->d_beam_tok, 4 * (size_t)n * BEAM_MAX_LEN);
+      add(out->beam_len, e->d_beam_len, 4 * (size_t)n);
+      add(out->beam_score, e->d_beam_score, 4 * (size_t)n);
+    }
   }
   for (auto& it : items) ASR_CUDA_OK(cudaMemcpyAsync(ho + it.hoff, it.src, it.bytes, cudaMemcpyDeviceToHost, e->stream));
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -436,6 +456,7 @@ int reset_slot(AsrEngine* e, int slot) {
   ASR_CUDA_OK(cudaMemcpyAsync(e->n_frames.as<int>() + slot, &zero, 4, cudaMemcpyHostToDevice, e->stream));
   ASR_CUDA_OK(cudaMemcpyAsync(e->prev_id.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
   ASR_CUDA_OK(cudaMemcpyAsync(e->last_tok.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
+  if (e->beam > 0 && beam_reset_launch(beam_params(e, 0), slot, e->cfg.max_sessions, e->stream)) return -1;
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));     // the 4-byte host sources are stack variables
   return 0;
 }
@@ -446,7 +467,8 @@ void destroy_engine(AsrEngine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->d_pcm, &e->d_slots, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
-                    &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs};
+                    &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
+                    &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
   for (DevBuf* b : bufs) b->free();
   for (FbankPlan* pl : {&e->mel128, &e->kaldi80}) {
     pl->window.free(); pl->tw.free(); pl->w2.free(); pl->mel_start.free(); pl->mel_cnt.free(); pl->mel_off.free(); pl->mel_w.free();
@@ -533,7 +555,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     for (size_t i = 0; i < S; ++i) e->free_slots[i] = (int)(S - 1 - i);
     // ---- pinned staging: [pcm (f32 worst case) | slots | outputs]
     const size_t in_bytes = round_up(pcm_bytes(e, B, ASR_PCM_F32), 256) + round_up(4 * (size_t)B, 256);
-    const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 3 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256);
+    const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 5 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256) +
+                             round_up(4 * (size_t)B * BEAM_MAX_LEN, 256);
     e->h_out_off = in_bytes; e->h_stage_bytes = in_bytes + out_bytes;
     if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", e->h_stage_bytes); break; }
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("engine init: %s", cudaGetErrorString(cudaGetLastError())); break; }
@@ -749,6 +772,28 @@ int asr_fbank(AsrEngine* e, int32_t kind, int32_t n, const void* pcm, int32_t fm
   if (run_fbank_kind(e, kind, n, fmt, n_samples, subtract_mean, e->fb_f32.as<float>(), &nf)) return -1;
   ASR_CUDA_OK(cudaMemcpyAsync(out, e->fb_f32.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (beam < 0 || beam > BEAM_MAX || (beam > 0 && (cand_k < 1 || cand_k > BEAM_CAND_MAX))) {
+    set_error("asr_set_beam: beam must be in [0, %d], cand_k in [1, %d]", BEAM_MAX, BEAM_CAND_MAX); return -1;
+  }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  if (beam > 0 && !e->bm_tokens.p) {
+    const size_t S = e->cfg.max_sessions, B = e->cfg.max_batch;
+    if (e->bm_n.alloc(4 * S) || e->bm_cur.alloc(4 * S) || e->bm_len.alloc(4 * S * BEAM_MAX) || e->bm_last.alloc(4 * S * BEAM_MAX) ||
+        e->bm_pb.alloc(4 * S * BEAM_MAX) || e->bm_pnb.alloc(4 * S * BEAM_MAX) || e->bm_hash.alloc(8 * S * BEAM_MAX) ||
+        e->bm_tokens.alloc(2 * S * 2 * BEAM_MAX * BEAM_MAX_LEN) || e->d_beam_tok.alloc(4 * B * BEAM_MAX_LEN) || e->d_beam_len.alloc(4 * B) ||
+        e->d_beam_score.alloc(4 * B)) return -1;
+  }
+  e->beam = beam; e->cand_k = cand_k;
+  if (beam > 0) {
+    if (beam_reset_launch(beam_params(e, 0), -1, e->cfg.max_sessions, e->stream)) return -1;
+    ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
   return 0;
 }
 

@@ -73,6 +73,28 @@ struct CtcParams {
 };
 int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st);
 
+// ---------------------------------------------------------------- CTC prefix beam search (warp per stream)
+constexpr int BEAM_MAX = 16;         // beam width limit
+constexpr int BEAM_CAND_MAX = 8;     // extension candidates per frame limit
+constexpr int BEAM_MAX_LEN = 256;    // tokens per hypothesis (an utterance is force-ended at 40 s = 1000 frames, asr-online.yaml:103-107)
+struct BeamParams {
+  const float* logprobs;   // [n*seg_rows, vocab] of the current step
+  const int* slots;        // [n]
+  int n, seg_rows, vocab, beam, cand_k, max_len;
+  // per-slot state
+  int* n_beam; int* cur;               // [slots]
+  int* len; int* last;                 // [slots*BEAM_MAX]
+  float* pb; float* pnb;               // [slots*BEAM_MAX]
+  unsigned long long* hash;            // [slots*BEAM_MAX]
+  int16_t* tokens;                     // [slots][2][BEAM_MAX][BEAM_MAX_LEN]
+  // outputs of the step: best hypothesis so far per stream
+  int* out_tokens;         // [n*BEAM_MAX_LEN]
+  int* out_len;            // [n]
+  float* out_score;        // [n]
+};
+int beam_launch(const BeamParams& P, cudaStream_t st);
+int beam_reset_launch(const BeamParams& P, int slot /* -1: all */, int n_slots_all, cudaStream_t st);
+
 // fp32 [n] -> bf16 hi (+ lo) weight conversion at engine creation
 int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int lo_off, cudaStream_t st);
 int fill_i32(int* p, int v, size_t n, cudaStream_t st);

@@ -13,6 +13,7 @@ from .config import ModelConfig
 FRAMERATE = 0.04            # recognition.py:30
 PCM_I16, PCM_F32 = 0, 1
 FBANK_MELSPEC128, FBANK_KALDI80 = 0, 1
+BEAM_MAX_LEN = 256
 
 
 @dataclass
@@ -23,6 +24,8 @@ class StepResult:
     blank_frames: np.ndarray               # [n] int32
     has_token: np.ndarray                  # [n] bool
     logprobs: Optional[np.ndarray]         # [n, S, V] float32 or None
+    beam_tokens: Optional[List[np.ndarray]] = None   # n arrays: best prefix-beam hypothesis of the utterance so far
+    beam_score: Optional[np.ndarray] = None          # [n] log-probability of that hypothesis
 
     def last_blank(self, i: int) -> float:
         """The reference's ``last_blank`` (recognition.py:38-43): python float 0.04*T when the segment has no
@@ -58,6 +61,12 @@ class Engine:
         _lib.check(self.lib, self.lib.asr_engine_create(C.byref(self._c), w.ctypes.data, w.size, device, C.byref(h)), "asr_engine_create")
         self._h = h
         self.S = cfg.seg_rows
+        self.beam = 0
+
+    def set_beam(self, beam: int, cand_k: int = 8) -> None:
+        """Enable CTC prefix beam search (beam <= 16, cand_k <= 8) as part of every step; 0 disables."""
+        _lib.check(self.lib, self.lib.asr_set_beam(self._h, beam, cand_k), "asr_set_beam")
+        self.beam = beam
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -109,12 +118,21 @@ class Engine:
                     logprobs=np.empty((n, S, V), np.float32) if want_logprobs else None)
         o = _lib.AsrStepOutC(bufs["argmax"].ctypes.data, bufs["newtok"].ctypes.data, bufs["nnew"].ctypes.data, bufs["blank"].ctypes.data,
                              bufs["hastok"].ctypes.data, bufs["logprobs"].ctypes.data if want_logprobs else None)
+        if self.beam:
+            bufs["btok"] = np.empty((n, BEAM_MAX_LEN), np.int32)
+            bufs["blen"] = np.empty(n, np.int32)
+            bufs["bscore"] = np.empty(n, np.float32)
+            o.beam_tokens, o.beam_len, o.beam_score = bufs["btok"].ctypes.data, bufs["blen"].ctypes.data, bufs["bscore"].ctypes.data
         return bufs, o
 
     @staticmethod
     def _result(bufs, n) -> StepResult:
         new = [bufs["newtok"][i, :bufs["nnew"][i]].copy() for i in range(n)]
-        return StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"])
+        r = StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"])
+        if "btok" in bufs:
+            r.beam_tokens = [bufs["btok"][i, :bufs["blen"][i]].copy() for i in range(n)]
+            r.beam_score = bufs["bscore"]
+        return r
 
     def step(self, slots: Sequence[int], pcm: np.ndarray, want_logprobs: bool = False) -> StepResult:
         """One chunk for each of ``slots`` (any mix of progress).  pcm: [n, chunk_length] int16 or float32."""

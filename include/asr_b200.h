@@ -71,7 +71,13 @@ typedef struct AsrStepOut {     /* all pointers nullable, host memory, n = strea
   int32_t* blank_frames;        /* [n]    frames since the last id > 1, or all frames of the segment if none (:38-43) */
   int32_t* has_token;           /* [n]                                                                                */
   float* logprobs;              /* [n*S*vocab]  the reference's `emission` (recognition.py:203-204)                   */
+  /* CTC prefix beam search (only when asr_set_beam enabled it): best hypothesis of the utterance so far               */
+  int32_t* beam_tokens;         /* [n*ASR_BEAM_MAX_LEN]                                                               */
+  int32_t* beam_len;            /* [n]                                                                                */
+  float* beam_score;            /* [n]  log P(best prefix)                                                            */
 } AsrStepOut;
+
+#define ASR_BEAM_MAX_LEN 256
 
 typedef struct AsrStats {
   uint64_t steps;               /* asr_step calls                                  */
@@ -125,6 +131,12 @@ ASR_API int asr_fbank(AsrEngine* e, int32_t kind, int32_t n, const void* pcm, in
               float* out);
 ASR_API int asr_fbank_staged(AsrEngine* e, int32_t kind, int32_t n, int32_t pcm_format, int32_t n_samples);   /* kernels only, inputs from asr_stage_raw */
 ASR_API int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes);
+
+/* CTC prefix beam search as part of every step (north-star; BASELINE config #4: beam = 10).  beam = 0 disables it.
+ * beam <= 16, cand_k (extension candidates per frame) <= 8.  State is per session and is cleared by asr_session_reset.
+ * The reference has no CTC prefix beam (its final pass is the flashlight lexicon decoder, recognition.py:220-300):
+ * semantics = oracle/ctc_beam_oracle.py, parity unpinned. */
+ASR_API int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k);
 
 ASR_API int asr_get_stats(AsrEngine* e, AsrStats* out);
 

@@ -256,3 +256,32 @@ def test_lightning_asr_dropin(packed_weights, golden, meta):
         audio = audio[10240:]
         k += 1
     assert j == mc["n_chunks"]
+
+
+# ------------------------------------------------------------------------------------------------ prefix beam search
+def test_prefix_beam_kernel_matches_oracle(packed_weights, golden):
+    """Warp-per-stream CTC prefix beam (beam 10, 8 candidates/frame, state carried across chunks, ragged batch) vs
+    oracle/ctc_beam_oracle.py run on the very log-probs the device produced.  Parity unpinned vs the reference."""
+    from asr_streaming_b200 import Engine, PRECISION_EXACT
+    from oracle import ctc_beam_oracle as B
+    e = Engine(model_cfg(PRECISION_EXACT, max_batch=8, max_sessions=8), packed_weights)
+    e.set_beam(10, 8)
+    names = ["synth_noise", "testwav", "synth_tone"]
+    chunks = [chunks_i16(golden(n)["pcm"]) for n in names]
+    slots = [e.open_session() for _ in names]
+    states = [B.BeamState() for _ in names]
+    n_cmp = 0
+    for tick in range(6):
+        idx = [i for i in range(len(names)) if tick < len(chunks[i])]
+        if tick == 3:                                                  # endpoint on stream 0: beam state must clear too
+            e.reset_session(slots[0])
+            states[0] = B.BeamState()
+        r = e.step([slots[i] for i in idx], np.stack([chunks[i][tick] for i in idx]), want_logprobs=True)
+        for j, i in enumerate(idx):
+            states[i] = B.beam_step(states[i], r.logprobs[j].astype(np.float64), beam=10, cand_k=8, max_len=255)
+            pre, score = B.best(states[i])
+            assert list(r.beam_tokens[j]) == pre, f"{names[i]} tick {tick}"
+            assert abs(float(r.beam_score[j]) - score) < 1e-3 * max(1.0, abs(score))
+            n_cmp += 1
+    report(f"prefix beam (beam 10, cand 8): {n_cmp} stream-chunks token-exact vs oracle; last score {score:.4f} vs device {float(r.beam_score[j]):.4f}")
+    e.close()

@@ -46,6 +46,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_burst": 1590.0, "source": "fallback"}
 
 
+def ncu_traffic(workload: str, family: str):
+    """dram bytes per launch of `family` from the committed ncu --set full capture of the same workload, else None."""
+    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(workload, {}).get(family)
+    except (OSError, ValueError):
+        return None
+
+
 def synth_pcm(n_streams: int, n_samples: int, first_id: int = 0) -> np.ndarray:
     """int16 audio ~ N(0, (0.1*32768)^2) + a 440 Hz tone, seeded per stream id."""
     out = np.empty((n_streams, n_samples), np.int16)
@@ -244,6 +254,30 @@ def run_ours(args):
     value = world * args.steps * audio_per_step / (dev_ms / 1e3)
     e2e_value = world * args.steps * audio_per_step / e2e_s
 
+    # ---- larger batches on the same GPU (device-resident leg only; explains where the headline sits on the curve)
+    sweep = []
+    if world == 1 and not fbank_only and not args.no_sweep:
+        for s_n in (1024, 4096):
+            if s_n == streams:
+                continue
+            eng.close()
+            cfg2 = ModelConfig(precision=precision, max_batch=s_n, max_sessions=s_n)
+            eng = Engine(cfg2, blob, local)
+            ext2 = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
+            sl = [eng.open_session() for _ in range(s_n)]
+            eng.stage(sl, synth_pcm(s_n, cfg2.chunk_length))
+            for _ in range(3):
+                eng.run_staged(s_n)
+            eng.sync()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ext2)
+            for _ in range(5):
+                eng.run_staged(s_n)
+            b.record(ext2)
+            eng.sync()
+            ms = a.elapsed_time(b) / 5
+            sweep.append({"streams": s_n, "ms_per_step": ms, "audio_s_per_s": s_n * 0.64 / (ms / 1e3)})
+
     if rank == 0:
         fam = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items() if v[1]}
         if fbank_only:
@@ -263,7 +297,7 @@ def run_ours(args):
             all_gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
             all_gemm_flop = streams * (FLOP_PER_STREAM_CHUNK - 20 * 2_129_920)
             roof = {"kernel": f"gemm_tc_kernel ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                    "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(args.workload if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,
                     "all_gemms": {"ms_per_step": all_gemm_ms, "tflops": all_gemm_flop / (all_gemm_ms / 1e3) / 1e12}}
             extra["path_roofline"] = {"flop_per_stream_chunk": FLOP_PER_STREAM_CHUNK,
@@ -285,6 +319,8 @@ def run_ours(args):
             "realtime_streams_supported": int(value / 1.0) // world,
         }
         line.update(extra)
+        if world == 1 and not fbank_only and not args.no_sweep:
+            line["stream_sweep"] = sweep
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, ms, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=args.ref_streams, threads=threads)
@@ -308,6 +344,7 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--ref-streams", type=int, default=16, help="streams per step in the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     sys.exit(run_reference_arm(args) if args.impl == "reference" else run_ours(args))
 

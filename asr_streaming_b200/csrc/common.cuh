@@ -87,20 +87,23 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA, branch-free.
-// The GELU epilogue of FFN1 runs once per output of a K=512 GEMM, i.e. it has ~16 issue slots per element before it,
-// not the tensor pipe, bounds the kernel; libdevice erff costs about twice this.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-ax * ax);
-  return copysignf(e, x);
+// erf(x) = sign(x) * (1 - 2^q(min(|x|, 4))), q = degree-6 minimax fit of log2(erfc) with zero constant term (weights =
+// d erf / d q); max abs error 3.1e-7 over the whole line in fp32 (fit + check: DESIGN.md §2).  One MUFU.EX2 + 7 FMA,
+// branch-free.  The GELU epilogue of FFN1 runs once per output of a K = 512 GEMM, i.e. it has ~16 issue slots per element
+// before it, not the tensor pipe, bounds the kernel; libdevice erff costs ~25 instructions, a rational form 2 MUFU ops.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float a = fminf(fabsf(x), 4.0f);
+  float q = 1.420474000e-04f;
+  q = fmaf(q, a, -3.664300360e-03f);
+  q = fmaf(q, a, 3.089622360e-02f);
+  q = fmaf(q, a, -1.496994580e-01f);
+  q = fmaf(q, a, -9.181654620e-01f);
+  q = fmaf(q, a, -1.627925070e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * a));       // q*a in [-27, 0]: no denormal / overflow handling needed
+  return copysignf(1.0f - e, x);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------

@@ -165,6 +165,10 @@ def run_ours(args):
     import torch
     from asr_streaming_b200 import Engine, ModelConfig, PRECISION_EXACT, PRECISION_FAST, pack_weights, random_weights
     rank, world, local = dist_env()
+    # Only the final JSON line may reach stdout: NCCL / torchrun chatter is routed to stderr for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -326,7 +330,10 @@ def run_ours(args):
             v, ms, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=args.ref_streams, threads=threads)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.ref_streams} streams x 2 steps of the same workload, batch 1 per stream, {threads} torch threads"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         torch.distributed.destroy_process_group()
     eng.close()

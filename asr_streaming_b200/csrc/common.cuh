@@ -106,12 +106,20 @@ __device__ __forceinline__ float erf_fast(float x) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+template <typename C> __device__ __forceinline__ C shfl_ctx(C v, int src);
+template <> __device__ __forceinline__ int shfl_ctx<int>(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ unsigned long long shfl_ctx<unsigned long long>(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 // ------------------------------------------------------------------------------------------
-// GEMM epilogues.  One thread owns one accumulator row (the shape tcgen05.ld 32x32b delivers) and gets it in
-// fragments of 32 consecutive columns; every global access is a 16-byte vector.  Anything that depends only on
-// the row (destination of a K/V row in the session ring) is computed once per tile (RowCtx).
-// (Measured on B200: a shared-memory transpose to lane = column with 4-byte accesses doubles the epilogue time;
-//  profiles/r01_notes.md.)
+// GEMM epilogues.  tcgen05.ld hands every thread one accumulator ROW (32 columns at a time).  Storing in that shape makes
+// each 16-byte store instruction touch 32 different 128-byte lines, and the K = 512 GEMMs of this model become store-bound
+// at ~2 TB/s (profiles/r01_gemm_sweep_rowstore_epilogue.txt: time tracks output bytes while the same mainloop reaches
+// 1.7 PFLOP/s at K = 4096).  So the kernel transposes each 32x32 block through a padded shared-memory tile with 16-byte
+// accesses; afterwards lane l owns 4 consecutive columns 4*(l&7).. of the 8 rows 4*i + (l>>3): every global load/store
+// instruction covers 4 rows x one full 128-byte line.  The functors get that fragment:
+//     v[i][0..3]  = rows row0 + 4*i + (lane>>3),  columns col .. col+3        (col = col0 + 4*(lane&7))
+//     ctx[i]      = RowCtx of those rows (computed once per tile by lane = row, gathered by shuffle)
+//     b4          = bias[col .. col+3]
 // ------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
@@ -124,26 +132,44 @@ struct EpiF32 {
   int n_valid;
   typedef int RowCtx;
   __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
-  __device__ __forceinline__ void store(int row, int col0, float (&v)[32], RowCtx) const {
-    float* o = out + (size_t)row * ld + col0;
-    const float* r = res ? res + (size_t)row * ld + col0 : nullptr;
-    if (col0 + 32 <= n_valid) {
+  __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  // residual rows of this thread for the whole tile -> L2, issued while the MMAs of the tile are still running
+  __device__ __forceinline__ void prefetch_tile(int row, int col0, int n_cols, RowCtx) const {
+    if (res) {
+      const float* r = res + (size_t)row * ld + col0;
+      for (int c = 0; c < n_cols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + c));
+    }
+  }
+  __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&)[8], const float4& b4) const {
+    const int rsub = lane >> 3;
+    if (col + 4 <= n_valid) {
       float4 rr[8];
-      if (r) {
+      if (res) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(r + 4 * j);      // all loads in flight first
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + 4 * i + rsub;
+          rr[i] = row < M ? *reinterpret_cast<const float4*>(res + (size_t)row * ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j); t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w; }
-        if (r) { t.x += rr[j].x; t.y += rr[j].y; t.z += rr[j].z; t.w += rr[j].w; }
-        *reinterpret_cast<float4*>(o + 4 * j) = t;
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        float4 t = make_float4(v[i][0] + b4.x, v[i][1] + b4.y, v[i][2] + b4.z, v[i][3] + b4.w);
+        if (res) { t.x += rr[i].x; t.y += rr[i].y; t.z += rr[i].z; t.w += rr[i].w; }
+        if (row < M) *reinterpret_cast<float4*>(out + (size_t)row * ld + col) = t;
       }
     } else {
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < n_valid) o[j] = v[j] + (bias ? bias[col0 + j] : 0.f) + (r ? r[j] : 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        if (row < M)
+          for (int j = 0; j < 4; ++j)
+            if (col + j < n_valid) {
+              const size_t o = (size_t)row * ld + col + j;
+              out[o] = v[i][j] + bb[j] + (res ? res[o] : 0.f);
+            }
+      }
     }
   }
 };
@@ -157,22 +183,38 @@ struct EpiOperand {
   int act;
   typedef int RowCtx;
   __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
-  __device__ __forceinline__ void store(int row, int col0, float (&v)[32], RowCtx) const {
-    bf16* o = out + (size_t)row * ld;
+  __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
+  __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&)[8], const float4& b4) const {
+    const int rsub = lane >> 3;
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = v[i][j] + bb[j];
+        v[i][j] = act == ACT_GELU ? gelu_erf(x) : (act == ACT_SILU ? silu(x) : x);
+      }
     }
-    if (act == ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else if (act == ACT_SILU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      if (row < M) {
+        bf16* o = out + (size_t)row * ld + col;
+        const bf16 h0 = __float2bfloat16_rn(v[i][0]), h1 = __float2bfloat16_rn(v[i][1]);
+        const bf16 h2 = __float2bfloat16_rn(v[i][2]), h3 = __float2bfloat16_rn(v[i][3]);
+        uint2 h;
+        h.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        h.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+        *reinterpret_cast<uint2*>(o) = h;
+        if (lo_off) {
+          uint2 l;
+          l.x = pack_bf16x2(v[i][0] - __bfloat162float(h0), v[i][1] - __bfloat162float(h1));
+          l.y = pack_bf16x2(v[i][2] - __bfloat162float(h2), v[i][3] - __bfloat162float(h3));
+          *reinterpret_cast<uint2*>(o + lo_off) = l;
+        }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) store_operand8(o, col0 + j, lo_off, &v[j]);
   }
 };
 
@@ -191,38 +233,35 @@ struct EpiQKV {
   const int* past_len;   // [n_slots]
   int rows, seg_rows, rc_rows, ring, d;
   float qscale;
-  typedef T* RowCtx;                          // column 0 of this tile's section (q | k | v) in the destination row
+  typedef unsigned long long RowCtx;          // T* of column 0 of this tile's section (q | k | v) in the destination row
   __device__ __forceinline__ RowCtx row_ctx(int row, int tile_col0) const {
     const int sec = tile_col0 / d;            // 0: q, 1: k, 2: v
-    if (sec == 0) return q + (size_t)row * d;
+    if (sec == 0) return (RowCtx)(q + (size_t)row * d);
     const int which = sec - 1;
     const int b = row / rows, t = row - b * rows;
     if (t < seg_rows) {
       const int slot = slots[b];
       const int rr = (past_len[slot] + t) % ring;
-      return cache_layer + (size_t)slot * slot_stride + ((size_t)which * ring + rr) * d;
+      return (RowCtx)(cache_layer + (size_t)slot * slot_stride + ((size_t)which * ring + rr) * d);
     }
-    return rc + (((size_t)b * 2 + which) * rc_rows + (t - seg_rows)) * d;
+    return (RowCtx)(rc + (((size_t)b * 2 + which) * rc_rows + (t - seg_rows)) * d);
   }
-  __device__ __forceinline__ void store(int, int col0, float (&v)[32], RowCtx dst_row) const {
-    const int sec = col0 / d;
+  __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
+  __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&ctx)[8], const float4& b4) const {
+    const int rsub = lane >> 3;
+    const int sec = col / d;
     const float sc = sec == 0 ? qscale : 1.0f;
+    const int lc = col - sec * d;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
-      v[j] = (v[j] + b.x) * sc; v[j + 1] = (v[j + 1] + b.y) * sc; v[j + 2] = (v[j + 2] + b.z) * sc; v[j + 3] = (v[j + 3] + b.w) * sc;
-    }
-    T* dst = dst_row + (col0 - sec * d);
-    if (sizeof(T) == 4) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst) + j) =
-            make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
-                       pack_bf16x2(v[j + 6], v[j + 7]));
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      const float x0 = (v[i][0] + b4.x) * sc, x1 = (v[i][1] + b4.y) * sc, x2 = (v[i][2] + b4.z) * sc, x3 = (v[i][3] + b4.w) * sc;
+      if (row < M) {
+        T* dst = reinterpret_cast<T*>(ctx[i]) + lc;
+        if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+        else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+      }
     }
   }
 };

@@ -73,6 +73,7 @@ struct AsrEngine {
   Geo geo;
   int device = 0, num_sms = 148;
   int simt_gemm = 0;
+  int no_pair = 0;
   int staged_fmt = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;
@@ -286,8 +287,13 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
   ProfScope ps(e, cat);
   if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
-  const int bn = pick_bn(e, M, w.N);
-  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
+  int bn = pick_bn(e, M, w.N);
+  // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand ingest per SM) pay off when the mainloop dominates: measured
+  // on B200 (profiles/r01_gemm_sweep_transposed_epilogue.txt) the pair kernel wins at K = 2048 (FFN2: 136 vs 156 us) and loses
+  // at K = 512, where the tile time is set by the epilogue and coupling two CTAs' epilogues costs more than the ingest saves.
+  if (bn == 256 && !e->no_pair && w.K * (e->geo.split ? 3 : 1) >= 1024 && w.N % 256 == 0 && ((M + 255) / 256) * (w.N / 256) >= e->num_sms / 2)
+    bn = kPairTile;
+  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 || bn == kPairTile ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
 }
 
 // ------------------------------------------------------------------------------------------ the per-step kernel chain
@@ -497,6 +503,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   e->cfg = *cfg; e->geo = g; e->device = device; e->num_sms = prop.multiProcessorCount;
   const char* dbg = getenv("ASR_B200_DEBUG_SIMT_GEMM");
   e->simt_gemm = dbg && dbg[0] == '1';
+  const char* np_ = getenv("ASR_B200_NO_PAIR_GEMM");
+  e->no_pair = np_ && np_[0] == '1';
   int rc = -1;
   do {
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); break; }
@@ -913,7 +921,7 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
       if (gemm_simt<EpiF32>(dA.as<bf16>(), ld, dB.as<bf16>(), ld, p, epi, 0)) break;
     } else {
       CUtensorMap ta, tb;
-      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn)) break;
+      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile ? 128 : bn)) break;
       if (gemm_tc<EpiF32>(ta, tb, p, epi, bn, prop.multiProcessorCount, 0)) break;
     }
     cudaError_t err = cudaDeviceSynchronize();
@@ -922,6 +930,51 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
     rc = 0;
   } while (0);
   dA32.free(); dB32.free(); dA.free(); dB.free(); dC.free(); dbias.free();
+  return rc;
+}
+
+/* Times `iters` launches of the tcgen05 GEMM on random bf16 operands already in HBM (diagnostic microbenchmark).
+ * epi: 0 = plain fp32 store, 1 = + bias + fp32 residual, 2 = bias + GELU -> bf16 operand.  Returns mean ms per launch. */
+int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, int32_t epi_kind, int32_t iters, float* ms_out, int device) {
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 || !ms_out || iters <= 0) { set_error("asr_debug_gemm_time: bad arguments"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int ld = split ? 2 * K : K;
+  const int Mp = (int)round_up(M, 256);
+  DevBuf dA, dB, dC, dR, dO, dbias;
+  int rc = -1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  do {
+    if (dA.alloc(2 * (size_t)Mp * ld) || dB.alloc(2 * (size_t)N * ld) || dC.alloc(4 * (size_t)M * N) || dR.alloc(4 * (size_t)M * N) ||
+        dO.alloc(2 * (size_t)M * N) || dbias.alloc(4 * (size_t)N)) break;
+    cudaMemset(dA.p, 0x3c, dA.bytes); cudaMemset(dB.p, 0x3c, dB.bytes); cudaMemset(dR.p, 0, dR.bytes); cudaMemset(dbias.p, 0, dbias.bytes);
+    const GemmProblem p = make_problem(M, N, K, split);
+    CUtensorMap ta, tb;
+    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile ? 128 : bn)) break;
+    EpiF32 e_plain{dC.as<float>(), nullptr, nullptr, N, N};
+    EpiF32 e_res{dC.as<float>(), dbias.as<float>(), dR.as<float>(), N, N};
+    EpiOperand e_op{dO.as<bf16>(), dbias.as<float>(), N, 0, ACT_GELU};
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bool ok = true;
+    for (int it = 0; it < iters + 3 && ok; ++it) {
+      if (it == 3) cudaEventRecord(e0, 0);
+      if (epi_kind == 0) ok = !gemm_tc<EpiF32>(ta, tb, p, e_plain, bn, prop.multiProcessorCount, 0);
+      else if (epi_kind == 1) ok = !gemm_tc<EpiF32>(ta, tb, p, e_res, bn, prop.multiProcessorCount, 0);
+      else ok = !gemm_tc<EpiOperand>(ta, tb, p, e_op, bn, prop.multiProcessorCount, 0);
+    }
+    if (!ok) break;
+    cudaEventRecord(e1, 0);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { set_error("asr_debug_gemm_time: %s", cudaGetErrorString(err)); break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    rc = 0;
+  } while (0);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  dA.free(); dB.free(); dC.free(); dR.free(); dO.free(); dbias.free();
   return rc;
 }
 

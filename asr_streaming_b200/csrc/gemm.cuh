@@ -4,6 +4,8 @@
 
 namespace asr {
 
+constexpr int kPairTile = 512;   // `bn` value selecting the cta_group::2 kernel (256 x 256 tile per CTA pair; tmB = box-128 map)
+
 // C = A * B^T with fused epilogue.  tmA / tmB: 2D bf16 tensor maps, box {64, 128} and {64, bn}, 128B swizzle.
 template <class Epi>
 int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const Epi& epi, int bn, int num_sms, cudaStream_t st);

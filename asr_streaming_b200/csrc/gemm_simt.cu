@@ -34,7 +34,29 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const bf16* __restrict__
       }
     }
   }
-  if (row < p.M) epi.store(row, col0, acc, epi.row_ctx(row, col0));
+  // hand the 128 x 32 block to the epilogue in the same fragment shape the tcgen05 kernel uses
+  __shared__ __align__(16) float tile[4][32][36];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.y * 128 + warp * 32;
+  const typename Epi::RowCtx my_ctx = epi.row_ctx(row < p.M ? row : p.M - 1, col0);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[warp][lane][j] = acc[j];
+  __syncwarp();
+  typename Epi::RowCtx ctx[8];
+  float v[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ctx[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 4 * i + (lane >> 3));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = tile[warp][4 * i + (lane >> 3)][4 * (lane & 7) + j];
+  }
+  const int col = col0 + 4 * (lane & 7);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (epi.bias_ptr()) {
+    const float* bp = epi.bias_ptr();
+    b4 = make_float4(col < p.N ? bp[col] : 0.f, col + 1 < p.N ? bp[col + 1] : 0.f, col + 2 < p.N ? bp[col + 2] : 0.f, col + 3 < p.N ? bp[col + 3] : 0.f);
+  }
+  if (col < p.N) epi.store(row0, col, lane, p.M, v, ctx, b4);
 }
 
 }  // namespace

@@ -8,10 +8,9 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN,
 //               K=16 per instruction), fp32 accumulators in TMEM, double-buffered (2 x BN columns);
 //               tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 2..9  epilogue, two warps per TMEM lane quarter alternating 32-column blocks (a single warp per SM
-//               sub-partition cannot hide the tcgen05.ld / residual-load latency: measured 2x): tcgen05.ld
-//               32x32b.x32 (one accumulator row per thread), fused bias / residual / GELU / SiLU / Q-scaling /
-//               KV-ring scatter, 16-byte global accesses.
+//   warps 2..9  epilogue, two warps per TMEM lane quarter alternating 32-column blocks: tcgen05.ld 32x32b.x32 (one
+//               accumulator row per thread, one chunk ahead), 16-byte transpose through shared memory, then fused bias /
+//               residual / GELU / SiLU / Q-scaling / KV-ring scatter with full-line (4 rows x 128 B) global accesses.
 #include "gemm.cuh"
 
 namespace asr {
@@ -23,7 +22,6 @@ constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kStagingBytes = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -108,12 +106,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr int kStageLd = 36;                          // fp32 row stride of the per-warp transpose tile: STS.128 by row and LDS.128 by
+constexpr int kXposeFloats = 32 * kStageLd;           // (4 rows x 8 lanes) are both bank-conflict-free
+constexpr int kStagingBytes = 8 * kXposeFloats * 4;   // 8 epilogue warps
+
+// One accumulator tile (128 rows x BN columns of this CTA) from TMEM to global memory.
+//   * before the accumulator is complete (overlapping the MMAs): RowCtx of the thread's row, L2 prefetch of its residual rows;
+//   * tcgen05.ld (thread = row) runs one 32-column chunk ahead of the math (two register sets);
+//   * each chunk is transposed through shared memory so that global accesses are full 128-byte lines (see common.cuh).
+template <int BN, class Epi>
+__device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem& p, int row0, int tile_col0, int half, int lane,
+                                              uint32_t taddr, uint32_t tfull, uint32_t tfull_phase, float* xpose) {
+  constexpr int kChunks = BN / 32;
+  const int my_row = row0 + lane;
+  const typename Epi::RowCtx my_ctx = epi.row_ctx(my_row < p.M ? my_row : p.M - 1, tile_col0);
+  if (my_row < p.M) epi.prefetch_tile(my_row, tile_col0, (p.N - tile_col0) < BN ? (p.N - tile_col0) : BN, my_ctx);
+  typename Epi::RowCtx ctx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ctx[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 4 * i + (lane >> 3));
+  const float* bias = epi.bias_ptr();
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (half >= kChunks) return;
+  float va[32], vb[32];
+  tmem_ld32(taddr + (uint32_t)(half * 32), va);
+  tmem_ld_wait();
+  auto finish = [&](float (&raw)[32], int c) {
+    const int col = tile_col0 + c * 32 + 4 * (lane & 7);
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && col < p.N) b4 = *reinterpret_cast<const float4*>(bias + col);      // N is a multiple of 4 for every matrix here
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(xpose + lane * kStageLd + j) = make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+    __syncwarp();
+    float v[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(xpose + (4 * i + (lane >> 3)) * kStageLd + 4 * (lane & 7));
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    }
+    __syncwarp();
+    if (row0 < p.M && col < p.N) epi.store(row0, col, lane, p.M, v, ctx, b4);
+  };
+#pragma unroll 1
+  for (int i = 0; half + 2 * i < kChunks; i += 2) {
+    const int c0 = half + 2 * i, c1 = c0 + 2;
+    if (c1 < kChunks) tmem_ld32(taddr + (uint32_t)(c1 * 32), vb);
+    finish(va, c0);
+    tmem_ld_wait();
+    if (c1 >= kChunks) break;
+    const int c2 = c1 + 2;
+    if (c2 < kChunks) tmem_ld32(taddr + (uint32_t)(c2 * 32), va);
+    finish(vb, c1);
+    tmem_ld_wait();
+  }
 }
 
 template <int BN> struct TileCfg {
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
   static constexpr int kTmemCols = 2 * BN;   // power of two for BN in {64,128,256}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -209,22 +262,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;
     const int quarter = warp & 3;                           // TMEM lane quarter this warp may read
     const int half = ew >> 2;                               // which of the two warps sharing the quarter
+    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * kXposeFloats;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-      const int row = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const typename Epi::RowCtx ctx = epi.row_ctx(row_ok ? row : p.M - 1, n_blk * BN);   // before the wait: overlaps the MMA
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) epi.store(row, col0, v, ctx);
-      }
+      epilogue_tile<BN, Epi>(epi, p, row0, n_blk * BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -238,6 +282,189 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
+}
+
+
+// ==========================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA loads its own
+// 128 rows of A and HALF of the B tile (128 of the 256 weight rows); the leader's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads A/B from both CTAs' shared memory and writes each CTA's 128
+// accumulator rows into that CTA's TMEM.  Per SM and k-block this ingests 32 KB instead of 48 KB from L2 — the 1-CTA
+// kernel sits at ~40 B/clk/SM, the chip-wide L2 cap (profiles/r01_ncu_full_4096streams_gemm_attention.csv) — and the
+// smaller stage allows a 6-deep ring.
+//   full[s]   : leader's barrier only; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA), leader arms 64 KB
+//   empty[s]  : per CTA, arrived by the leader's tcgen05.commit multicast (mask 0b11)
+//   tfull[a]  : per CTA, same multicast commit after the last k-block
+//   tempty[a] : leader's barrier only; 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
+// ==========================================================================================================
+constexpr int P_BN = 256;
+constexpr int P_STAGES = 5;
+constexpr int P_STAGE_BYTES = (BM + P_BN / 2) * BK * 2;            // 32 KB per CTA
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + kStagingBytes + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {      // arrive on CTA 0's copy of `bar`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar) : "memory");
+}
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t staging_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  const uint32_t bar_base = staging_base + kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * P_STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + P_BN - 1) / P_BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int kb_per_pass = p.K / BK;
+  const int total_kb = kb_per_pass * p.passes;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                      // peer's barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+        const int row_a = m_pair * 2 * BM + (int)rank * BM;
+        const int row_b = n_blk * P_BN + (int)rank * (P_BN / 2);
+        for (int ps = 0; ps < p.passes; ++ps) {
+          for (int kb = 0; kb < kb_per_pass; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);       // own slot free: the leader's MMAs that read it (in both CTAs) retired
+            const uint32_t sa = smem_base + stage * P_STAGE_BYTES;
+            const uint32_t sb = sa + BM * BK * 2;
+            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)P_STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, p.a_koff[ps] + kb * BK, row_a, lbar);
+            tma_load_2d_pair(sb, &tmB, p.b_koff[ps] + kb * BK, row_b, lbar);
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);        // both CTAs' epilogues drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P_BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * P_STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + BM * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(empty_bar(stage));
+            if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * kXposeFloats;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int row0 = m_pair * 2 * BM + (int)rank * BM + quarter * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P_BN);
+      epilogue_tile<P_BN, Epi>(epi, p, row0, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cta0(tempty_bar(acc));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still signal or read
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <class Epi>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P_BN - 1) / P_BN);
+  const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  gemm_tc2_kernel<Epi><<<2 * pairs, kThreads, P_SMEM_BYTES, st>>>(tmA, tmB128, p, epi);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 template <int BN, class Epi>
@@ -262,6 +489,7 @@ int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p
   if (p.M <= 0) return 0;
   if (p.K % BK != 0) { set_error("gemm_tc: K=%d not a multiple of %d", p.K, BK); return -1; }
   switch (bn) {
+    case kPairTile: return launch_pair<Epi>(tmA, tmB, p, epi, num_sms, st);   // tmB must be the 128-row-box map
     case 64: return launch_bn<64, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 128: return launch_bn<128, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 256: return launch_bn<256, Epi>(tmA, tmB, p, epi, num_sms, st);

@@ -160,6 +160,10 @@ ASR_API int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int3
 ASR_API int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, const float* A, const float* B, const float* bias,
                    float* C, int device);
 
+/* Mean milliseconds per launch of the tcgen05 GEMM on operands resident in HBM (microbenchmark; bn = 512 selects the CTA-pair
+ * kernel).  epi_kind: 0 plain fp32 store, 1 bias + fp32 residual, 2 bias + GELU -> bf16. */
+ASR_API int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, int32_t epi_kind, int32_t iters, float* ms_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

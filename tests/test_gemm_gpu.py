@@ -32,6 +32,12 @@ CASES = [
     (640, 804, 512, 64, 0),
     (777, 512, 512, 64, 0),
     (1000, 1536, 512, 256, 1),       # EXACT: three passes
+    (512, 256, 64, 512, 0),          # bn = 512 selects the cta_group::2 CTA-pair kernel: one pair tile, one k-block
+    (256, 512, 512, 512, 0),
+    (5120, 1536, 512, 512, 0),       # QKV at 256 streams: 120 pair tiles on 74 pairs
+    (5000, 2048, 512, 512, 0),       # ragged M inside a pair (last pair: second CTA partly / fully out of range)
+    (2432, 512, 2048, 512, 0),       # odd number of 128-row tiles (19): the peer CTA of the last pair is all padding
+    (1000, 1536, 512, 512, 1),       # pair kernel, EXACT passes
     (300, 804, 512, 128, 1),
 ]
 

@@ -20,8 +20,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
+// 16 epilogue warps (4 per TMEM lane quarter): with 8 the epilogue is latency-bound (tcgen05.ld -> smem transpose -> global),
+// measured 242 -> 173 us on the FFN1 shape (profiles/r01_gemm_sweep_*.txt).  96 registers per thread at 576 threads.
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+template <class Epi> struct EpiWarps { static constexpr int value = kEpiWarps; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,13 +114,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 constexpr int kStageLd = 36;                          // fp32 row stride of the per-warp transpose tile: STS.128 by row and LDS.128 by
 constexpr int kXposeFloats = 32 * kStageLd;           // (4 rows x 8 lanes) are both bank-conflict-free
-constexpr int kStagingBytes = 8 * kXposeFloats * 4;   // 8 epilogue warps
+constexpr int kStagingBytes = kEpiWarps * kXposeFloats * 4;   // pair kernel
 
 // One accumulator tile (128 rows x BN columns of this CTA) from TMEM to global memory.
 //   * before the accumulator is complete (overlapping the MMAs): RowCtx of the thread's row, L2 prefetch of its residual rows;
 //   * tcgen05.ld (thread = row) runs one 32-column chunk ahead of the math (two register sets);
 //   * each chunk is transposed through shared memory so that global accesses are full 128-byte lines (see common.cuh).
-template <int BN, class Epi>
+template <int BN, int kStride, class Epi>
 __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem& p, int row0, int tile_col0, int half, int lane,
                                               uint32_t taddr, uint32_t tfull, uint32_t tfull_phase, float* xpose) {
   constexpr int kChunks = BN / 32;
@@ -131,9 +134,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   if (half >= kChunks) return;
-  float va[32], vb[32];
-  tmem_ld32(taddr + (uint32_t)(half * 32), va);
-  tmem_ld_wait();
+  float va[32];
   auto finish = [&](float (&raw)[32], int c) {
     const int col = tile_col0 + c * 32 + 4 * (lane & 7);
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -150,35 +151,50 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
     __syncwarp();
     if (row0 < p.M && col < p.N) epi.store(row0, col, lane, p.M, v, ctx, b4);
   };
+  if constexpr (kStride >= 4) {          // 16 epilogue warps: thread-level parallelism hides the tcgen05.ld latency, keep registers low
 #pragma unroll 1
-  for (int i = 0; half + 2 * i < kChunks; i += 2) {
-    const int c0 = half + 2 * i, c1 = c0 + 2;
+    for (int c = half; c < kChunks; c += kStride) {
+      tmem_ld32(taddr + (uint32_t)(c * 32), va);
+      tmem_ld_wait();
+      finish(va, c);
+    }
+    return;
+  }
+  float vb[32];
+  tmem_ld32(taddr + (uint32_t)(half * 32), va);
+  tmem_ld_wait();
+#pragma unroll 1
+  for (int i = 0; half + kStride * i < kChunks; i += 2) {
+    const int c0 = half + kStride * i, c1 = c0 + kStride;
     if (c1 < kChunks) tmem_ld32(taddr + (uint32_t)(c1 * 32), vb);
     finish(va, c0);
     tmem_ld_wait();
     if (c1 >= kChunks) break;
-    const int c2 = c1 + 2;
+    const int c2 = c1 + kStride;
     if (c2 < kChunks) tmem_ld32(taddr + (uint32_t)(c2 * 32), va);
     finish(vb, c1);
     tmem_ld_wait();
   }
 }
 
-template <int BN> struct TileCfg {
+template <int BN, int EW> struct TileCfg {
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
-  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int kXposeBytes = EW * kXposeFloats * 4;
+  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;   // power of two for BN in {64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kXposeBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kThreadsCta = 64 + 32 * EW;
 };
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<Epi>::value, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi) {
-  using Cfg = TileCfg<BN>;
+  constexpr int EW = EpiWarps<Epi>::value;
+  using Cfg = TileCfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024B alignment
   const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  const uint32_t bar_base = staging_base + kStagingBytes;
+  const uint32_t bar_base = staging_base + Cfg::kXposeBytes;
   // barrier layout (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
@@ -197,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -261,14 +277,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;                           // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                               // which of the two warps sharing the quarter
+    const int half = ew >> 2;                               // which of the EW/4 warps sharing the quarter
     float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * kXposeFloats;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN, Epi>(epi, p, row0, n_blk * BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+      epilogue_tile<BN, EW / 4, Epi>(epi, p, row0, n_blk * BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -298,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   tempty[a] : leader's barrier only; 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
 // ==========================================================================================================
 constexpr int P_BN = 256;
-constexpr int P_STAGES = 5;
+constexpr int P_STAGES = 4;
 constexpr int P_STAGE_BYTES = (BM + P_BN / 2) * BK * 2;            // 32 KB per CTA
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + kStagingBytes + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address
@@ -434,7 +450,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
       const int row0 = m_pair * 2 * BM + (int)rank * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P_BN);
-      epilogue_tile<P_BN, Epi>(epi, p, row0, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+      epilogue_tile<P_BN, kEpiWarps / 4, Epi>(epi, p, row0, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -469,7 +485,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmPro
 
 template <int BN, class Epi>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EpiWarps<Epi>::value>;
   static bool attr_set = false;
   if (!attr_set) {
     ASR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -477,7 +493,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem&
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN, Epi><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p, epi);
+  gemm_tc_kernel<BN, Epi><<<grid, Cfg::kThreadsCta, Cfg::kSmemBytes, st>>>(tmA, tmB, p, epi);
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

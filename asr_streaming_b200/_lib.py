@@ -46,6 +46,8 @@ SIGNATURES = {
     "asr_session_reset": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_session_close": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
+    "asr_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "asr_collect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
     "asr_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "asr_run_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "asr_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),

@@ -97,9 +97,19 @@ struct AsrEngine {
   // prefix beam search (optional)
   int beam = 0, cand_k = 0;
   DevBuf bm_n, bm_cur, bm_len, bm_last, bm_pb, bm_pnb, bm_hash, bm_tokens, d_beam_tok, d_beam_len, d_beam_score;
-  void* h_stage = nullptr;      // pinned: pcm + slots in, results out
+  // Double-buffered staging so that step k+1's H2D overlaps step k's kernels (asr_submit / asr_collect):
+  // pinned host [pcm | slots | results] x 2, device pcm/slots x 2 (buffer 0 = d_pcm / d_slots above), a copy stream.
+  void* h_stage = nullptr;      // == h_buf[0]
+  void* h_buf[2] = {nullptr, nullptr};
   size_t h_stage_bytes = 0;
   size_t h_out_off = 0;
+  DevBuf d_pcm2, d_slots2;
+  void* act_pcm = nullptr;      // input buffers the kernels of the step being enqueued read
+  int* act_slots = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  struct Pending { int n = 0; int want_lp = 0; int active = 0; std::chrono::steady_clock::time_point t0; } pend[2];
+  int cur_buf = 0;
 
   // per-kernel-family CUDA-event profiling (bench.py roofline): pairs recorded on the launching stream
   int prof_on = 0;
@@ -301,7 +311,7 @@ template <typename T>
 int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
   const Geo& g = e->geo;
   const int M = n * g.rows, d = g.d_model;
-  const int* slots = e->d_slots.as<int>();
+  const int* slots = e->act_slots;
   for (int l = 0; l < n_layers_to_run; ++l) {
     const LayerW& L = e->layers[l];
     T* cache_layer = e->kv_cache.as<T>() + (size_t)l * 2 * g.ring * d;
@@ -344,7 +354,7 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
   const FbankPlan& pl = e->mel128;
   FbankParams P;
   memset(&P, 0, sizeof(P));
-  P.pcm = e->d_pcm.p; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
+  P.pcm = e->act_pcm; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
   P.n_frames = g.frames; P.hop = g.hop; P.frame_len = g.win; P.frame_off = (g.n_fft - g.win) / 2; P.nc = pl.nc; P.kaldi = 0;
   P.in_scale = P.pcm_is_f32 ? 1.0f : 1.0f / 32768.0f;                                  // streaming_server.py:362-363
   P.preemph = 0.f; P.log_floor = 1e-5f;                                                // audio.py:25 clamp(1e-5)
@@ -358,7 +368,7 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
 
 BeamParams beam_params(AsrEngine* e, int n) {
   BeamParams P;
-  P.logprobs = e->d_logprobs.as<float>(); P.slots = e->d_slots.as<int>();
+  P.logprobs = e->d_logprobs.as<float>(); P.slots = e->act_slots;
   P.n = n; P.seg_rows = e->geo.seg_rows; P.vocab = e->geo.vocab; P.beam = e->beam; P.cand_k = e->cand_k; P.max_len = BEAM_MAX_LEN - 1;
   P.n_beam = e->bm_n.as<int>(); P.cur = e->bm_cur.as<int>(); P.len = e->bm_len.as<int>(); P.last = e->bm_last.as<int>();
   P.pb = e->bm_pb.as<float>(); P.pnb = e->bm_pnb.as<float>(); P.hash = e->bm_hash.as<unsigned long long>(); P.tokens = e->bm_tokens.as<int16_t>();
@@ -385,7 +395,7 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   EpiF32 ec2{e->logits.as<float>(), e->ctc_b2, nullptr, g.vocab, g.vocab};                        // decoder.py:68
   if (run_gemm(e, ASR_PROF_GEMM_CTC2, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
   CtcParams cp;
-  cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->d_slots.as<int>();
+  cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->act_slots;
   cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
   cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
   cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>();
@@ -406,47 +416,116 @@ int check_step_args(AsrEngine* e, int n, const int32_t* slots) {
 
 size_t pcm_bytes(const AsrEngine* e, int n, int fmt) { return (size_t)n * e->geo.chunk_len * (fmt == ASR_PCM_F32 ? 4 : 2); }
 
-int stage_inputs(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int fmt) {
+size_t slots_off(const AsrEngine* e) { return round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256); }
+void* dev_pcm(AsrEngine* e, int b) { return b ? e->d_pcm2.p : e->d_pcm.p; }
+int* dev_slots(AsrEngine* e, int b) { return b ? e->d_slots2.as<int>() : e->d_slots.as<int>(); }
+void use_buffer(AsrEngine* e, int b) { e->act_pcm = dev_pcm(e, b); e->act_slots = dev_slots(e, b); }
+
+// host -> pinned (skipped when the caller assembled the batch in the pinned buffer) -> device, on `st`
+int stage_inputs(AsrEngine* e, int b, int n, const int32_t* slots, const void* pcm, int fmt, cudaStream_t st) {
   if (check_step_args(e, n, slots)) return -1;
   if (n && !pcm) { set_error("null pcm"); return -1; }
   if (fmt != ASR_PCM_I16 && fmt != ASR_PCM_F32) { set_error("bad pcm_format %d", fmt); return -1; }
   if (!n) return 0;
   ASR_CUDA_OK(cudaSetDevice(e->device));
   const size_t pb = pcm_bytes(e, n, fmt);
-  uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_stage);
-  if (pcm != hs) memcpy(hs, pcm, pb);                      // asr_pinned_pcm callers filled the staging buffer themselves
-  memcpy(hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), slots, 4 * (size_t)n);
-  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, hs, pb, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaMemcpyAsync(e->d_slots.p, hs + round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256), 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_buf[b]);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(pcm);
+  const bool pinned_src = (src == reinterpret_cast<uint8_t*>(e->h_buf[0]) || src == reinterpret_cast<uint8_t*>(e->h_buf[1]));
+  if (!pinned_src) { memcpy(hs, pcm, pb); src = hs; }        // asr_pinned_pcm callers filled a staging buffer themselves
+  memcpy(hs + slots_off(e), slots, 4 * (size_t)n);
+  ASR_CUDA_OK(cudaMemcpyAsync(dev_pcm(e, b), src, pb, cudaMemcpyHostToDevice, st));
+  ASR_CUDA_OK(cudaMemcpyAsync(dev_slots(e, b), hs + slots_off(e), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
   return 0;
 }
 
-int fetch_outputs(AsrEngine* e, int n, const AsrStepOut* out, bool sync_only) {
+struct OutItem { const DevBuf* src; size_t bytes, hoff; int field; };
+
+// fixed layout of the pinned result area of one staging buffer
+std::vector<OutItem> out_layout(AsrEngine* e, int n, bool want_lp) {
   const Geo& g = e->geo;
-  uint8_t* ho = reinterpret_cast<uint8_t*>(e->h_stage) + e->h_out_off;
-  const size_t nS = (size_t)n * g.seg_rows;
+  const size_t nS = (size_t)n * g.seg_rows, B = e->cfg.max_batch, BS = B * g.seg_rows;
+  std::vector<OutItem> v;
   size_t off = 0;
-  struct Item { void* dst; const void* src; size_t bytes; size_t hoff; };
-  std::vector<Item> items;
-  auto add = [&](void* dst, const DevBuf& src, size_t bytes) {
-    if (dst && bytes) { items.push_back({dst, src.p, bytes, off}); off += round_up(bytes, 256); }
+  auto add = [&](const DevBuf& src, size_t bytes, size_t cap, int field, bool on) {
+    if (on && bytes) v.push_back({&src, bytes, off, field});
+    off += round_up(cap, 256);
   };
-  if (out && !sync_only && n) {
-    add(out->argmax_ids, e->d_argmax, 4 * nS);
-    add(out->new_tokens, e->d_newtok, 4 * nS);
-    add(out->n_new, e->d_nnew, 4 * (size_t)n);
-    add(out->blank_frames, e->d_blank, 4 * (size_t)n);
-    add(out->has_token, e->d_hastok, 4 * (size_t)n);
-    add(out->logprobs, e->d_logprobs, 4 * nS * g.vocab);
-    if (e->beam > 0) {
-      add(out->beam_tokens, e->d_beam_tok, 4 * (size_t)n * BEAM_MAX_LEN);
-      add(out->beam_len, e->d_beam_len, 4 * (size_t)n);
-      add(out->beam_score, e->d_beam_score, 4 * (size_t)n);
-    }
+  add(e->d_argmax, 4 * nS, 4 * BS, 0, true);
+  add(e->d_newtok, 4 * nS, 4 * BS, 1, true);
+  add(e->d_nnew, 4 * (size_t)n, 4 * B, 2, true);
+  add(e->d_blank, 4 * (size_t)n, 4 * B, 3, true);
+  add(e->d_hastok, 4 * (size_t)n, 4 * B, 4, true);
+  add(e->d_beam_tok, 4 * (size_t)n * BEAM_MAX_LEN, 4 * B * BEAM_MAX_LEN, 6, e->beam > 0);
+  add(e->d_beam_len, 4 * (size_t)n, 4 * B, 7, e->beam > 0);
+  add(e->d_beam_score, 4 * (size_t)n, 4 * B, 8, e->beam > 0);
+  add(e->d_logprobs, 4 * nS * g.vocab, 4 * BS * g.vocab, 5, want_lp);
+  return v;
+}
+
+void* out_field(const AsrStepOut* o, int f) {
+  switch (f) {
+    case 0: return o->argmax_ids; case 1: return o->new_tokens; case 2: return o->n_new; case 3: return o->blank_frames;
+    case 4: return o->has_token; case 5: return o->logprobs; case 6: return o->beam_tokens; case 7: return o->beam_len; case 8: return o->beam_score;
   }
-  for (auto& it : items) ASR_CUDA_OK(cudaMemcpyAsync(ho + it.hoff, it.src, it.bytes, cudaMemcpyDeviceToHost, e->stream));
+  return nullptr;
+}
+
+int enqueue_d2h(AsrEngine* e, int b, int n, bool want_lp) {
+  uint8_t* ho = reinterpret_cast<uint8_t*>(e->h_buf[b]) + e->h_out_off;
+  for (auto& it : out_layout(e, n, want_lp))
+    ASR_CUDA_OK(cudaMemcpyAsync(ho + it.hoff, it.src->p, it.bytes, cudaMemcpyDeviceToHost, e->stream));
+  return 0;
+}
+
+void deliver(AsrEngine* e, int b, int n, bool want_lp, const AsrStepOut* out) {
+  if (!out) return;
+  const uint8_t* ho = reinterpret_cast<const uint8_t*>(e->h_buf[b]) + e->h_out_off;
+  for (auto& it : out_layout(e, n, want_lp)) {
+    void* dst = out_field(out, it.field);
+    if (dst) memcpy(dst, ho + it.hoff, it.bytes);
+  }
+}
+
+// enqueue one step on buffer b: H2D on the copy stream, kernels + D2H on the compute stream
+int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int fmt, bool want_lp, int* ticket) {
+  const int b = e->cur_buf;
+  if (e->pend[b].active) { set_error("two steps are already in flight: asr_collect the oldest ticket first"); return -1; }
+  const auto t0 = std::chrono::steady_clock::now();
+  if (stage_inputs(e, b, n, slots, pcm, fmt, e->copy_stream)) return -1;
+  if (n) {
+    ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
+    ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+    use_buffer(e, b);
+    if (run_pipeline(e, n, fmt, e->geo.n_layers, true, want_lp)) return -1;
+    if (enqueue_d2h(e, b, n, want_lp)) return -1;
+    ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
+  }
+  e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
+  e->cur_buf ^= 1;
+  if (ticket) *ticket = b;
+  return 0;
+}
+
+int collect_step(AsrEngine* e, int ticket, const AsrStepOut* out) {
+  if (ticket < 0 || ticket > 1 || !e->pend[ticket].active) { set_error("asr_collect: ticket %d is not in flight", ticket); return -1; }
+  auto& pd = e->pend[ticket];
+  if (pd.n) {
+    ASR_CUDA_OK(cudaSetDevice(e->device));
+    ASR_CUDA_OK(cudaEventSynchronize(e->ev_done[ticket]));
+    deliver(e, ticket, pd.n, pd.want_lp, out);
+  }
+  pd.active = 0;
+  return 0;
+}
+
+// legacy split path (asr_stage / asr_run_staged / asr_fetch) works on buffer 0 and the compute stream only
+int fetch_outputs(AsrEngine* e, int n, const AsrStepOut* out, bool) {
+  if (n && out) {
+    if (enqueue_d2h(e, 0, n, out->logprobs != nullptr)) return -1;
+  }
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
-  for (auto& it : items) memcpy(it.dst, ho + it.hoff, it.bytes);
+  if (n && out) deliver(e, 0, n, out->logprobs != nullptr, out);
   return 0;
 }
 
@@ -471,7 +550,7 @@ void destroy_engine(AsrEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->d_pcm, &e->d_slots, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
+  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
@@ -481,7 +560,8 @@ void destroy_engine(AsrEngine* e) {
   }
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
-  if (e->h_stage) cudaFreeHost(e->h_stage);
+  for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -545,7 +625,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     // ---- activations
     const int B = cfg->max_batch, M = B * g.rows, Mc = B * g.seg_rows;
     const size_t esz = g.split ? 4 : 2;
-    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
+    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
         e->x2.alloc(4 * (size_t)M * d) || e->q.alloc(4 * (size_t)M * d) || e->rc_kv.alloc(esz * (size_t)B * 2 * g.rc_rows * d) ||
         e->logits.alloc(4 * (size_t)Mc * g.vocab) || e->d_logprobs.alloc(4 * (size_t)Mc * g.vocab) || e->d_argmax.alloc(4 * (size_t)Mc) ||
         e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B)) break;
@@ -564,9 +644,19 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     // ---- pinned staging: [pcm (f32 worst case) | slots | outputs]
     const size_t in_bytes = round_up(pcm_bytes(e, B, ASR_PCM_F32), 256) + round_up(4 * (size_t)B, 256);
     const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 5 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256) +
-                             round_up(4 * (size_t)B * BEAM_MAX_LEN, 256);
+                             round_up(4 * (size_t)B * BEAM_MAX_LEN, 256) + 4096;
     e->h_out_off = in_bytes; e->h_stage_bytes = in_bytes + out_bytes;
-    if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", e->h_stage_bytes); break; }
+    if (cudaMallocHost(&e->h_buf[0], e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_buf[1], e->h_stage_bytes) != cudaSuccess) {
+      set_error("cudaMallocHost(2 x %zu) failed", e->h_stage_bytes); break;
+    }
+    e->h_stage = e->h_buf[0];
+    if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); break; }
+    bool ev_ok = true;
+    for (int i = 0; i < 2; ++i)
+      ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) { set_error("cudaEventCreate failed"); break; }
+    use_buffer(e, 0);
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("engine init: %s", cudaGetErrorString(cudaGetLastError())); break; }
     rc = 0;
   } while (0);
@@ -580,6 +670,7 @@ int run_fbank_kind(AsrEngine* e, int kind, int n, int fmt, int n_samples, int su
   if (kind == ASR_FBANK_MELSPEC128) {
     if (n_samples != g.chunk_len) { set_error("melspec128 takes chunk_length = %d samples per stream", g.chunk_len); return -1; }
     *n_frames_out = g.frames;
+    use_buffer(e, 0);
     return run_fbank_melspec(e, n, fmt, d_out, false);
   }
   if (kind != ASR_FBANK_KALDI80) { set_error("unknown fbank kind %d", kind); return -1; }
@@ -688,11 +779,27 @@ int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   const auto t0 = std::chrono::steady_clock::now();
-  if (stage_inputs(e, n, slots, pcm, fmt)) return -1;
-  if (n == 0) return 0;
-  if (run_pipeline(e, n, fmt, e->geo.n_layers, true, out && out->logprobs)) return -1;
-  if (fetch_outputs(e, n, out, false)) return -1;
-  record_step(e, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  if (e->pend[0].active || e->pend[1].active) { set_error("asr_step while an asr_submit ticket is in flight"); return -1; }
+  int ticket = 0;
+  if (submit_step(e, n, slots, pcm, fmt, out && out->logprobs, &ticket)) return -1;
+  if (collect_step(e, ticket, out)) return -1;
+  if (n) record_step(e, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
+}
+
+int asr_submit(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t fmt, int32_t want_logprobs, int32_t* ticket) {
+  if (!e || !ticket) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  return submit_step(e, n, slots, pcm, fmt, want_logprobs != 0, ticket);
+}
+
+int asr_collect(AsrEngine* e, int32_t ticket, const AsrStepOut* out) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int n = (ticket == 0 || ticket == 1) ? e->pend[ticket].n : 0;
+  const auto t0 = (ticket == 0 || ticket == 1) ? e->pend[ticket].t0 : std::chrono::steady_clock::now();
+  if (collect_step(e, ticket, out)) return -1;
+  if (n) record_step(e, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return 0;
 }
 
@@ -700,7 +807,8 @@ int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, in
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   e->staged_fmt = fmt;
-  return stage_inputs(e, n, slots, pcm, fmt);
+  use_buffer(e, 0);
+  return stage_inputs(e, 0, n, slots, pcm, fmt, e->stream);
 }
 
 int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
@@ -708,6 +816,7 @@ int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
   std::lock_guard<std::mutex> lk(e->mu);
   if (n <= 0 || n > e->cfg.max_batch) { set_error("n = %d outside (0, max_batch]", n); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
+  use_buffer(e, 0);
   if (run_pipeline(e, n, e->staged_fmt, e->geo.n_layers, true, want_logprobs != 0)) return -1;
   ++e->steps; e->stream_chunks += n;
   return 0;
@@ -732,7 +841,7 @@ void* asr_stream_handle(AsrEngine* e) { return e ? (void*)e->stream : nullptr; }
 void* asr_pinned_pcm(AsrEngine* e, uint64_t* capacity_bytes) {
   if (!e) return nullptr;
   if (capacity_bytes) *capacity_bytes = pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32);
-  return e->h_stage;
+  return e->h_buf[e->cur_buf];                              // the buffer the NEXT asr_step / asr_submit stages from
 }
 
 int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes) {
@@ -740,8 +849,8 @@ int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes) {
   std::lock_guard<std::mutex> lk(e->mu);
   if (bytes > e->d_pcm.bytes) { set_error("asr_stage_raw: %llu bytes > staging capacity %zu", (unsigned long long)bytes, e->d_pcm.bytes); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  memcpy(e->h_stage, pcm, bytes);
-  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, e->h_stage, bytes, cudaMemcpyHostToDevice, e->stream));
+  memcpy(e->h_buf[0], pcm, bytes);
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_pcm.p, e->h_buf[0], bytes, cudaMemcpyHostToDevice, e->stream));
   return 0;
 }
 
@@ -852,7 +961,8 @@ int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const 
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (n_layers < 0 || n_layers > e->geo.n_layers) { set_error("n_layers out of range"); return -1; }
-  if (stage_inputs(e, n, slots, pcm, fmt)) return -1;
+  use_buffer(e, 0);
+  if (stage_inputs(e, 0, n, slots, pcm, fmt, e->stream)) return -1;
   if (n == 0) return 0;
   if (run_pipeline(e, n, fmt, n_layers, false, false)) return -1;
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));

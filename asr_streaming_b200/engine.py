@@ -143,7 +143,22 @@ class Engine:
         _lib.check(self.lib, self.lib.asr_step(self._h, n, sl.ctypes.data, a.ctypes.data, fmt, C.byref(o)), "asr_step")
         return self._result(bufs, n)
 
-    # split form (pipelining / device-resident timing)
+    # pipelined form: up to two steps in flight, H2D of step k+1 overlaps the kernels of step k
+    def submit(self, slots: Sequence[int], pcm: np.ndarray, want_logprobs: bool = False):
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        n = int(sl.size)
+        a, fmt = self._pcm(pcm, n)
+        t = C.c_int32()
+        _lib.check(self.lib, self.lib.asr_submit(self._h, n, sl.ctypes.data, a.ctypes.data, fmt, int(want_logprobs), C.byref(t)), "asr_submit")
+        return (t.value, n, want_logprobs)
+
+    def collect(self, ticket) -> StepResult:
+        t, n, want = ticket
+        bufs, o = self._alloc_out(n, want)
+        _lib.check(self.lib, self.lib.asr_collect(self._h, t, C.byref(o)), "asr_collect")
+        return self._result(bufs, n)
+
+    # split form (device-resident timing)
     def stage(self, slots: Sequence[int], pcm: np.ndarray) -> int:
         sl = np.ascontiguousarray(slots, dtype=np.int32)
         a, fmt = self._pcm(pcm, int(sl.size))

@@ -67,8 +67,7 @@ class SessionScheduler:
         self.sessions: Dict[int, StreamSession] = {}
         self._next_id = 0
         self._rr: Deque[int] = deque()            # round-robin order so a backlog cannot starve old sessions
-        # batch assembly happens directly in the engine's pinned staging buffer (no second host copy)
-        self._pack = engine.pinned_pcm(np.int16) if hasattr(engine, "pinned_pcm") else np.empty((self.cfg.max_batch, self.cfg.chunk_length), np.int16)
+        self._fallback_pack = None if hasattr(engine, "pinned_pcm") else np.empty((self.cfg.max_batch, self.cfg.chunk_length), np.int16)
 
     def open(self) -> StreamSession:
         s = StreamSession(self._next_id, self.engine.open_session(), self.cfg)
@@ -113,6 +112,8 @@ class SessionScheduler:
         """Runs one step over the ready streams.  ``gate(session, chunk) -> bool`` (optional) is the VAD decision
         (streaming_server.py:374-379); gated-out streams are skipped.  Returns (session, new token ids, logprobs|None)."""
         batch = self.ready_sessions()
+        # batch assembly happens directly in the engine's pinned staging buffer of the next step (no second host copy)
+        self._pack = self.engine.pinned_pcm(np.int16) if self._fallback_pack is None else self._fallback_pack
         run: List[StreamSession] = []
         for s in batch:
             if gate is not None and not s.is_contain_token and not gate(s, s.chunk()):

@@ -112,15 +112,21 @@ ASR_API int asr_session_close(AsrEngine* e, int32_t slot);
  * streaming_server.py:362) or float32 in [-1,1).  A session may appear at most once per step. */
 ASR_API int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, const AsrStepOut* out);
 
+/* Pipelined form: asr_submit enqueues a step (H2D on a copy stream, kernels + D2H of the results on the compute stream) and
+ * returns a ticket without waiting; asr_collect waits for that ticket and delivers its results.  Up to two tickets may be
+ * in flight, so the input copy of step k+1 overlaps the kernels of step k.  Steps execute in submission order. */
+ASR_API int asr_submit(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t want_logprobs, int32_t* ticket);
+ASR_API int asr_collect(AsrEngine* e, int32_t ticket, const AsrStepOut* out);
+
 /* Same, split for pipelining / device-resident timing: stage = H2D of inputs; run = kernels only (async on the
  * engine stream); fetch = D2H of results + synchronise. */
 ASR_API int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format);
 ASR_API int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs);
 ASR_API int asr_fetch(AsrEngine* e, int32_t n, const AsrStepOut* out);
 ASR_API int asr_sync(AsrEngine* e);
-/* Zero-copy input: the engine's pinned host staging buffer for PCM (capacity max_batch * chunk_length * 4 bytes).  A caller
- * that assembles its batch directly in this buffer passes the returned pointer as `pcm` to asr_step / asr_stage and the
- * host-side copy is skipped (the websocket receive path can write chunks straight into pinned memory). */
+/* Zero-copy input: the pinned host staging buffer the NEXT asr_step / asr_submit will read (two alternate; capacity
+ * max_batch * chunk_length * 4 bytes).  A caller that assembles its batch directly in this buffer passes the returned pointer
+ * as `pcm` and the host-side copy is skipped (the websocket receive path can write chunks straight into pinned memory). */
 ASR_API void* asr_pinned_pcm(AsrEngine* e, uint64_t* capacity_bytes);
 ASR_API void* asr_stream_handle(AsrEngine* e);      /* cudaStream_t the engine launches on (for CUDA-event timing) */
 

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
   __shared__ WarpState ws_all[BW];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * BW + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (w >= P.n) return;
   WarpState& S = ws_all[warp];
   const int slot = P.slots[w];
@@ -217,8 +219,7 @@ int beam_launch(const BeamParams& P, cudaStream_t st) {
     set_error("beam: unsupported parameters (beam %d <= %d, cand_k %d <= %d, vocab %d)", P.beam, BEAM_MAX, P.cand_k, BEAM_CAND_MAX, P.vocab);
     return -1;
   }
-  beam_kernel<<<(P.n + BW - 1) / BW, BW * 32, 0, st>>>(P);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(beam_kernel, dim3((P.n + BW - 1) / BW), dim3(BW * 32), 0, st, P));
   return 0;
 }
 

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 namespace asr {
 
 typedef __nv_bfloat16 bf16;
@@ -46,6 +48,30 @@ struct Geo {
   } while (0)
 
 void set_error(const char* fmt, ...);
+
+// Programmatic dependent launch: every kernel of the per-step chain is launched with programmaticStreamSerialization, calls
+// pdl_launch_dependents() early (the next kernel's CTAs may be scheduled as soon as SM resources free up and run their
+// prologue: barrier init, TMEM allocation, tensor-map prefetch, table loads) and pdl_wait() before its first access to memory
+// produced by a predecessor (griddepcontrol.wait returns once all prerequisite grids have completed and flushed).
+// Measured on B200: +15 % at 256 streams (2.35 -> 2.05 ms/step), -3.5 % at 4096 streams (launch latency is already hidden
+// behind 100+ us kernels and early-resident dependents only take SM slots), so the engine enables it per step for small
+// batches only.  ASR_B200_NO_PDL=1 falls back to plain stream order everywhere.
+bool pdl_enabled();
+void pdl_set_active(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Small device helpers

@@ -25,6 +25,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local bool g_pdl_active = true;
+void pdl_set_active(bool on) { g_pdl_active = on; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("ASR_B200_NO_PDL"); return !(v && v[0] == '1'); }();
+  return on && g_pdl_active;
+}
+
 namespace {
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -74,6 +81,7 @@ struct AsrEngine {
   int device = 0, num_sms = 148;
   int simt_gemm = 0;
   int no_pair = 0;
+  int pdl_max_streams = 1536;   // programmatic dependent launch below this batch size (see common.cuh)
   int staged_fmt = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;
@@ -262,16 +270,19 @@ int make_operand(AsrEngine* e, Operand* a, int rows, int K) {
 }
 
 int pick_bn(const AsrEngine* e, int M, int N) {
-  // Largest N tile that still gives every SM a tile; small problems (few streams) take the smallest tile so the
-  // chunk latency is spread over more SMs.  Ragged N (vocab 804) is fine: TMA zero-fills, the epilogue masks.
+  // N-tile width by a two-term cost model fitted to the B200 sweeps (profiles/r01_gemm_sweep_16warp_epilogue.txt):
+  // time ~ rounds(bn) * (bn + 64), rounds = ceil(tiles / SMs); the +64 is the per-tile fixed cost (pipeline fill, epilogue
+  // drain).  Large problems get 256-wide tiles, a single stream gets 64-wide ones so its latency spreads over more SMs.
+  // Ragged N (vocab 804) is fine: TMA zero-fills, the epilogue masks.
   const int mt = (M + 127) / 128;
-  int last = 64;
+  int best = 64; long best_cost = -1;
   for (int bn : {256, 128, 64}) {
     if (bn > 64 && bn / 2 >= N) continue;
-    last = bn;
-    if (mt * ((N + bn - 1) / bn) >= e->num_sms) return bn;
+    const long tiles = (long)mt * ((N + bn - 1) / bn);
+    const long cost = ((tiles + e->num_sms - 1) / e->num_sms) * (bn + 64);
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
   }
-  return last;
+  return best;
 }
 
 cudaEvent_t prof_event(AsrEngine* e) {
@@ -378,6 +389,7 @@ BeamParams beam_params(AsrEngine* e, int n) {
 
 int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool with_ctc, bool want_logprobs) {
   if (e->beam > 0) want_logprobs = true;
+  pdl_set_active(n <= e->pdl_max_streams);
   const Geo& g = e->geo;
   if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
   // input_linear (encoder.py:142, no bias); its [n*frames, d/stride] output *is* the time-reduced [n*rows, d] (common.py:118-119)
@@ -585,6 +597,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   e->simt_gemm = dbg && dbg[0] == '1';
   const char* np_ = getenv("ASR_B200_NO_PAIR_GEMM");
   e->no_pair = np_ && np_[0] == '1';
+  if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
   int rc = -1;
   do {
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); break; }

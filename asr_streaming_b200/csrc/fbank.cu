@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(kWarps * 32) fbank_kernel(FbankParams P) {
   for (int i = tid; i < NC; i += blockDim.x) s_tw[i] = P.tw[i];
   for (int i = tid; i <= NC; i += blockDim.x) s_w2[i] = P.w2[i];
   for (int i = tid; i < P.frame_len; i += blockDim.x) s_win[i] = P.window[i];
+  pdl_launch_dependents();
+  pdl_wait();                                              // the tables above are constants; PCM / outputs are not
   {
     // 16-byte vectorised, coalesced PCM stage-in (stream base is 16B aligned: pcm_stride * sizeof(PcmT) % 16 == 0)
     const int n_vec = (P.n_samples * (int)sizeof(PcmT)) / 16;
@@ -180,8 +182,7 @@ int launch(const FbankParams& P, int n_streams, cudaStream_t st) {
     ASR_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<NC, PcmT, KALDI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  fbank_kernel<NC, PcmT, KALDI><<<n_streams, kWarps * 32, smem, st>>>(P);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(fbank_kernel<NC, PcmT, KALDI>, dim3(n_streams), dim3(kWarps * 32), smem, st, P));
   return 0;
 }
 

@@ -224,6 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_launch_dependents();
+  pdl_wait();                                              // A operand / residual / slot tables come from predecessor kernels
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -387,6 +389,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                                      // peer's barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -478,8 +482,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmPro
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P_BN - 1) / P_BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  gemm_tc2_kernel<Epi><<<2 * pairs, kThreads, P_SMEM_BYTES, st>>>(tmA, tmB128, p, epi);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi>, dim3(2 * pairs), dim3(kThreads), P_SMEM_BYTES, st, tmA, tmB128, p, epi));
   return 0;
 }
 
@@ -493,8 +496,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem&
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN, Epi><<<grid, Cfg::kThreadsCta, Cfg::kSmemBytes, st>>>(tmA, tmB, p, epi);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, Epi>, dim3(grid), dim3(Cfg::kThreadsCta), Cfg::kSmemBytes, st, tmA, tmB, p, epi));
   return 0;
 }
 

@@ -65,6 +65,8 @@ __device__ __forceinline__ void ln_store_operand(bf16* __restrict__ o, int lo_of
 __global__ void __launch_bounds__(256) ln_to_operand_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                                                             bf16* __restrict__ out, int ld, int lo_off, int M) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= M) return;
   float v[LN_V * 4];
   ln_load(x + (size_t)row * LN_D, lane, v);
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(256) ln_out_fused_kernel(const float* __restri
                                                            float* __restrict__ y, const float* __restrict__ g2, const float* __restrict__ b2,
                                                            bf16* __restrict__ out, int ld, int lo_off, int M, int rows, int seg_rows) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= M) return;
   float v[LN_V * 4];
   ln_load(x2 + (size_t)row * LN_D, lane, v);
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_kernel(AttnParams<T> 
   float* s_q = at_smem + warp * (ROWS * AT_DH + AT_MAXK * AT_KST + AT_MAXK * ROWS);
   float* s_kv = s_q + ROWS * AT_DH;
   float* s_p = s_kv + AT_MAXK * AT_KST;                   // pT[key][ROWS]
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int slot = P.slots[b];
   const int pl = P.past_len[slot];
@@ -236,6 +242,8 @@ __global__ void __launch_bounds__(AM_WARPS * 32, 2) attention_mma_kernel(AttnPar
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int b = blockIdx.x, head = warp;
+  pdl_launch_dependents();
+  pdl_wait();
   const int slot = P.slots[b];
   const int pl = P.past_len[slot];
   const int lv = pl < P.left ? pl : P.left;
@@ -400,8 +408,7 @@ int attention_mma_launch(const AttnParams<bf16>& P, int n_streams, cudaStream_t 
     ASR_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  attention_mma_kernel<ROWS><<<n_streams, AM_WARPS * 32, smem, st>>>(P);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(attention_mma_kernel<ROWS>, dim3(n_streams), dim3(AM_WARPS * 32), smem, st, P));
   return 0;
 }
 
@@ -415,8 +422,7 @@ int attention_launch_rows(const AttnParams<T>& P, int n_streams, cudaStream_t st
     attr = true;
   }
   dim3 grid(n_streams, P.n_heads / AT_WARPS);
-  attention_kernel<T, ROWS><<<grid, AT_WARPS * 32, smem, st>>>(P);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(attention_kernel<T, ROWS>, grid, dim3(AT_WARPS * 32), smem, st, P));
   return 0;
 }
 
@@ -430,6 +436,8 @@ constexpr int CTC_MAXV = 32;   // vocab <= 1024
 __global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
   __shared__ int s_ids[64];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int r = warp; r < P.seg_rows; r += 8) {
     const size_t row = (size_t)b * P.seg_rows + r;
     const float* z = P.logits + row * P.vocab;
@@ -513,8 +521,7 @@ __global__ void fill_i32_kernel(int* p, int v, size_t n) {
 int ln_to_operand(const float* x, const float* g, const float* b, bf16* out, int ld, int lo_off, int M, int d, cudaStream_t st) {
   if (M <= 0) return 0;
   if (d != LN_D) { set_error("layer norm kernels are built for d_model = %d (got %d)", LN_D, d); return -1; }
-  ln_to_operand_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, b, out, ld, lo_off, M);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(ln_to_operand_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, g, b, out, ld, lo_off, M));
   return 0;
 }
 
@@ -522,8 +529,7 @@ int ln_out_fused(const float* x2, const float* g1, const float* b1, float* y, co
                  int lo_off, int M, int d, int rows, int seg_rows, cudaStream_t st) {
   if (M <= 0) return 0;
   if (d != LN_D) { set_error("layer norm kernels are built for d_model = %d (got %d)", LN_D, d); return -1; }
-  ln_out_fused_kernel<<<(M + 7) / 8, 256, 0, st>>>(x2, g1, b1, y, g2, b2, out, ld, lo_off, M, rows, seg_rows);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(ln_out_fused_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x2, g1, b1, y, g2, b2, out, ld, lo_off, M, rows, seg_rows));
   return 0;
 }
 
@@ -551,8 +557,7 @@ template int attention_launch<bf16>(const AttnParams<bf16>&, int, cudaStream_t);
 int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return 0;
   if (P.vocab > 32 * CTC_MAXV || P.seg_rows > 64) { set_error("ctc: vocab %d / seg_rows %d too large", P.vocab, P.seg_rows); return -1; }
-  ctc_greedy_kernel<<<n_streams, 256, 0, st>>>(P);
-  ASR_CUDA_OK(cudaGetLastError());
+  ASR_CUDA_OK(launch_pdl(ctc_greedy_kernel, dim3(n_streams), dim3(256), 0, st, P));
   return 0;
 }
 

@@ -33,6 +33,7 @@ WORKLOADS = {
     "streams4096": (4096, "configs[3] batch size: 4096 concurrent streams, chunk_size=16, greedy CTC"),
     "streams10240": (10240, "north-star target: 10,240 concurrent streams, chunk_size=16, greedy CTC"),
     "fbank1024": (1024, "configs[1]: fbank-only, 1024 streams x 640 ms, 80-bin Kaldi fbank"),
+    "lowlat4096": (4096, "configs[4] per-GPU share: 4096 concurrent streams per GPU, chunk_size=8 low-latency mode (320 ms chunks), greedy CTC"),
 }
 FLOP_PER_STREAM_CHUNK = 2_583_363_584          # SURVEY.md §8a (L_valid = 32)
 
@@ -182,7 +183,8 @@ def run_ours(args):
     pk = peaks()
     fbank_only = args.workload.startswith("fbank")
 
-    cfg = ModelConfig(precision=precision, max_batch=streams, max_sessions=streams)
+    low_latency = args.workload.startswith("lowlat")
+    cfg = ModelConfig(precision=precision, max_batch=streams, max_sessions=streams, segment_size=32 if low_latency else 64)
     blob = pack_weights(random_weights(WEIGHT_SEED, cfg), cfg)
     eng = Engine(cfg, blob, local)
     ext = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
@@ -292,7 +294,7 @@ def run_ours(args):
             if s_n == streams:
                 continue
             eng.close()
-            cfg2 = ModelConfig(precision=precision, max_batch=s_n, max_sessions=s_n)
+            cfg2 = ModelConfig(precision=precision, max_batch=s_n, max_sessions=s_n, segment_size=cfg.segment_size)
             eng = Engine(cfg2, blob, local)
             ext2 = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
             sl = [eng.open_session() for _ in range(s_n)]
@@ -307,7 +309,7 @@ def run_ours(args):
             b.record(ext2)
             eng.sync()
             ms = a.elapsed_time(b) / 5
-            sweep.append({"streams": s_n, "ms_per_step": ms, "audio_s_per_s": s_n * 0.64 / (ms / 1e3)})
+            sweep.append({"streams": s_n, "ms_per_step": ms, "audio_s_per_s": s_n * (cfg.segment_length / cfg.sample_rate) / (ms / 1e3)})
 
     if rank == 0:
         fam = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items() if v[1]}
@@ -321,24 +323,27 @@ def run_ours(args):
             M = streams * cfg.rows
             gemm_flops = {"gemm_qkv": 2 * M * 1536 * 512, "gemm_out_proj": 2 * M * 512 * 512, "gemm_ffn1": 2 * M * 2048 * 512,
                           "gemm_ffn2": 2 * M * 512 * 2048}
+            keys = cfg.rc_rows + cfg.left_context + cfg.seg_rows
+            flop_sc = (20 * sum(gemm_flops.values()) // streams + 2 * cfg.frames * 128 * 128 + 2 * cfg.seg_rows * (512 * 512 + 512 * 804)
+                       + 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
             dom = max(gemm_flops, key=lambda k: fam[k]["ms_per_step"])
             t = fam[dom]["ms_per_step"] / fam[dom]["launches_per_step"]
             mult = 3 if precision == PRECISION_EXACT else 1
             ach = gemm_flops[dom] / (t / 1e3) / 1e12
             all_gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
-            all_gemm_flop = streams * (FLOP_PER_STREAM_CHUNK - 20 * 2_129_920)
+            all_gemm_flop = streams * (flop_sc - 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
             roof = {"kernel": f"gemm_tc_kernel ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(args.workload if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,
                     "all_gemms": {"ms_per_step": all_gemm_ms, "tflops": all_gemm_flop / (all_gemm_ms / 1e3) / 1e12}}
-            extra["path_roofline"] = {"flop_per_stream_chunk": FLOP_PER_STREAM_CHUNK,
-                                      "achieved_tflops": streams * FLOP_PER_STREAM_CHUNK * world * args.steps / (dev_ms / 1e3) / 1e12,
-                                      "frac_of_tensor_peak": streams * FLOP_PER_STREAM_CHUNK * args.steps / (dev_ms / 1e3) / 1e12 / pk["bf16_tflops"]}
+            extra["path_roofline"] = {"flop_per_stream_chunk": flop_sc,
+                                      "achieved_tflops": streams * flop_sc * world * args.steps / (dev_ms / 1e3) / 1e12,
+                                      "frac_of_tensor_peak": streams * flop_sc * args.steps / (dev_ms / 1e3) / 1e12 / pk["bf16_tflops"]}
         line = {
             "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == PRECISION_FAST else "bf16x3-split (fp32-equivalent)", "data": "synthetic",
-            "config": {"workload": desc, "streams_per_gpu": streams, "chunk_ms": 640, "weights": f"random-init seed {WEIGHT_SEED}",
+            "config": {"workload": desc, "streams_per_gpu": streams, "chunk_ms": int(1000 * cfg.segment_length / cfg.sample_rate), "weights": f"random-init seed {WEIGHT_SEED}",
                        "l2": "no explicit flush: per-step working set (bf16 weights 128 MB + K/V rings %.0f MB + activations) exceeds the 126 MB L2"
                              % (streams * 1.97), "parallelism": f"sessions partitioned per GPU x{world}, no collective"},
             "clocks": clocks,
@@ -351,7 +356,7 @@ def run_ours(args):
                                   "what": "synchronous Engine.step of the whole batch from pinned host memory: H2D + kernels + D2H of ids"}
                                  if lat_ms else None),
             # real-time capacity: every stream needs one chunk per 640 ms; ticks of this batch size back to back
-            "realtime_streams_per_gpu": (int(streams * 640.0 / (1e3 * e2e_s / args.steps)) if not fbank_only else None),
+            "realtime_streams_per_gpu": (int(streams * (1e3 * cfg.segment_length / cfg.sample_rate) / (1e3 * e2e_s / args.steps)) if not fbank_only else None),
         }
         line.update(extra)
         if world == 1 and not fbank_only and not args.no_sweep:

@@ -45,6 +45,8 @@ SIGNATURES = {
     "asr_session_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "asr_session_reset": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_session_close": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_session_reset_many": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "asr_gather_pcm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
     "asr_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "asr_collect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),

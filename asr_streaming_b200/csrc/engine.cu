@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/asr_b200.h"
@@ -777,6 +778,53 @@ int asr_session_reset(AsrEngine* e, int32_t slot) {
   if (slot < 0 || slot >= e->cfg.max_sessions || !e->slot_open[slot]) { set_error("slot %d is not an open session", slot); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   return reset_slot(e, slot);
+}
+
+int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
+  if (!e || (n > 0 && !slots)) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n <= 0) return 0;
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= e->cfg.max_sessions || !e->slot_open[slots[i]]) { set_error("slot %d is not an open session", slots[i]); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  DevBuf d;
+  if (d.alloc(4 * (size_t)n)) return -1;
+  int rc = -1;
+  do {
+    if (cudaMemcpyAsync(d.p, slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) { set_error("H2D failed"); break; }
+    if (reset_slots_launch(d.as<int>(), n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) break;
+    if (e->beam > 0) {
+      bool ok = true;
+      for (int i = 0; i < n && ok; ++i) ok = !beam_reset_launch(beam_params(e, 0), slots[i], e->cfg.max_sessions, e->stream);
+      if (!ok) break;
+    }
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("reset_many: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    rc = 0;
+  } while (0);
+  d.free();
+  return rc;
+}
+
+/* Batch assembly in native code: copies, for i < n, chunk_length samples starting at base[rows[i] * row_stride + offsets[i]] into
+ * row i of the pinned staging buffer of the next step (multi-threaded memcpy).  Returns that buffer through *pinned_out. */
+int asr_gather_pcm(AsrEngine* e, int32_t n, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets, void** pinned_out) {
+  if (!e || !base || (n > 0 && (!rows || !offsets))) { set_error("null argument"); return -1; }
+  if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch]", n); return -1; }
+  int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[e->cur_buf]);
+  const size_t L = e->geo.chunk_len;
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nt = std::max(1, std::min({8, hw > 0 ? hw : 1, n / 64 + 1}));
+  auto work = [&](int t) {
+    for (int i = t; i < n; i += nt) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  if (pinned_out) *pinned_out = dst;
+  return 0;
 }
 
 int asr_session_close(AsrEngine* e, int32_t slot) {

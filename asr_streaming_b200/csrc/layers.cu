@@ -512,6 +512,13 @@ __global__ void subtract_mean_kernel(float* __restrict__ x, int n_frames, int n_
   }
 }
 
+__global__ void reset_slots_kernel(const int* __restrict__ slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = slots[i];
+    past_len[s] = 0; n_frames[s] = 0; prev_id[s] = -1; last_tok[s] = -1;
+  }
+}
+
 __global__ void fill_i32_kernel(int* p, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -569,6 +576,13 @@ int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int 
 
 int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cudaStream_t st) {
   subtract_mean_kernel<<<n_streams, 128, 0, st>>>(x, n_frames, n_mels);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, cudaStream_t st) {
+  if (n <= 0) return 0;
+  reset_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(slots, n, past_len, n_frames, prev_id, last_tok);
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -26,6 +26,8 @@ class StepResult:
     logprobs: Optional[np.ndarray]         # [n, S, V] float32 or None
     beam_tokens: Optional[List[np.ndarray]] = None   # n arrays: best prefix-beam hypothesis of the utterance so far
     beam_score: Optional[np.ndarray] = None          # [n] log-probability of that hypothesis
+    n_new: Optional[np.ndarray] = None               # [n] int32: len(new_tokens[i])
+    new_tokens_padded: Optional[np.ndarray] = None   # [n, S] int32, row i valid in [:n_new[i]] (struct-of-arrays form)
 
     def last_blank(self, i: int) -> float:
         """The reference's ``last_blank`` (recognition.py:38-43): python float 0.04*T when the segment has no
@@ -95,6 +97,26 @@ class Engine:
     def reset_session(self, slot: int) -> None:
         _lib.check(self.lib, self.lib.asr_session_reset(self._h, slot), "asr_session_reset")
 
+    def reset_sessions(self, slots: Sequence[int]) -> None:
+        """Endpoint on many sessions in one launch."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        if sl.size:
+            _lib.check(self.lib, self.lib.asr_session_reset_many(self._h, int(sl.size), sl.ctypes.data), "asr_session_reset_many")
+
+    def gather_pcm(self, audio: np.ndarray, rows: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """Native batch assembly: chunk i = audio[rows[i], offsets[i] : offsets[i] + chunk_length] -> row i of the pinned staging
+        buffer of the next step.  Returns the [n, chunk_length] view to pass to step()/submit()."""
+        assert audio.dtype == np.int16 and audio.flags.c_contiguous and audio.ndim == 2
+        rows = np.ascontiguousarray(rows, np.int32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = int(rows.size)
+        out = C.c_void_p()
+        _lib.check(self.lib, self.lib.asr_gather_pcm(self._h, n, audio.ctypes.data, audio.shape[1], rows.ctypes.data, offsets.ctypes.data,
+                                                     C.byref(out)), "asr_gather_pcm")
+        L = self.cfg.chunk_length
+        buf = (C.c_char * (n * L * 2)).from_address(out.value)
+        return np.frombuffer(buf, dtype=np.int16, count=n * L).reshape(n, L)
+
     def close_session(self, slot: int) -> None:
         _lib.check(self.lib, self.lib.asr_session_close(self._h, slot), "asr_session_close")
 
@@ -128,7 +150,8 @@ class Engine:
     @staticmethod
     def _result(bufs, n) -> StepResult:
         new = [bufs["newtok"][i, :bufs["nnew"][i]].copy() for i in range(n)]
-        r = StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"])
+        r = StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"],
+                       n_new=bufs["nnew"], new_tokens_padded=bufs["newtok"])
         if "btok" in bufs:
             r.beam_tokens = [bufs["btok"][i, :bufs["blen"][i]].copy() for i in range(n)]
             r.beam_score = bufs["bscore"]

@@ -1,148 +1,340 @@
 """Ragged session batching: packs every stream that has a full chunk buffered into ONE engine step per tick.
 
-Host-side mirror of the reference's per-connection loop (streaming_decoder/streaming_server.py:367-470) and of the v1
+Host-side mirror of the reference's per-connection loop (streaming_decoder/streaming_server.py:367-546) and of the v1
 cross-stream batcher ``StreamingE2E.process`` (streaming_decoder_v1/streaming_asr.py:41-119), with the buffer semantics of
-``Stream`` (streaming_decoder/stream.py:23-26 initial zero buffer, :78-87 accept_waveform, :159-160 advance by
-segment_length).  Streams progress independently: a tick may mix first chunks (no left context), steady-state chunks,
-and streams that were just reset by an endpoint; the device applies per-stream left-context validity.
-Sessions never interact, so a multi-GPU box partitions them per GPU (GpuRouter) with no collective.
+``Stream`` (streaming_decoder/stream.py:23-26 initial zero buffer, :78-87 accept_waveform, :110-125 update_stream,
+:127-163 endpoint_detected, :159-160 advance by segment_length, :166-189 VAD skip).  Streams progress independently: a tick
+may mix first chunks (no left context), steady-state chunks and streams that were just reset by an endpoint; the device
+applies per-stream left-context validity.
+
+Scale: session state is struct-of-arrays numpy (one row per session), so a tick over thousands of sessions is a handful
+of vectorised operations plus one native multi-threaded gather into the engine's pinned staging buffer
+(``asr_gather_pcm``); endpoint rules (online_endpoint.py:42-94) are evaluated for all sessions at once and the endpoints
+of a tick are one ``asr_session_reset_many`` launch.  Sessions never interact, so a multi-GPU box partitions them per GPU
+(``GpuRouter``) with no collective.
 """
 from __future__ import annotations
 
 import threading
-from collections import deque
-from typing import Deque, Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 
 from .config import ModelConfig
-from .engine import Engine, FRAMERATE, StepResult
+from .endpoint import EndpointRules
+from .engine import FRAMERATE
 from .recognition import ids_to_text
+
+MAX_TOKENS = 512          # tokens kept per utterance segment (an utterance is force-ended at 40 s, asr-online.yaml:103-107)
 
 
 class StreamSession:
-    """Per-websocket state the hot path needs (subset of ``Stream``, stream.py:10-64)."""
+    """Handle of one websocket session (row of the scheduler's tables); exposes the fields of ``Stream`` the hot path uses."""
 
-    def __init__(self, sid: int, slot: int, cfg: ModelConfig):
-        self.id, self.slot, self.cfg = sid, slot, cfg
-        self.audio = np.zeros(cfg.buffer_length, np.int16)          # stream.py:23 (buffer_length leading zeros)
-        self.length_of_segment = cfg.buffer_length                  # stream.py:26
-        self.tokens: List[int] = []
-        self.n_frames = 0
-        self.chunk_processed = 0
-        self.chunk_processed_total = 0
-        self.trailing_blank_duration = 0.0
-        self.is_contain_token = False
-        self.segment = 0
-        self.gpu = 0
+    __slots__ = ("sched", "row", "id", "gpu")
 
+    def __init__(self, sched: "SessionScheduler", row: int, sid: int):
+        self.sched, self.row, self.id, self.gpu = sched, row, sid, 0
+
+    # -- audio in (stream.py:78-87) -------------------------------------------------------------------
     def accept_waveform(self, pcm: np.ndarray) -> None:
-        """stream.py:78-87 (messages of <= 100 samples are dropped).  int16, or float in [-1, 1) (converted)."""
-        if pcm.dtype != np.int16:
-            pcm = np.clip(np.round(pcm.astype(np.float32) * 32768.0), -32768, 32767).astype(np.int16)
-        if pcm.size > 100:
-            self.audio = np.concatenate([self.audio, pcm.reshape(-1)])
-            self.length_of_segment += pcm.size
+        self.sched.accept(self, pcm)
 
     def ready(self) -> bool:
-        return self.length_of_segment >= self.cfg.chunk_length        # streaming_server.py:371
+        s = self.sched
+        return bool(s.wr[self.row] - s.rd[self.row] >= s.cfg.chunk_length)        # streaming_server.py:371
 
-    def chunk(self) -> np.ndarray:
-        return self.audio[:self.cfg.chunk_length]                     # streaming_server.py:384
+    # -- state the server reads ------------------------------------------------------------------------
+    @property
+    def slot(self) -> int:
+        return int(self.sched.slot[self.row])
 
-    def advance(self) -> None:
-        self.audio = self.audio[self.cfg.segment_length:]             # stream.py:159-160
-        self.length_of_segment -= self.cfg.segment_length
+    @property
+    def length_of_segment(self) -> int:
+        return int(self.sched.wr[self.row] - self.sched.rd[self.row])
+
+    @property
+    def tokens(self) -> List[int]:
+        s = self.sched
+        return [int(t) for t in s.tok[self.row, :s.ntok[self.row]]]
 
     @property
     def text(self) -> str:
         return ids_to_text(self.tokens)
 
+    @property
+    def n_frames(self) -> int:
+        return int(self.sched.n_frames[self.row])
+
+    @property
+    def chunk_processed(self) -> int:
+        return int(self.sched.chunk_processed[self.row])
+
+    @property
+    def trailing_blank_duration(self) -> float:
+        return float(self.sched.trailing[self.row])
+
+    @property
+    def is_contain_token(self) -> bool:
+        return bool(self.sched.contain_token[self.row])
+
+    @property
+    def segment(self) -> int:
+        return int(self.sched.segment[self.row])
+
+
+@dataclass
+class TickResult:
+    """Outcome of one tick, struct-of-arrays (n = streams run through the model this tick)."""
+    sessions: List[StreamSession] = field(default_factory=list)     # the n sessions, in batch order
+    n_new: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))          # [n]
+    new_tokens: np.ndarray = field(default_factory=lambda: np.zeros((0, 0), np.int32))  # [n, S], valid [:n_new]
+    logprobs: Optional[np.ndarray] = None                            # [n, S, V] when requested
+    beam_tokens: Optional[List[np.ndarray]] = None
+    skipped: List[StreamSession] = field(default_factory=list)       # VAD-gated chunks (not run)
+    final: np.ndarray = field(default_factory=lambda: np.zeros(0, bool))              # [n] endpoint fired after this chunk
+    final_rule: List[Optional[str]] = field(default_factory=list)    # rule name per session (None if not final)
+    final_tokens: Dict[int, List[int]] = field(default_factory=dict)  # session id -> tokens of the finished segment
+
+    def __iter__(self):
+        """(session, new token ids, logprobs | None) — the shape of the first-generation API."""
+        for i, s in enumerate(self.sessions):
+            yield s, [int(t) for t in self.new_tokens[i, :self.n_new[i]]], (self.logprobs[i] if self.logprobs is not None else None)
+
+    def __len__(self):
+        return len(self.sessions)
+
+
+def energy_gate(threshold: int = 328):
+    """Vectorised stand-in for the WebRTC / Silero VAD gate (both absent here): speech iff the new 640 ms of the
+    chunk peaks above ``threshold`` int16 units (default 1 % of full scale).  Marks itself as vectorised for the scheduler."""
+    def gate(chunks: np.ndarray, buffer_length: int) -> np.ndarray:
+        return np.abs(chunks[:, buffer_length:]).max(axis=1) >= threshold
+    gate.vectorised = True
+    return gate
+
 
 class SessionScheduler:
     """One engine (one GPU).  ``tick()`` = one launch chain over all ready streams (up to max_batch)."""
 
-    def __init__(self, engine: Engine):
+    def __init__(self, engine, capacity: Optional[int] = None, backlog_chunks: int = 4,
+                 endpoint_rules: Optional[EndpointRules] = None, relative_cost: float = 10.0):
         self.engine, self.cfg = engine, engine.cfg
-        self.sessions: Dict[int, StreamSession] = {}
+        cfg = self.cfg
+        self.capacity = capacity or cfg.max_sessions
+        self.CAP = cfg.chunk_length + backlog_chunks * cfg.segment_length
+        n = self.capacity
+        self.audio = np.zeros((n, self.CAP), np.int16)
+        self.rd = np.zeros(n, np.int64)
+        self.wr = np.zeros(n, np.int64)
+        self.active = np.zeros(n, bool)
+        self.slot = np.full(n, -1, np.int32)
+        self.tok = np.zeros((n, MAX_TOKENS), np.int32)
+        self.ntok = np.zeros(n, np.int32)
+        self.n_frames = np.zeros(n, np.int64)
+        self.chunk_processed = np.zeros(n, np.int64)
+        self.chunk_processed_total = np.zeros(n, np.int64)
+        self.trailing = np.zeros(n, np.float64)
+        self.contain_token = np.zeros(n, bool)
+        self.segment = np.zeros(n, np.int64)
+        self.last_served = np.zeros(n, np.int64)          # service sequence number of the last service (strict LRU under backlog)
+        self._seq = 0
+        self._tick = 0
+        self._free = list(range(n - 1, -1, -1))
         self._next_id = 0
-        self._rr: Deque[int] = deque()            # round-robin order so a backlog cannot starve old sessions
-        self._fallback_pack = None if hasattr(engine, "pinned_pcm") else np.empty((self.cfg.max_batch, self.cfg.chunk_length), np.int16)
+        self.sessions: Dict[int, StreamSession] = {}       # id -> handle
+        self._by_row: Dict[int, StreamSession] = {}
+        self.endpoint_rules = endpoint_rules
+        self.relative_cost = relative_cost                 # LM relative cost fed to the rules when no ARPA LM is loaded (utils.py:126-139)
+        self._chunk_s = cfg.segment_length / cfg.sample_rate   # 0.64 s (0.32 in low-latency mode)
+        self._fallback_pack = None if hasattr(engine, "gather_pcm") else np.empty((cfg.max_batch, cfg.chunk_length), np.int16)
 
+    # ------------------------------------------------------------------ session lifecycle
     def open(self) -> StreamSession:
-        s = StreamSession(self._next_id, self.engine.open_session(), self.cfg)
+        if not self._free:
+            raise RuntimeError(f"scheduler is full ({self.capacity} sessions)")
+        row = self._free.pop()
+        s = StreamSession(self, row, self._next_id)
         self._next_id += 1
         self.sessions[s.id] = s
-        self._rr.append(s.id)
+        self._by_row[row] = s
+        self.slot[row] = self.engine.open_session()
+        self.audio[row, :self.cfg.buffer_length] = 0            # stream.py:23 (buffer_length leading zeros)
+        self.rd[row], self.wr[row] = 0, self.cfg.buffer_length
+        self.active[row] = True
+        self._clear_segment(np.array([row]))
+        self.chunk_processed_total[row] = 0
+        self.segment[row] = 0
+        self.last_served[row] = self._seq
+        self._seq += 1
         return s
 
     def close(self, s: StreamSession) -> None:
-        self.engine.close_session(s.slot)
+        self.engine.close_session(int(self.slot[s.row]))
+        self.active[s.row] = False
+        self.slot[s.row] = -1
         self.sessions.pop(s.id, None)
-        try:
-            self._rr.remove(s.id)
-        except ValueError:
-            pass
+        self._by_row.pop(s.row, None)
+        self._free.append(s.row)
+
+    def _clear_segment(self, rows: np.ndarray) -> None:
+        self.ntok[rows] = 0
+        self.n_frames[rows] = 0
+        self.chunk_processed[rows] = 0
+        self.contain_token[rows] = False
+        self.trailing[rows] = 0.0
 
     def reset(self, s: StreamSession) -> None:
         """Endpoint: emission := [], state := init (streaming_server.py:514-515, :530; stream.py:152-157)."""
-        self.engine.reset_session(s.slot)
-        s.tokens, s.n_frames = [], 0
-        s.chunk_processed, s.is_contain_token, s.trailing_blank_duration = 0, False, 0.0
-        s.segment += 1
+        self.engine.reset_session(int(self.slot[s.row]))
+        self._clear_segment(np.array([s.row]))
+        self.segment[s.row] += 1
 
-    def skip(self, s: StreamSession) -> None:
-        """VAD said no speech (stream.py:183-189): the chunk is consumed without touching encoder state."""
-        s.trailing_blank_duration += 0.64 * self.cfg.segment_size / 64
-        s.chunk_processed += 1
-        s.chunk_processed_total += 1
-        s.advance()
+    # ------------------------------------------------------------------ audio in
+    def accept(self, s: StreamSession, pcm: np.ndarray) -> None:
+        """stream.py:78-87 (messages of <= 100 samples are dropped).  int16, or float in [-1, 1) (converted)."""
+        pcm = np.asarray(pcm).reshape(-1)
+        if pcm.dtype != np.int16:
+            pcm = np.clip(np.round(pcm.astype(np.float32) * 32768.0), -32768, 32767).astype(np.int16)
+        n = pcm.size
+        if n <= 100:
+            return
+        r = s.row
+        if self.wr[r] + n > self.CAP:                                  # compact: move the unread tail to the front
+            live = int(self.wr[r] - self.rd[r])
+            if live + n > self.CAP:
+                raise BufferError(f"session {s.id}: backlog of {live + n} samples exceeds the {self.CAP}-sample buffer")
+            self.audio[r, :live] = self.audio[r, self.rd[r]:self.wr[r]]
+            self.rd[r], self.wr[r] = 0, live
+        self.audio[r, self.wr[r]:self.wr[r] + n] = pcm
+        self.wr[r] += n
+
+    # ------------------------------------------------------------------ the tick
+    def ready_rows(self) -> np.ndarray:
+        rows = np.nonzero(self.active & (self.wr - self.rd >= self.cfg.chunk_length))[0]
+        if rows.size > self.cfg.max_batch:                            # backlog: longest-waiting first, nobody starves
+            order = np.argsort(self.last_served[rows], kind="stable")
+            rows = rows[order[:self.cfg.max_batch]]
+        return rows
 
     def ready_sessions(self) -> List[StreamSession]:
-        out = []
-        for sid in list(self._rr):
-            s = self.sessions[sid]
-            if s.ready():
-                out.append(s)
-                if len(out) == self.cfg.max_batch:
-                    break
-        return out
+        return [self._by_row[int(r)] for r in self.ready_rows()]
 
-    def tick(self, want_logprobs: bool = False, gate=None) -> List[Tuple[StreamSession, List[int], Optional[np.ndarray]]]:
-        """Runs one step over the ready streams.  ``gate(session, chunk) -> bool`` (optional) is the VAD decision
-        (streaming_server.py:374-379); gated-out streams are skipped.  Returns (session, new token ids, logprobs|None)."""
-        batch = self.ready_sessions()
-        # batch assembly happens directly in the engine's pinned staging buffer of the next step (no second host copy)
-        self._pack = self.engine.pinned_pcm(np.int16) if self._fallback_pack is None else self._fallback_pack
-        run: List[StreamSession] = []
-        for s in batch:
-            if gate is not None and not s.is_contain_token and not gate(s, s.chunk()):
-                self.skip(s)
-            else:
-                self._pack[len(run)] = s.chunk()
-                run.append(s)
-        if not run:
-            return []
-        n = len(run)
-        res: StepResult = self.engine.step([s.slot for s in run], self._pack[:n], want_logprobs)
-        out = []
-        for i, s in enumerate(run):
-            new = [int(t) for t in res.new_tokens[i]]
-            s.tokens.extend(new)
-            s.n_frames += self.cfg.seg_rows
-            # update_stream (stream.py:110-125)
-            s.chunk_processed += 1
-            s.chunk_processed_total += 1
-            if s.tokens:
-                s.trailing_blank_duration = res.last_blank(i)
-                s.is_contain_token = True
-            else:
-                s.trailing_blank_duration += 0.64 * self.cfg.segment_size / 64
-            s.advance()
-            self._rr.remove(s.id)
-            self._rr.append(s.id)
-            out.append((s, new, res.logprobs[i] if res.logprobs is not None else None))
-        return out
+    def _advance(self, rows: np.ndarray) -> None:
+        self.rd[rows] += self.cfg.segment_length                      # stream.py:159-160
+        self.last_served[rows] = self._seq + np.arange(rows.size)
+        self._seq += int(rows.size)
+
+    def skip(self, s: StreamSession) -> None:
+        self._skip_rows(np.array([s.row]))
+
+    def _skip_rows(self, rows: np.ndarray) -> None:
+        """VAD said no speech (stream.py:183-189): the chunk is consumed without touching encoder state."""
+        self.trailing[rows] += self._chunk_s
+        self.chunk_processed[rows] += 1
+        self.chunk_processed_total[rows] += 1
+        self._advance(rows)
+
+    def tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None) -> TickResult:
+        """One step over the ready streams.  ``gate``: ``energy_gate()`` (vectorised) or ``gate(session, chunk) -> bool``
+        (streaming_server.py:374-379); it is consulted only for streams without a token in the current segment, and
+        gated-out chunks are skipped.  Endpoint rules, when configured, are evaluated after the step for every served
+        stream; fired endpoints reset encoder state and are reported in ``TickResult.final*``."""
+        self._tick += 1
+        cfg = self.cfg
+        rows = self.ready_rows()
+        res = TickResult()
+        if rows.size == 0:
+            return res
+        # ---- VAD gate
+        if gate is not None:
+            need = ~self.contain_token[rows]
+            keep = np.ones(rows.size, bool)
+            if need.any():
+                if getattr(gate, "vectorised", False):
+                    idx = rows[need]
+                    chunks = np.stack([self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length] for r in idx]) if idx.size else np.zeros((0, cfg.chunk_length), np.int16)
+                    keep[need] = gate(chunks, cfg.buffer_length)
+                else:
+                    for j in np.nonzero(need)[0]:
+                        r = int(rows[j])
+                        keep[j] = bool(gate(self._by_row[r], self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length]))
+            skipped = rows[~keep]
+            if skipped.size:
+                res.skipped = [self._by_row[int(r)] for r in skipped]
+                self._skip_rows(skipped)
+            rows = rows[keep]
+            if rows.size == 0:
+                self._endpoints(np.array([r.row for r in res.skipped]), res, np.zeros(0, np.int64))
+                return res
+        n = int(rows.size)
+        # ---- batch assembly straight into the pinned staging buffer of the next step
+        if self._fallback_pack is None:
+            pcm = self.engine.gather_pcm(self.audio, rows, self.rd[rows])
+        else:
+            pcm = self._fallback_pack[:n]
+            for i, r in enumerate(rows):
+                pcm[i] = self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length]
+        out = self.engine.step(self.slot[rows], pcm, want_logprobs)
+        # ---- vectorised bookkeeping (update_stream, stream.py:110-125)
+        S = cfg.seg_rows
+        if out.n_new is not None:
+            n_new = np.asarray(out.n_new, np.int32)
+            new_tok = np.where(np.arange(S)[None, :] < n_new[:, None], out.new_tokens_padded, 0).astype(np.int32)
+        else:
+            n_new = np.array([len(t) for t in out.new_tokens], np.int32)
+            new_tok = np.zeros((n, S), np.int32)
+            for i, t in enumerate(out.new_tokens):
+                new_tok[i, :len(t)] = t
+        for j in range(int(n_new.max()) if n else 0):
+            m = n_new > j
+            dst = np.minimum(self.ntok[rows[m]] + j, MAX_TOKENS - 1)
+            self.tok[rows[m], dst] = new_tok[m, j]
+        self.ntok[rows] = np.minimum(self.ntok[rows] + n_new, MAX_TOKENS)
+        self.n_frames[rows] += S
+        self.chunk_processed[rows] += 1
+        self.chunk_processed_total[rows] += 1
+        has = np.asarray(out.has_token, bool)              # a frame with id > 1 exists in the segment  <=>  non-empty text
+        blank = np.asarray(out.blank_frames)
+        lb = np.where(has, (blank.astype(np.float32) * np.float32(FRAMERATE)).astype(np.float64), FRAMERATE * blank)
+        self.trailing[rows] = np.where(has, lb, self.trailing[rows] + self._chunk_s)
+        self.contain_token[rows] |= has
+        self._advance(rows)
+        res.sessions = [self._by_row[int(r)] for r in rows]
+        res.n_new, res.new_tokens, res.logprobs, res.beam_tokens = n_new, new_tok, out.logprobs, out.beam_tokens
+        res.final = np.zeros(n, bool)
+        res.final_rule = [None] * n
+        extra = np.array([s.row for s in res.skipped], np.int64)
+        self._endpoints(np.concatenate([rows, extra]) if extra.size else rows, res, rows)
+        return res
+
+    # ------------------------------------------------------------------ endpointing (stream.py:127-163, online_endpoint.py)
+    def _endpoints(self, rows: np.ndarray, res: TickResult, run_rows: np.ndarray) -> None:
+        if self.endpoint_rules is None or rows.size == 0:
+            return
+        utt = self.chunk_processed[rows] * self.cfg.segment_length / self.cfg.sample_rate
+        trailing = np.round(self.trailing[rows], 2)
+        self.trailing[rows] = trailing
+        rc = np.full(rows.size, float(self.relative_cost))
+        fired, which = self.endpoint_rules.detect(utt, trailing, rc)
+        if not fired.any():
+            return
+        frows = rows[fired]
+        for r, w in zip(frows, which[fired]):
+            s = self._by_row[int(r)]
+            res.final_tokens[s.id] = [int(t) for t in self.tok[r, :self.ntok[r]]]
+            pos = np.nonzero(run_rows == r)[0]
+            if pos.size:
+                res.final[pos[0]] = True
+                res.final_rule[pos[0]] = self.endpoint_rules.names[w]
+        if hasattr(self.engine, "reset_sessions"):
+            self.engine.reset_sessions(self.slot[frows])
+        else:
+            for r in frows:
+                self.engine.reset_session(int(self.slot[r]))
+        self._clear_segment(frows)
+        self.segment[frows] += 1
 
 
 class GpuRouter:
@@ -150,8 +342,9 @@ class GpuRouter:
     open(), independent ticks (one host thread per GPU; ctypes releases the GIL during the step).  No collectives:
     the path has no cross-session term."""
 
-    def __init__(self, cfg: ModelConfig, weights: np.ndarray, devices: Sequence[int]):
-        self.schedulers = [SessionScheduler(Engine(cfg, weights, d)) for d in devices]
+    def __init__(self, cfg: ModelConfig, weights: np.ndarray, devices: Sequence[int], **sched_kw):
+        from .engine import Engine
+        self.schedulers = [SessionScheduler(Engine(cfg, weights, d), **sched_kw) for d in devices]
 
     def open(self) -> StreamSession:
         g = min(range(len(self.schedulers)), key=lambda i: len(self.schedulers[i].sessions))
@@ -165,18 +358,18 @@ class GpuRouter:
     def reset(self, s: StreamSession) -> None:
         self.schedulers[s.gpu].reset(s)
 
-    def tick(self, want_logprobs: bool = False):
-        results: List[list] = [[] for _ in self.schedulers]
+    def tick(self, want_logprobs: bool = False, gate=None) -> List[TickResult]:
+        results: List[Optional[TickResult]] = [None] * len(self.schedulers)
 
         def run(i):
-            results[i] = self.schedulers[i].tick(want_logprobs)
+            results[i] = self.schedulers[i].tick(want_logprobs, gate)
 
         threads = [threading.Thread(target=run, args=(i,)) for i in range(len(self.schedulers))]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
-        return [r for rs in results for r in rs]
+        return results
 
 
 def partition_streams(n_streams: int, world_size: int, rank: int) -> range:

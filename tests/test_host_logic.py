@@ -177,11 +177,181 @@ def test_scheduler_round_robin_fairness_and_vad_gate():
     # VAD gate: gated-out chunk advances the buffer and the silence clock, not the encoder (stream.py:183-189)
     s = sch.open()
     s.accept_waveform(np.zeros(10240, np.int16))
-    n_calls = len(eng.calls)
-    sch._rr.rotate(1)                                                 # put the new session first
-    out = sch.tick(gate=lambda sess, chunk: bool(np.abs(chunk).max() > 0))
+    out = []
+    for _ in range(3):                                                # the newcomer queues behind the remaining backlog
+        out += list(sch.tick(gate=lambda sess, chunk: bool(np.abs(chunk).max() > 0)))
     assert s.id not in [x.id for x, _, _ in out] and s.chunk_processed == 1 and abs(s.trailing_blank_duration - 0.64) < 1e-9
     assert s.length_of_segment == cfg.buffer_length
+
+
+def _scalar_rule_activated(rule, trailing_silence, utterance_length, relative_cost):
+    """Scalar restatement of online_endpoint.py:42-66 (checker for the vectorised table)."""
+    contains_nonsilence = utterance_length > trailing_silence
+    return ((contains_nonsilence or not rule.must_contain_nonsilence) and trailing_silence >= rule.min_trailing_silence
+            and relative_cost < rule.max_relative_cost and utterance_length >= rule.min_utterance_length)
+
+
+def test_endpoint_rules_vectorised_equals_scalar_first_match():
+    from asr_streaming_b200.endpoint import DEFAULT_RULES, EndpointRules, OnlineEndpointRule, detect_endpointing, load_endpointing_rule
+    rules = dict(DEFAULT_RULES)
+    rules["free"] = OnlineEndpointRule(False, 5.0, 0.0, float("inf"))          # a rule that fires on pure silence
+    tab = EndpointRules(rules)
+    rng = np.random.default_rng(3)
+    n = 4000
+    utt = np.round(rng.integers(0, 70, n) * 0.64, 2)
+    sil = np.round(np.minimum(utt, rng.integers(0, 30, n) * 0.04 + rng.integers(0, 10, n) * 0.64), 2)
+    cost = rng.choice([0.5, 1.99, 2.0, 4.9, 5.0, 7.5, 8.0, 10.0, float("inf")], n)
+    fired, which = tab.detect(utt, sil, cost)
+    names = list(rules)
+    for i in range(n):
+        exp = next((k for k, name in enumerate(names) if _scalar_rule_activated(rules[name], sil[i], utt[i], cost[i])), -1)
+        assert which[i] == exp and fired[i] == (exp >= 0)
+    assert fired.any() and not fired.all() and len(set(which.tolist())) > 4
+    ok, name, over = detect_endpointing(DEFAULT_RULES, 6.4, 1.0, 10.0)
+    assert (ok, name) == (True, "rule1.1") and abs(over) < 1e-12
+    assert detect_endpointing(DEFAULT_RULES, 6.4, 0.96, 10.0) == (False, None, None)
+    assert detect_endpointing(DEFAULT_RULES, 6.4, 0.92, 7.9)[1] == "rule1.2"
+    assert detect_endpointing(DEFAULT_RULES, 40.32, 0.0, 10.0)[1] == "rule4"
+    assert detect_endpointing(DEFAULT_RULES, 1.28, 1.28, 0.0) == (False, None, None)     # only silence so far
+    y = {"a": dict(must_contain_nonsilence=True, min_trailing_silence=1, min_utterance_length=0.0, max_relative_cost=float("inf"))}
+    assert load_endpointing_rule(y)["a"] == DEFAULT_RULES["rule1.1"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/streaming_decoder"), reason="reference tree not present")
+def test_endpoint_rules_match_live_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_online_endpoint", "/root/reference/streaming_decoder/online_endpoint.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from asr_streaming_b200.endpoint import DEFAULT_RULES, EndpointRules
+    import yaml
+    y = yaml.safe_load(open("/root/reference/streaming_decoder/config/asr-online.yaml"))["Endpointing_rules"]["DEFAULT"]
+    ref_rules = ref.load_endpointing_rule(y)
+    assert list(ref_rules) == list(DEFAULT_RULES)
+    for k in ref_rules:
+        for f in ("must_contain_nonsilence", "min_trailing_silence", "min_utterance_length", "max_relative_cost"):
+            assert float(getattr(ref_rules[k], f)) == float(getattr(DEFAULT_RULES[k], f)), (k, f)
+    tab = EndpointRules()
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        utt = round(int(rng.integers(0, 70)) * 0.64, 2)
+        sil = round(min(utt, int(rng.integers(0, 40)) * 0.04), 2)
+        cost = float(rng.choice([0.5, 2.0, 4.9, 5.0, 7.5, 8.0, 10.0]))
+        d, name, _ = ref.detect_endpointing(ref_rules, utt, sil, cost)
+        fired, which = tab.detect([utt], [sil], [cost])
+        assert bool(fired[0]) == bool(d) and (tab.names[which[0]] if d else None) == name
+
+
+class TokenEngine(FakeEngine):
+    """Fake engine whose chunk decodes to a token iff the chunk's last sample is positive; blank frames = 16 - (sample % 17)."""
+
+    def reset_sessions(self, slots):
+        self.resets.extend(int(s) for s in slots)
+
+    def gather_pcm(self, audio, rows, offsets):
+        L = self.cfg.chunk_length
+        return np.stack([audio[r, o:o + L] for r, o in zip(rows, offsets)]) if len(rows) else np.zeros((0, L), np.int16)
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.frames = {}
+
+    def step(self, slots, pcm, want_logprobs=False):
+        slots = [int(s) for s in slots]
+        self.calls.append((slots, pcm.copy()))
+        n, S = len(slots), self.cfg.seg_rows
+        last = pcm[:, -1].astype(np.int64)
+        nnew = (last > 0).astype(np.int32)
+        newtok = np.zeros((n, S), np.int32)
+        newtok[:, 0] = 2 + last % 5
+        blank, has = np.zeros(n, np.int32), np.zeros(n, bool)
+        for i, s in enumerate(slots):
+            st = self.frames.setdefault(s, dict(n=0, last=-1))
+            if s in self.resets:
+                st["n"], st["last"] = 0, -1
+                self.resets = [x for x in self.resets if x != s]
+            if nnew[i]:
+                st["last"] = st["n"] + S - 1 - int(last[i] % S)
+            st["n"] += S
+            has[i] = st["last"] >= 0
+            blank[i] = st["n"] - 1 - st["last"] if has[i] else st["n"]
+        new = [newtok[i, :nnew[i]].copy() for i in range(n)]
+        return A.StepResult(np.zeros((n, S), np.int32), new, blank, has, None, n_new=nnew, new_tokens_padded=newtok)
+
+
+def _stream_py_oracle(chunks_last, S=16):
+    """Per-session scalar restatement of the reference loop (stream.py:110-163 + online_endpoint.py) fed with the TokenEngine's
+    decode rule; returns [(chunk index, rule name)] of the endpoints."""
+    from asr_streaming_b200.endpoint import DEFAULT_RULES
+    out, chunk_processed, trailing, n, last_tok = [], 0, 0.0, 0, -1
+    for k, last in enumerate(chunks_last):
+        if last > 0:
+            last_tok = n + S - 1 - int(last % S)
+        n += S
+        text = last_tok >= 0
+        chunk_processed += 1
+        if text:
+            trailing = float(np.float32(n - 1 - last_tok) * np.float32(0.04))
+        else:
+            trailing += 0.64
+        utt = chunk_processed * 10240 / 16000
+        trailing = round(trailing, 2)
+        name = next((nm for nm, r in DEFAULT_RULES.items() if _scalar_rule_activated(r, trailing, utt, 10.0)), None)
+        if name:
+            out.append((k, name))
+            chunk_processed, trailing, n, last_tok = 0, 0.0, 0, -1
+    return out
+
+
+def test_scheduler_endpointing_matches_scalar_stream_loop():
+    from asr_streaming_b200.endpoint import EndpointRules
+    cfg = A.ModelConfig(max_batch=64, max_sessions=64)
+    eng = TokenEngine(cfg)
+    sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules())
+    rng = np.random.default_rng(11)
+    n_sess, n_chunks = 24, 80
+    ss = [sch.open() for _ in range(n_sess)]
+    lasts = np.where(rng.random((n_sess, n_chunks)) < 0.35, rng.integers(1, 3000, (n_sess, n_chunks)), -rng.integers(0, 3000, (n_sess, n_chunks)))
+    lasts[3] = -5                                        # a session that never says anything: never endpoints (must_contain_nonsilence)
+    lasts[4] = 7                                         # talks all the time: rule4 at 40.32 s (63 chunks)
+    got = {s.id: [] for s in ss}
+    for k in range(n_chunks):
+        for i, s in enumerate(ss):
+            a = np.zeros(cfg.segment_length, np.int16)
+            a[-1] = lasts[i, k]
+            s.accept_waveform(a)
+        res = sch.tick()
+        assert len(res) == n_sess
+        for j, s in enumerate(res.sessions):
+            if res.final[j]:
+                got[s.id].append((k, res.final_rule[j]))
+                assert s.id in res.final_tokens and s.tokens == [] and s.chunk_processed == 0
+    for i, s in enumerate(ss):
+        assert got[s.id] == _stream_py_oracle(lasts[i]), i
+    assert got[ss[3].id] == [] and got[ss[4].id] == [(62, "rule4")]
+    assert sum(len(v) for v in got.values()) > 20
+
+
+def test_scheduler_vectorised_gate_and_backlog_compaction():
+    from asr_streaming_b200.scheduler import energy_gate
+    cfg = A.ModelConfig(max_batch=8, max_sessions=8)
+    eng = TokenEngine(cfg)
+    sch = A.SessionScheduler(eng, backlog_chunks=2)
+    a, b = sch.open(), sch.open()
+    loud = np.full(cfg.segment_length, 1000, np.int16)
+    quiet = np.full(cfg.segment_length, 10, np.int16)
+    for k in range(12):                                   # ring compaction: many more samples than CAP flow through
+        a.accept_waveform(loud + k)
+        b.accept_waveform(quiet)
+        res = sch.tick(gate=energy_gate())
+        assert [s.id for s in res.sessions] == [a.id] and [s.id for s in res.skipped] == [b.id]
+        assert np.array_equal(eng.calls[-1][1][0, cfg.buffer_length:], loud + k)
+        if k:
+            assert np.array_equal(eng.calls[-1][1][0, :cfg.buffer_length], (loud + k - 1)[-cfg.buffer_length:])
+    assert b.chunk_processed == 12 and abs(b.trailing_blank_duration - 12 * 0.64) < 1e-9 and b.n_frames == 0
+    with pytest.raises(BufferError):
+        for _ in range(5):
+            b.accept_waveform(quiet)
 
 
 def test_partition_streams_covers_everything_once():

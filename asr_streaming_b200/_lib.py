@@ -47,6 +47,7 @@ SIGNATURES = {
     "asr_session_close": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_session_reset_many": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "asr_gather_pcm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "asr_pcm_peaks": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
     "asr_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "asr_collect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),

@@ -113,10 +113,19 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction at the scalar issue rate).  The epilogues
+// of the K = 512 GEMMs have ~16 issue slots per output element before they, not the tensor pipe, bound the kernel.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 f2_bcast(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // erf(x) = sign(x) * (1 - 2^q(min(|x|, 4))), q = degree-6 minimax fit of log2(erfc) with zero constant term (weights =
 // d erf / d q); max abs error 3.1e-7 over the whole line in fp32 (fit + check: DESIGN.md §2).  One MUFU.EX2 + 7 FMA,
-// branch-free.  The GELU epilogue of FFN1 runs once per output of a K = 512 GEMM, i.e. it has ~16 issue slots per element
-// before it, not the tensor pipe, bounds the kernel; libdevice erff costs ~25 instructions, a rational form 2 MUFU ops.
+// branch-free; libdevice erff costs ~25 instructions, a rational form 2 MUFU ops.
 __device__ __forceinline__ float erf_fast(float x) {
   const float a = fminf(fabsf(x), 4.0f);
   float q = 1.420474000e-04f;
@@ -130,6 +139,28 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(1.0f - e, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+
+// Exact-erf GELU (torch.nn.GELU() default, TA:emformer.py:42-43) on two values at once.  With u = |x| and
+// e = erfc(u / sqrt 2) = 2^(u' * p(u')), u' = min(u, 4 sqrt 2) (the 1/sqrt 2 is folded into the coefficients of erf_fast's fit):
+//     gelu(x) = 0.5 x (1 + sign(x)(1 - e)) = (0.5 x + 0.5 u) - 0.5 u e
+// which needs no sign handling: 9 packed FMA-pipe instructions, 2 MUFU.EX2 and 4 ALU-pipe ops per PAIR (the scalar form
+// is ~19 instructions per element).  Max abs error vs float64 5.8e-7 on [-12, 12] (checked in numpy with fp32 rounding).
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float u0 = fabsf(x0), u1 = fabsf(x1);
+  const f32x2 u = f2_pack(u0, u1);
+  const f32x2 a = f2_pack(fminf(u0, 5.65685425f), fminf(u1, 5.65685425f));
+  f32x2 q = f2_fma(f2_bcast(1.775592500e-05f), a, f2_bcast(-6.477629067e-04f));
+  q = f2_fma(q, a, f2_bcast(7.724056020e-03f));
+  q = f2_fma(q, a, f2_bcast(-5.292675272e-02f));
+  q = f2_fma(q, a, f2_bcast(-4.590827227e-01f));
+  q = f2_fma(q, a, f2_bcast(-1.151116848e+00f));
+  float t0, t1, e0, e1;
+  f2_unpack(f2_mul(q, a), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));        // exponent in [-27, 0]
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  const f32x2 s = f2_fma(f2_bcast(0.5f), f2_pack(x0, x1), f2_mul(u, f2_bcast(0.5f)));
+  f2_unpack(f2_fma(f2_mul(u, f2_bcast(-0.5f)), f2_pack(e0, e1), s), x0, x1);
+}
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 template <typename C> __device__ __forceinline__ C shfl_ctx(C v, int src);
@@ -213,13 +244,24 @@ struct EpiOperand {
   __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
   __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&)[8], const float4& b4) const {
     const int rsub = lane >> 3;
-    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    if (act == ACT_GELU) {
+      const f32x2 b01 = f2_pack(b4.x, b4.y), b23 = f2_pack(b4.z, b4.w);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
+        f2_unpack(f2_add(f2_pack(v[i][0], v[i][1]), b01), v[i][0], v[i][1]);
+        f2_unpack(f2_add(f2_pack(v[i][2], v[i][3]), b23), v[i][2], v[i][3]);
+        gelu_erf2(v[i][0], v[i][1]);
+        gelu_erf2(v[i][2], v[i][3]);
+      }
+    } else {
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = v[i][j] + bb[j];
-        v[i][j] = act == ACT_GELU ? gelu_erf(x) : (act == ACT_SILU ? silu(x) : x);
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = v[i][j] + bb[j];
+          v[i][j] = act == ACT_SILU ? silu(x) : x;
+        }
       }
     }
 #pragma unroll
@@ -227,16 +269,17 @@ struct EpiOperand {
       const int row = row0 + 4 * i + rsub;
       if (row < M) {
         bf16* o = out + (size_t)row * ld + col;
-        const bf16 h0 = __float2bfloat16_rn(v[i][0]), h1 = __float2bfloat16_rn(v[i][1]);
-        const bf16 h2 = __float2bfloat16_rn(v[i][2]), h3 = __float2bfloat16_rn(v[i][3]);
+        // packed conversions (F2FP.BF16.PACK_AB); single-value cvt goes through the XU pipe (ncu: 48 % XU in this epilogue)
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[i][0], v[i][1]), h23 = __floats2bfloat162_rn(v[i][2], v[i][3]);
         uint2 h;
-        h.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        h.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+        h.x = *reinterpret_cast<const uint32_t*>(&h01);
+        h.y = *reinterpret_cast<const uint32_t*>(&h23);
         *reinterpret_cast<uint2*>(o) = h;
         if (lo_off) {
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
           uint2 l;
-          l.x = pack_bf16x2(v[i][0] - __bfloat162float(h0), v[i][1] - __bfloat162float(h1));
-          l.y = pack_bf16x2(v[i][2] - __bfloat162float(h2), v[i][3] - __bfloat162float(h3));
+          l.x = pack_bf16x2(v[i][0] - f01.x, v[i][1] - f01.y);
+          l.y = pack_bf16x2(v[i][2] - f23.x, v[i][3] - f23.y);
           *reinterpret_cast<uint2*>(o + lo_off) = l;
         }
       }

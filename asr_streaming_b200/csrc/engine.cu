@@ -37,6 +37,16 @@ namespace {
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
+template <class F>
+void parallel_rows(int n, int max_threads, F&& work) {          // work(first, last) over [0, n) on a few host threads
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nt = std::max(1, std::min({max_threads, hw > 0 ? hw : 1, n / 64 + 1}));
+  if (nt == 1) { work(0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { work((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); });
+  for (auto& x : th) x.join();
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -117,6 +127,9 @@ struct AsrEngine {
   int* act_slots = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_reset = nullptr;   // asr_session_reset_many: pinned slot list + its H2D completion
+  int32_t* h_reset = nullptr;
+  DevBuf d_reset;
   struct Pending { int n = 0; int want_lp = 0; int active = 0; std::chrono::steady_clock::time_point t0; } pend[2];
   int cur_buf = 0;
 
@@ -574,6 +587,9 @@ void destroy_engine(AsrEngine* e) {
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
+  if (e->h_reset) cudaFreeHost(e->h_reset);
+  if (e->ev_reset) cudaEventDestroy(e->ev_reset);
+  e->d_reset.free();
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -669,7 +685,11 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     for (int i = 0; i < 2; ++i)
       ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_reset, cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok) { set_error("cudaEventCreate failed"); break; }
+    if (cudaMallocHost((void**)&e->h_reset, 4 * (size_t)cfg->max_sessions) != cudaSuccess || e->d_reset.alloc(4 * (size_t)cfg->max_sessions)) {
+      set_error("reset staging allocation failed"); break;
+    }
     use_buffer(e, 0);
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("engine init: %s", cudaGetErrorString(cudaGetLastError())); break; }
     rc = 0;
@@ -784,25 +804,21 @@ int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
   if (!e || (n > 0 && !slots)) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (n <= 0) return 0;
+  if (n > e->cfg.max_sessions) { set_error("reset_many: n = %d > max_sessions", n); return -1; }
   for (int i = 0; i < n; ++i)
     if (slots[i] < 0 || slots[i] >= e->cfg.max_sessions || !e->slot_open[slots[i]]) { set_error("slot %d is not an open session", slots[i]); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  DevBuf d;
-  if (d.alloc(4 * (size_t)n)) return -1;
-  int rc = -1;
-  do {
-    if (cudaMemcpyAsync(d.p, slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) { set_error("H2D failed"); break; }
-    if (reset_slots_launch(d.as<int>(), n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) break;
-    if (e->beam > 0) {
-      bool ok = true;
-      for (int i = 0; i < n && ok; ++i) ok = !beam_reset_launch(beam_params(e, 0), slots[i], e->cfg.max_sessions, e->stream);
-      if (!ok) break;
-    }
-    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("reset_many: %s", cudaGetErrorString(cudaGetLastError())); break; }
-    rc = 0;
-  } while (0);
-  d.free();
-  return rc;
+  // Stream-ordered and asynchronous: the resets take effect after every step already enqueued (a step in flight must not be
+  // waited for here, the scheduler pipelines ticks).  The pinned slot list is reused, so wait for the previous list's H2D only.
+  ASR_CUDA_OK(cudaEventSynchronize(e->ev_reset));
+  memcpy(e->h_reset, slots, 4 * (size_t)n);
+  ASR_CUDA_OK(cudaMemcpyAsync(e->d_reset.p, e->h_reset, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaEventRecord(e->ev_reset, e->stream));
+  if (reset_slots_launch(e->d_reset.as<int>(), n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) return -1;
+  if (e->beam > 0)
+    for (int i = 0; i < n; ++i)
+      if (beam_reset_launch(beam_params(e, 0), slots[i], e->cfg.max_sessions, e->stream)) return -1;
+  return 0;
 }
 
 /* Batch assembly in native code: copies, for i < n, chunk_length samples starting at base[rows[i] * row_stride + offsets[i]] into
@@ -810,20 +826,30 @@ int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
 int asr_gather_pcm(AsrEngine* e, int32_t n, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets, void** pinned_out) {
   if (!e || !base || (n > 0 && (!rows || !offsets))) { set_error("null argument"); return -1; }
   if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch]", n); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->pend[e->cur_buf].active) { set_error("gather_pcm: the next staging buffer still belongs to a step in flight (asr_collect it first)"); return -1; }
   int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[e->cur_buf]);
   const size_t L = e->geo.chunk_len;
-  const int hw = (int)std::thread::hardware_concurrency();
-  const int nt = std::max(1, std::min({8, hw > 0 ? hw : 1, n / 64 + 1}));
-  auto work = [&](int t) {
-    for (int i = t; i < n; i += nt) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
-  };
-  if (nt == 1) work(0);
-  else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-    for (auto& x : th) x.join();
-  }
+  parallel_rows(n, 8, [&](int a, int b) {
+    for (int i = a; i < b; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
+  });
   if (pinned_out) *pinned_out = dst;
+  return 0;
+}
+
+/* Energy gate support (stand-in for the WebRTC gate of stream.py:166-189): peaks[i] = max |x| over
+ * base[rows[i]*row_stride + offsets[i] + from .. + to).  Pure host helper, multi-threaded; no device work. */
+int asr_pcm_peaks(int32_t n, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets, int32_t from, int32_t to,
+                  int32_t* peaks) {
+  if (n < 0 || !base || (n > 0 && (!rows || !offsets || !peaks)) || from < 0 || to < from) { set_error("asr_pcm_peaks: bad argument"); return -1; }
+  parallel_rows(n, 8, [&](int a, int b) {
+    for (int i = a; i < b; ++i) {
+      const int16_t* x = base + (size_t)rows[i] * row_stride + offsets[i];
+      int lo = 0, hi = 0;
+      for (int j = from; j < to; ++j) { const int v = x[j]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+      peaks[i] = std::max(hi, -lo);
+    }
+  });
   return 0;
 }
 

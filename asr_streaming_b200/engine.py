@@ -117,6 +117,16 @@ class Engine:
         buf = (C.c_char * (n * L * 2)).from_address(out.value)
         return np.frombuffer(buf, dtype=np.int16, count=n * L).reshape(n, L)
 
+    def pcm_peaks(self, audio: np.ndarray, rows: np.ndarray, offsets: np.ndarray, start: int, stop: int) -> np.ndarray:
+        """max |x| over audio[rows[i], offsets[i] + start : offsets[i] + stop] for every i (host helper, multi-threaded)."""
+        assert audio.dtype == np.int16 and audio.flags.c_contiguous and audio.ndim == 2
+        rows = np.ascontiguousarray(rows, np.int32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        out = np.empty(rows.size, np.int32)
+        _lib.check(self.lib, self.lib.asr_pcm_peaks(int(rows.size), audio.ctypes.data, audio.shape[1], rows.ctypes.data, offsets.ctypes.data,
+                                                    int(start), int(stop), out.ctypes.data), "asr_pcm_peaks")
+        return out
+
     def close_session(self, slot: int) -> None:
         _lib.check(self.lib, self.lib.asr_session_close(self._h, slot), "asr_session_close")
 

@@ -87,7 +87,8 @@ class StreamSession:
 @dataclass
 class TickResult:
     """Outcome of one tick, struct-of-arrays (n = streams run through the model this tick)."""
-    sessions: List[StreamSession] = field(default_factory=list)     # the n sessions, in batch order
+    rows: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))           # [n] scheduler rows, in batch order
+    _sched: Optional["SessionScheduler"] = None
     n_new: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))          # [n]
     new_tokens: np.ndarray = field(default_factory=lambda: np.zeros((0, 0), np.int32))  # [n, S], valid [:n_new]
     logprobs: Optional[np.ndarray] = None                            # [n, S, V] when requested
@@ -97,13 +98,28 @@ class TickResult:
     final_rule: List[Optional[str]] = field(default_factory=list)    # rule name per session (None if not final)
     final_tokens: Dict[int, List[int]] = field(default_factory=dict)  # session id -> tokens of the finished segment
 
+    @property
+    def sessions(self) -> List[StreamSession]:
+        """The n sessions run through the model this tick, in batch order."""
+        return [self._sched._by_row[int(r)] for r in self.rows]
+
     def __iter__(self):
         """(session, new token ids, logprobs | None) — the shape of the first-generation API."""
         for i, s in enumerate(self.sessions):
             yield s, [int(t) for t in self.new_tokens[i, :self.n_new[i]]], (self.logprobs[i] if self.logprobs is not None else None)
 
     def __len__(self):
-        return len(self.sessions)
+        return int(self.rows.size)
+
+
+@dataclass
+class PendingTick:
+    """A submitted, not yet collected tick."""
+    res: TickResult
+    rows: np.ndarray
+    ticket: object
+    out: object
+    want_logprobs: bool
 
 
 def energy_gate(threshold: int = 328):
@@ -112,6 +128,16 @@ def energy_gate(threshold: int = 328):
     def gate(chunks: np.ndarray, buffer_length: int) -> np.ndarray:
         return np.abs(chunks[:, buffer_length:]).max(axis=1) >= threshold
     gate.vectorised = True
+    return gate
+
+
+def native_energy_gate(threshold: int = 328):
+    """Same decision as ``energy_gate`` computed by the library's multi-threaded host helper (asr_pcm_peaks) straight from the
+    scheduler's audio rings — no per-session Python work, no chunk copies."""
+    def gate(sched: "SessionScheduler", rows: np.ndarray) -> np.ndarray:
+        cfg = sched.cfg
+        return sched.engine.pcm_peaks(sched.audio, rows, sched.rd[rows], cfg.buffer_length, cfg.chunk_length) >= threshold
+    gate.native = True
     return gate
 
 
@@ -129,6 +155,7 @@ class SessionScheduler:
         self.rd = np.zeros(n, np.int64)
         self.wr = np.zeros(n, np.int64)
         self.active = np.zeros(n, bool)
+        self.inflight = np.zeros(n, bool)                  # a chunk of this session is in a submitted, uncollected tick
         self.slot = np.full(n, -1, np.int32)
         self.tok = np.zeros((n, MAX_TOKENS), np.int32)
         self.ntok = np.zeros(n, np.int32)
@@ -171,6 +198,8 @@ class SessionScheduler:
         return s
 
     def close(self, s: StreamSession) -> None:
+        if self.inflight[s.row]:
+            raise RuntimeError("close: the session has a chunk in flight; collect its tick first")
         self.engine.close_session(int(self.slot[s.row]))
         self.active[s.row] = False
         self.slot[s.row] = -1
@@ -187,6 +216,8 @@ class SessionScheduler:
 
     def reset(self, s: StreamSession) -> None:
         """Endpoint: emission := [], state := init (streaming_server.py:514-515, :530; stream.py:152-157)."""
+        if self.inflight[s.row]:
+            raise RuntimeError("reset: the session has a chunk in flight; collect its tick first")
         self.engine.reset_session(int(self.slot[s.row]))
         self._clear_segment(np.array([s.row]))
         self.segment[s.row] += 1
@@ -212,7 +243,7 @@ class SessionScheduler:
 
     # ------------------------------------------------------------------ the tick
     def ready_rows(self) -> np.ndarray:
-        rows = np.nonzero(self.active & (self.wr - self.rd >= self.cfg.chunk_length))[0]
+        rows = np.nonzero(self.active & ~self.inflight & (self.wr - self.rd >= self.cfg.chunk_length))[0]
         if rows.size > self.cfg.max_batch:                            # backlog: longest-waiting first, nobody starves
             order = np.argsort(self.last_served[rows], kind="stable")
             rows = rows[order[:self.cfg.max_batch]]
@@ -241,20 +272,30 @@ class SessionScheduler:
         (streaming_server.py:374-379); it is consulted only for streams without a token in the current segment, and
         gated-out chunks are skipped.  Endpoint rules, when configured, are evaluated after the step for every served
         stream; fired endpoints reset encoder state and are reported in ``TickResult.final*``."""
+        return self.collect_tick(self.submit_tick(want_logprobs, gate))
+
+    # Pipelined form: ``p1 = submit_tick(); p2 = submit_tick(); r1 = collect_tick(p1); ...`` keeps up to two ticks in flight, so
+    # batch assembly + H2D of tick k+1 overlap the kernels of tick k.  A session with a chunk in flight is not eligible for
+    # the next tick (its endpoint decision needs the results first), which preserves the reference's per-stream order
+    # chunk -> update_stream -> endpoint_detected -> next chunk exactly.
+    def submit_tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None) -> "PendingTick":
         self._tick += 1
         cfg = self.cfg
         rows = self.ready_rows()
-        res = TickResult()
+        res = TickResult(_sched=self)
+        pend = PendingTick(res, rows[:0], None, None, want_logprobs)
         if rows.size == 0:
-            return res
+            return pend
         # ---- VAD gate
         if gate is not None:
             need = ~self.contain_token[rows]
             keep = np.ones(rows.size, bool)
             if need.any():
-                if getattr(gate, "vectorised", False):
-                    idx = rows[need]
-                    chunks = np.stack([self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length] for r in idx]) if idx.size else np.zeros((0, cfg.chunk_length), np.int16)
+                idx = rows[need]
+                if getattr(gate, "native", False):
+                    keep[need] = gate(self, idx)
+                elif getattr(gate, "vectorised", False):
+                    chunks = np.stack([self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length] for r in idx])
                     keep[need] = gate(chunks, cfg.buffer_length)
                 else:
                     for j in np.nonzero(need)[0]:
@@ -264,10 +305,10 @@ class SessionScheduler:
             if skipped.size:
                 res.skipped = [self._by_row[int(r)] for r in skipped]
                 self._skip_rows(skipped)
+                self._endpoints(skipped, res, rows[:0])
             rows = rows[keep]
             if rows.size == 0:
-                self._endpoints(np.array([r.row for r in res.skipped]), res, np.zeros(0, np.int64))
-                return res
+                return pend
         n = int(rows.size)
         # ---- batch assembly straight into the pinned staging buffer of the next step
         if self._fallback_pack is None:
@@ -276,9 +317,24 @@ class SessionScheduler:
             pcm = self._fallback_pack[:n]
             for i, r in enumerate(rows):
                 pcm[i] = self.audio[r, self.rd[r]:self.rd[r] + cfg.chunk_length]
-        out = self.engine.step(self.slot[rows], pcm, want_logprobs)
+        if hasattr(self.engine, "submit"):
+            pend.ticket = self.engine.submit(self.slot[rows], pcm, want_logprobs)
+        else:
+            pend.out = self.engine.step(self.slot[rows], pcm, want_logprobs)
+        pend.rows = rows
+        self.inflight[rows] = True
+        self._advance(rows)
+        return pend
+
+    def collect_tick(self, pend: "PendingTick") -> TickResult:
+        res, rows = pend.res, pend.rows
+        n = int(rows.size)
+        if n == 0:
+            return res
+        out = pend.out if pend.out is not None else self.engine.collect(pend.ticket)
+        self.inflight[rows] = False
         # ---- vectorised bookkeeping (update_stream, stream.py:110-125)
-        S = cfg.seg_rows
+        S = self.cfg.seg_rows
         if out.n_new is not None:
             n_new = np.asarray(out.n_new, np.int32)
             new_tok = np.where(np.arange(S)[None, :] < n_new[:, None], out.new_tokens_padded, 0).astype(np.int32)
@@ -287,7 +343,7 @@ class SessionScheduler:
             new_tok = np.zeros((n, S), np.int32)
             for i, t in enumerate(out.new_tokens):
                 new_tok[i, :len(t)] = t
-        for j in range(int(n_new.max()) if n else 0):
+        for j in range(int(n_new.max())):
             m = n_new > j
             dst = np.minimum(self.ntok[rows[m]] + j, MAX_TOKENS - 1)
             self.tok[rows[m], dst] = new_tok[m, j]
@@ -300,14 +356,27 @@ class SessionScheduler:
         lb = np.where(has, (blank.astype(np.float32) * np.float32(FRAMERATE)).astype(np.float64), FRAMERATE * blank)
         self.trailing[rows] = np.where(has, lb, self.trailing[rows] + self._chunk_s)
         self.contain_token[rows] |= has
-        self._advance(rows)
-        res.sessions = [self._by_row[int(r)] for r in rows]
+        res.rows = rows
         res.n_new, res.new_tokens, res.logprobs, res.beam_tokens = n_new, new_tok, out.logprobs, out.beam_tokens
         res.final = np.zeros(n, bool)
         res.final_rule = [None] * n
-        extra = np.array([s.row for s in res.skipped], np.int64)
-        self._endpoints(np.concatenate([rows, extra]) if extra.size else rows, res, rows)
+        self._endpoints(rows, res, rows)
         return res
+
+    def reset_rows(self, rows: np.ndarray) -> None:
+        """Endpoint decided by the caller (e.g. a final-pass decoder or the client's EOS) for many sessions at once."""
+        rows = np.asarray(rows, np.int64)
+        if rows.size == 0:
+            return
+        if self.inflight[rows].any():
+            raise RuntimeError("reset_rows: a session with a chunk in flight cannot be reset before its tick is collected")
+        if hasattr(self.engine, "reset_sessions"):
+            self.engine.reset_sessions(self.slot[rows])
+        else:
+            for r in rows:
+                self.engine.reset_session(int(self.slot[r]))
+        self._clear_segment(rows)
+        self.segment[rows] += 1
 
     # ------------------------------------------------------------------ endpointing (stream.py:127-163, online_endpoint.py)
     def _endpoints(self, rows: np.ndarray, res: TickResult, run_rows: np.ndarray) -> None:
@@ -328,13 +397,7 @@ class SessionScheduler:
             if pos.size:
                 res.final[pos[0]] = True
                 res.final_rule[pos[0]] = self.endpoint_rules.names[w]
-        if hasattr(self.engine, "reset_sessions"):
-            self.engine.reset_sessions(self.slot[frows])
-        else:
-            for r in frows:
-                self.engine.reset_session(int(self.slot[r]))
-        self._clear_segment(frows)
-        self.segment[frows] += 1
+        self.reset_rows(frows)
 
 
 class GpuRouter:

@@ -106,12 +106,17 @@ ASR_API int asr_engine_destroy(AsrEngine* e);
 ASR_API int asr_session_open(AsrEngine* e, int32_t* slot_out);
 ASR_API int asr_session_reset(AsrEngine* e, int32_t slot);           /* endpoint: state := init, emission := []  (:514-515, :530) */
 ASR_API int asr_session_close(AsrEngine* e, int32_t slot);
-ASR_API int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots);   /* endpoints of one tick in one launch */
+/* Endpoints of one tick in one launch.  Asynchronous and stream-ordered: takes effect after every step already submitted. */
+ASR_API int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots);
 
 /* Native batch assembly for the scheduler: for i < n copy chunk_length int16 samples from base[rows[i]*row_stride + offsets[i]]
  * into row i of the pinned staging buffer of the NEXT step (multi-threaded); *pinned_out = that buffer (pass it as `pcm`). */
 ASR_API int asr_gather_pcm(AsrEngine* e, int32_t n, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
                            void** pinned_out);
+/* Host helper for the scheduler's energy gate (stand-in for the WebRTC VAD of stream.py:166-189, whose library is absent):
+ * peaks[i] = max |x| over samples [from, to) of the chunk at base[rows[i]*row_stride + offsets[i]].  Multi-threaded, no GPU work. */
+ASR_API int asr_pcm_peaks(int32_t n, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
+                          int32_t from, int32_t to, int32_t* peaks);
 
 /* Replaces LightningASR.stream (recognition.py:191-204) + greedy_search (recognition.py:33-57) for n sessions with
  * arbitrary, different progress.  pcm: packed [n, chunk_length] int16 (as received from the websocket,

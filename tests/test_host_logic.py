@@ -354,6 +354,91 @@ def test_scheduler_vectorised_gate_and_backlog_compaction():
             b.accept_waveform(quiet)
 
 
+class PipelinedTokenEngine(TokenEngine):
+    """TokenEngine + submit/collect (results computed at submit, delivered at collect), at most two tickets in flight."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.tickets, self.busy = {}, set()
+
+    def submit(self, slots, pcm, want_logprobs=False):
+        slots = [int(x) for x in slots]
+        assert len(self.tickets) < 2, "more than two steps in flight"
+        assert not (self.busy & set(slots)), "a session was submitted again before its previous chunk was collected"
+        self.busy |= set(slots)
+        t = len(self.calls)
+        self.tickets[t] = (slots, self.step(slots, pcm, want_logprobs))
+        return t
+
+    def collect(self, t):
+        slots, out = self.tickets.pop(t)
+        self.busy -= set(slots)
+        return out
+
+
+def test_pipelined_ticks_equal_synchronous_ticks():
+    """Two ticks in flight with a backlog larger than max_batch: per session the decoded tokens, endpoints and counters must be
+    exactly those of synchronous ticking, and no session may ride two in-flight steps."""
+    from asr_streaming_b200.endpoint import EndpointRules
+    cfg = A.ModelConfig(max_batch=8, max_sessions=32)
+    rng = np.random.default_rng(4)
+    n_sess, n_chunks = 20, 70
+    lasts = np.where(rng.random((n_sess, n_chunks)) < 0.3, rng.integers(1, 3000, (n_sess, n_chunks)), -rng.integers(0, 3000, (n_sess, n_chunks)))
+    audio = np.zeros((n_sess, n_chunks * cfg.segment_length), np.int16)
+    audio[:, cfg.segment_length - 1::cfg.segment_length] = lasts
+
+    def run(pipelined):
+        eng = PipelinedTokenEngine(cfg)
+        sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules(), backlog_chunks=n_chunks + 1)
+        ss = [sch.open() for _ in range(n_sess)]
+        for i, s in enumerate(ss):
+            s.accept_waveform(audio[i])
+        log = {s.id: [] for s in ss}
+
+        def note(res):
+            for j, s in enumerate(res.sessions):
+                log[s.id].append((tuple(int(t) for t in res.new_tokens[j, :res.n_new[j]]), bool(res.final[j]), res.final_rule[j]))
+        prev = None
+        for _ in range(10000):
+            if pipelined:
+                p = sch.submit_tick()
+                if prev is not None:
+                    note(sch.collect_tick(prev))
+                prev = p
+                if not len(p.rows) and not sch.ready_rows().size:
+                    break
+            else:
+                r = sch.tick()
+                note(r)
+                if not len(r):
+                    break
+        if prev is not None:
+            note(sch.collect_tick(prev))
+        return log, [(s.chunk_processed, s.segment, s.tokens) for s in ss]
+
+    log_sync, end_sync = run(False)
+    log_pipe, end_pipe = run(True)
+    assert log_sync == log_pipe and end_sync == end_pipe
+    assert all(len(v) == n_chunks for v in log_sync.values())
+    assert sum(f for v in log_sync.values() for _, f, _ in v) > 10
+
+
+def test_native_pcm_peaks_matches_numpy():
+    import ctypes as C
+    lib = _lib.load_library()
+    rng = np.random.default_rng(9)
+    audio = rng.integers(-32768, 32768, size=(300, 30000)).astype(np.int16)
+    audio[7] = 0
+    audio[8, 5000:] = -32768
+    rows = rng.permutation(300)[:257].astype(np.int32)
+    offs = rng.integers(0, 30000 - 13440, size=rows.size).astype(np.int64)
+    out = np.empty(rows.size, np.int32)
+    assert lib.asr_pcm_peaks(int(rows.size), audio.ctypes.data, audio.shape[1], rows.ctypes.data, offs.ctypes.data, 3200, 13440, out.ctypes.data) == 0
+    exp = np.array([np.abs(audio[r, o + 3200:o + 13440].astype(np.int32)).max() for r, o in zip(rows, offs)])
+    assert np.array_equal(out, exp)
+    assert lib.asr_pcm_peaks(0, audio.ctypes.data, audio.shape[1], None, None, 0, 0, None) == 0
+
+
 def test_partition_streams_covers_everything_once():
     from asr_streaming_b200.scheduler import partition_streams
     for n, w in ((32768, 8), (10, 3), (7, 8), (4096, 2)):

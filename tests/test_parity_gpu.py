@@ -315,3 +315,71 @@ def test_pipelined_submit_collect_equals_sync(engines):
     e.collect(t1); e.collect(t2)
     for s in a + b:
         e.close_session(s)
+
+
+# ------------------------------------------------------------------------------------------------ scheduler on the real engine
+def test_scheduler_ticks_match_reference_texts(engines, golden, meta):
+    """Websocket-style delivery (ragged message sizes, streams joining at different times) through SessionScheduler.tick:
+    native pinned gather (asr_gather_pcm) + one asr_step per tick.  Every stream's text / trailing-blank after each of
+    its chunks must equal the reference's batch-1 greedy_search on the accumulated emission (fixtures)."""
+    from asr_streaming_b200 import SessionScheduler, ids_to_text
+    e = engines(engines.EXACT)
+    names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale", "edge_dc"]
+    cases = [golden(n) for n in names]
+    sch = SessionScheduler(e, capacity=16, backlog_chunks=3)
+    rng = np.random.default_rng(5)
+    sess = [sch.open() for _ in names]
+    pos = [0] * len(names)
+    start = [0, 3, 1, 5, 2]
+    done_chunks = [0] * len(names)
+    for rnd in range(400):
+        for i, c in enumerate(cases):
+            if rnd < start[i] or pos[i] >= c["pcm"].size:
+                continue
+            room = sch.CAP - sess[i].length_of_segment
+            n = int(min(rng.integers(101, 9000), c["pcm"].size - pos[i], room))
+            if n > 100:
+                sess[i].accept_waveform(c["pcm"][pos[i]:pos[i] + n].astype(np.int16))
+                pos[i] += n
+            elif c["pcm"].size - pos[i] <= 100:
+                pos[i] = c["pcm"].size                                     # tail shorter than a message the server would keep
+        res = sch.tick()
+        for s in res.sessions:
+            i = sess.index(s)
+            mc = meta["cases"][names[i]]
+            j = done_chunks[i]
+            assert ids_to_text(s.tokens, meta["vocab"]) == mc["texts"][j], (names[i], j)
+            assert abs(s.trailing_blank_duration - (cases[i]["last_blank"][j] if s.tokens else 0.64 * (j + 1))) < 1e-6
+            done_chunks[i] += 1
+        if all(p >= c["pcm"].size for p, c in zip(pos, cases)) and not sch.ready_rows().size:
+            break
+    for i, n in enumerate(names):
+        assert done_chunks[i] == meta["cases"][n]["n_chunks"], n
+    for s in sess:
+        sch.close(s)
+
+
+def test_reset_many_equals_fresh_sessions(engines):
+    """asr_session_reset_many on a subset: the reset streams continue exactly like freshly opened sessions, the others
+    are untouched."""
+    e = engines(engines.FAST)
+    rng = np.random.default_rng(8)
+    n = 6
+    pcm = rng.integers(-4000, 4000, size=(5, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    a = [e.open_session() for _ in range(n)]
+    for t in range(3):
+        e.step(a, pcm[t])
+    e.reset_sessions([a[1], a[4]])
+    fresh = [e.open_session() for _ in range(2)]
+    keep = [e.open_session() for _ in range(n)]
+    for t in range(3):
+        e.step(keep, pcm[t])
+    for t in range(3, 5):
+        ra = e.step(a, pcm[t], want_logprobs=True)
+        rf = e.step(fresh, pcm[t][[1, 4]], want_logprobs=True)
+        rk = e.step(keep, pcm[t], want_logprobs=True)
+        assert np.array_equal(ra.logprobs[[1, 4]], rf.logprobs)
+        assert np.array_equal(ra.logprobs[[0, 2, 3, 5]], rk.logprobs[[0, 2, 3, 5]])
+        assert np.array_equal(ra.blank_frames[[1, 4]], rf.blank_frames)
+    for s in a + fresh + keep:
+        e.close_session(s)

@@ -201,6 +201,17 @@ __global__ void beam_reset_kernel(BeamParams P, int slot) {
   if (i == 0) { P.n_beam[slot] = 1; P.cur[slot] = 0; }
 }
 
+__global__ void beam_reset_many_kernel(BeamParams P, const int* __restrict__ slots, int n) {     // one warp per listed slot
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, i = threadIdx.x & 31;
+  if (w >= n) return;
+  const int slot = slots[w];
+  if (i < BEAM_MAX) {
+    const size_t o = (size_t)slot * BEAM_MAX + i;
+    P.len[o] = 0; P.last[o] = -1; P.pb[o] = i == 0 ? 0.f : -INFINITY; P.pnb[o] = -INFINITY; P.hash[o] = 0x1234567ull;
+  }
+  if (i == 0) { P.n_beam[slot] = 1; P.cur[slot] = 0; }
+}
+
 __global__ void beam_reset_all_kernel(BeamParams P, int n_slots) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
     for (int i = 0; i < BEAM_MAX; ++i) {
@@ -220,6 +231,13 @@ int beam_launch(const BeamParams& P, cudaStream_t st) {
     return -1;
   }
   ASR_CUDA_OK(launch_pdl(beam_kernel, dim3((P.n + BW - 1) / BW), dim3(BW * 32), 0, st, P));
+  return 0;
+}
+
+int beam_reset_many_launch(const BeamParams& P, const int* d_slots, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  beam_reset_many_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(P, d_slots, n);
+  ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

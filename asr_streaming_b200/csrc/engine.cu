@@ -127,9 +127,12 @@ struct AsrEngine {
   int* act_slots = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  cudaEvent_t ev_reset = nullptr;   // asr_session_reset_many: pinned slot list + its H2D completion
+  // asr_session_reset_many: ring of pinned slot lists (+ the event of each list's H2D) so that back-to-back calls never wait
+  static constexpr int kResetRing = 4;
+  cudaEvent_t ev_reset[kResetRing] = {nullptr, nullptr, nullptr, nullptr};
   int32_t* h_reset = nullptr;
   DevBuf d_reset;
+  int reset_pos = 0;
   struct Pending { int n = 0; int want_lp = 0; int active = 0; std::chrono::steady_clock::time_point t0; } pend[2];
   int cur_buf = 0;
 
@@ -588,7 +591,7 @@ void destroy_engine(AsrEngine* e) {
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
   if (e->h_reset) cudaFreeHost(e->h_reset);
-  if (e->ev_reset) cudaEventDestroy(e->ev_reset);
+  for (auto ev : e->ev_reset) if (ev) cudaEventDestroy(ev);
   e->d_reset.free();
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -685,9 +688,10 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     for (int i = 0; i < 2; ++i)
       ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
-    ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_reset, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < AsrEngine::kResetRing; ++i) ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_reset[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok) { set_error("cudaEventCreate failed"); break; }
-    if (cudaMallocHost((void**)&e->h_reset, 4 * (size_t)cfg->max_sessions) != cudaSuccess || e->d_reset.alloc(4 * (size_t)cfg->max_sessions)) {
+    if (cudaMallocHost((void**)&e->h_reset, 4 * (size_t)cfg->max_sessions * AsrEngine::kResetRing) != cudaSuccess ||
+        e->d_reset.alloc(4 * (size_t)cfg->max_sessions * AsrEngine::kResetRing)) {
       set_error("reset staging allocation failed"); break;
     }
     use_buffer(e, 0);
@@ -810,14 +814,16 @@ int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
   ASR_CUDA_OK(cudaSetDevice(e->device));
   // Stream-ordered and asynchronous: the resets take effect after every step already enqueued (a step in flight must not be
   // waited for here, the scheduler pipelines ticks).  The pinned slot list is reused, so wait for the previous list's H2D only.
-  ASR_CUDA_OK(cudaEventSynchronize(e->ev_reset));
-  memcpy(e->h_reset, slots, 4 * (size_t)n);
-  ASR_CUDA_OK(cudaMemcpyAsync(e->d_reset.p, e->h_reset, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaEventRecord(e->ev_reset, e->stream));
-  if (reset_slots_launch(e->d_reset.as<int>(), n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) return -1;
-  if (e->beam > 0)
-    for (int i = 0; i < n; ++i)
-      if (beam_reset_launch(beam_params(e, 0), slots[i], e->cfg.max_sessions, e->stream)) return -1;
+  const int r = e->reset_pos;
+  e->reset_pos = (r + 1) % AsrEngine::kResetRing;
+  int32_t* hs = e->h_reset + (size_t)r * e->cfg.max_sessions;
+  int* ds = e->d_reset.as<int>() + (size_t)r * e->cfg.max_sessions;
+  ASR_CUDA_OK(cudaEventSynchronize(e->ev_reset[r]));
+  memcpy(hs, slots, 4 * (size_t)n);
+  ASR_CUDA_OK(cudaMemcpyAsync(ds, hs, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaEventRecord(e->ev_reset[r], e->stream));
+  if (reset_slots_launch(ds, n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) return -1;
+  if (e->beam > 0 && beam_reset_many_launch(beam_params(e, 0), ds, n, e->stream)) return -1;
   return 0;
 }
 

@@ -93,6 +93,7 @@ struct BeamParams {
   float* out_score;        // [n]
 };
 int beam_launch(const BeamParams& P, cudaStream_t st);
+int beam_reset_many_launch(const BeamParams& P, const int* d_slots, int n, cudaStream_t st);
 int beam_reset_launch(const BeamParams& P, int slot /* -1: all */, int n_slots_all, cudaStream_t st);
 
 // fp32 [n] -> bf16 hi (+ lo) weight conversion at engine creation

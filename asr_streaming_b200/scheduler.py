@@ -241,12 +241,26 @@ class SessionScheduler:
         self.audio[r, self.wr[r]:self.wr[r] + n] = pcm
         self.wr[r] += n
 
+    def accept_block(self, rows: np.ndarray, block: np.ndarray) -> None:
+        """Bulk ingest: ``block[i]`` (int16, equal lengths) is appended to session row ``rows[i]`` (no compaction: must fit)."""
+        rows = np.asarray(rows, np.int64)
+        block = np.asarray(block)
+        assert block.dtype == np.int16 and block.ndim == 2 and block.shape[0] == rows.size
+        n = block.shape[1]
+        if (self.wr[rows] + n > self.CAP).any():
+            raise BufferError(f"accept_block: {n} samples do not fit behind the write pointer of every session (CAP {self.CAP})")
+        for w in np.unique(self.wr[rows]):
+            m = self.wr[rows] == w
+            self.audio[rows[m], w:w + n] = block[m]
+        self.wr[rows] += n
+
     # ------------------------------------------------------------------ the tick
-    def ready_rows(self) -> np.ndarray:
+    def ready_rows(self, max_rows: Optional[int] = None) -> np.ndarray:
+        cap = self.cfg.max_batch if max_rows is None else min(int(max_rows), self.cfg.max_batch)
         rows = np.nonzero(self.active & ~self.inflight & (self.wr - self.rd >= self.cfg.chunk_length))[0]
-        if rows.size > self.cfg.max_batch:                            # backlog: longest-waiting first, nobody starves
+        if rows.size > cap:                                           # backlog: longest-waiting first, nobody starves
             order = np.argsort(self.last_served[rows], kind="stable")
-            rows = rows[order[:self.cfg.max_batch]]
+            rows = rows[order[:cap]]
         return rows
 
     def ready_sessions(self) -> List[StreamSession]:
@@ -267,21 +281,21 @@ class SessionScheduler:
         self.chunk_processed_total[rows] += 1
         self._advance(rows)
 
-    def tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None) -> TickResult:
+    def tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None, max_rows: Optional[int] = None) -> TickResult:
         """One step over the ready streams.  ``gate``: ``energy_gate()`` (vectorised) or ``gate(session, chunk) -> bool``
         (streaming_server.py:374-379); it is consulted only for streams without a token in the current segment, and
         gated-out chunks are skipped.  Endpoint rules, when configured, are evaluated after the step for every served
         stream; fired endpoints reset encoder state and are reported in ``TickResult.final*``."""
-        return self.collect_tick(self.submit_tick(want_logprobs, gate))
+        return self.collect_tick(self.submit_tick(want_logprobs, gate, max_rows))
 
     # Pipelined form: ``p1 = submit_tick(); p2 = submit_tick(); r1 = collect_tick(p1); ...`` keeps up to two ticks in flight, so
     # batch assembly + H2D of tick k+1 overlap the kernels of tick k.  A session with a chunk in flight is not eligible for
     # the next tick (its endpoint decision needs the results first), which preserves the reference's per-stream order
     # chunk -> update_stream -> endpoint_detected -> next chunk exactly.
-    def submit_tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None) -> "PendingTick":
+    def submit_tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None, max_rows: Optional[int] = None) -> "PendingTick":
         self._tick += 1
         cfg = self.cfg
-        rows = self.ready_rows()
+        rows = self.ready_rows(max_rows)
         res = TickResult(_sched=self)
         pend = PendingTick(res, rows[:0], None, None, want_logprobs)
         if rows.size == 0:

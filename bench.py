@@ -33,6 +33,9 @@ WORKLOADS = {
     "streams4096": (4096, "configs[3] batch size: 4096 concurrent streams, chunk_size=16, greedy CTC"),
     "streams10240": (10240, "north-star target: 10,240 concurrent streams, chunk_size=16, greedy CTC"),
     "fbank1024": (1024, "configs[1]: fbank-only, 1024 streams x 640 ms, 80-bin Kaldi fbank"),
+    "ragged4096": (4096, "configs[3]: 4096 concurrent streams ragged-batched by the session scheduler (mixed progress: fresh / 1-chunk / steady-state "
+                         "left context), chunk_size=16, CTC prefix beam search (beam 10, 8 candidates/frame) + greedy, energy-gate VAD standing in for "
+                         "Silero (model absent) with ~20 % of chunks gated out, endpoints at ~1 %/s per stream + online_endpoint rules"),
     "lowlat4096": (4096, "configs[4] per-GPU share: 4096 concurrent streams per GPU, chunk_size=8 low-latency mode (320 ms chunks), greedy CTC"),
 }
 FLOP_PER_STREAM_CHUNK = 2_583_363_584          # SURVEY.md §8a (L_valid = 32)
@@ -161,7 +164,90 @@ def run_reference_arm(args):
     return 0
 
 
-# ------------------------------------------------------------------------------------------ our arm
+# ------------------------------------------------------------------------------------------ configs[3]: scheduler-driven workload
+class RaggedWorkload:
+    """4096 sessions with a scripted speech / silence pattern (2-state Markov chain per session, ~20 % of chunks silent, an
+    endpoint at every speech -> silence transition: ~1 % of the streams per second), driven through SessionScheduler with two
+    ticks in flight.  Audio for every pass is pre-loaded into the scheduler's per-session rings (the websocket receive path is
+    not part of the measured hot path); everything from 'which sessions are ready' to 'token ids on the host' is timed."""
+
+    P_END, P_START = 0.008, 0.032
+
+    def __init__(self, eng, cfg, streams, passes, seed, pool):
+        from asr_streaming_b200 import SessionScheduler
+        from asr_streaming_b200.endpoint import EndpointRules
+        from asr_streaming_b200.scheduler import native_energy_gate
+        self.eng, self.cfg, self.n, self.passes = eng, cfg, streams, passes
+        self.sch = SessionScheduler(eng, capacity=streams, backlog_chunks=passes, endpoint_rules=EndpointRules())
+        self.gate = native_energy_gate()
+        self.sess = [self.sch.open() for _ in range(streams)]
+        rng = np.random.Generator(np.random.PCG64(seed))
+        speech = np.empty((streams, passes), bool)
+        state = rng.random(streams) >= 0.2                          # stationary start: 20 % of the sessions in silence
+        for k in range(passes):
+            speech[:, k] = state
+            flip = rng.random(streams)
+            state = np.where(state, flip >= self.P_END, flip < self.P_START)
+        self.speech = speech
+        seg = cfg.segment_length
+        block = np.empty((streams, passes * seg), np.int16)
+        shift = rng.integers(0, pool.shape[1] - passes * seg, size=streams)
+        for i in range(streams):
+            block[i] = pool[i % pool.shape[0], shift[i]:shift[i] + passes * seg]
+        block.reshape(streams, passes, seg)[~speech] = 0
+        self.sch.accept_block(np.arange(streams), block)
+        self.sch.wr[:] = cfg.buffer_length                          # nothing has "arrived" yet: feed_pass() releases 640 ms at a time
+        self.fed = 0
+        self.run_chunks = self.skipped_chunks = self.endpoints = 0
+
+    def feed_pass(self):
+        """The next 640 ms of every stream arrive (the samples are already in the rings; only the write pointers move)."""
+        assert self.fed < self.passes, "RaggedWorkload: out of pre-loaded audio"
+        self.sch.wr += self.cfg.segment_length
+        self.fed += 1
+
+    def _after(self, res):
+        """Scripted endpoints: a session whose just-decoded chunk was the last speech chunk of an utterance is reset."""
+        self.skipped_chunks += len(res.skipped)
+        rows = res.rows
+        if rows.size == 0:
+            return
+        k = self.sch.chunk_processed_total[rows] - 1               # index of the chunk just decoded
+        nxt = np.minimum(k + 1, self.passes - 1)
+        ended = self.speech[rows, k] & ~self.speech[rows, nxt] & ~res.final
+        self.sch.reset_rows(rows[ended])
+        self.run_chunks += int(rows.size)
+        self.endpoints += int(ended.sum()) + int(res.final.sum())
+
+    def run_pipelined(self, n_passes, max_rows):
+        """n_passes x 640 ms for every session; ticks of <= max_rows sessions, two in flight, never draining between passes."""
+        prev = None
+        for _ in range(n_passes):
+            self.feed_pass()
+            while True:
+                p = self.sch.submit_tick(gate=self.gate, max_rows=max_rows)
+                if p.rows.size == 0 and not p.res.skipped:
+                    break                                           # nothing left to launch in this pass; `prev` stays in flight
+                if prev is not None:
+                    self._after(self.sch.collect_tick(prev))
+                    prev = None
+                if p.rows.size:
+                    prev = p
+                else:
+                    self._after(p.res)                              # VAD-skipped only: nothing to collect
+        if prev is not None:
+            self._after(self.sch.collect_tick(prev))
+
+    def run_sync(self):
+        """One pass, one synchronous tick over every ready session: the per-chunk latency a session sees."""
+        self.feed_pass()
+        t0 = time.perf_counter()
+        res = self.sch.tick(gate=self.gate)
+        dt = time.perf_counter() - t0
+        self._after(res)
+        return dt, len(res)
+
+
 def run_ours(args):
     import torch
     from asr_streaming_b200 import Engine, ModelConfig, PRECISION_EXACT, PRECISION_FAST, pack_weights, random_weights
@@ -183,6 +269,7 @@ def run_ours(args):
     pk = peaks()
     fbank_only = args.workload.startswith("fbank")
 
+    ragged = args.workload.startswith("ragged")
     low_latency = args.workload.startswith("lowlat")
     cfg = ModelConfig(precision=precision, max_batch=streams, max_sessions=streams, segment_size=32 if low_latency else 64)
     blob = pack_weights(random_weights(WEIGHT_SEED, cfg), cfg)
@@ -213,6 +300,28 @@ def run_ours(args):
         audio_per_step = streams * 0.64
         h2d, d2h = pcm.nbytes, streams * 64 * 80 * 4
         alg_bytes = pcm.nbytes + streams * 64 * 80 * 4
+    elif ragged:
+        # configs[3]: prefix beam 10 on every step, sessions at mixed progress, a trickle of endpoints (1 %/s per stream)
+        eng.set_beam(10, 8)
+        lat_passes = min(args.steps, 8)
+        passes = 2 + lat_passes + 2 + args.steps + 1
+        pool = synth_pcm(32, cfg.buffer_length + passes * cfg.segment_length + 4096, first_id=rank * 32)
+        wl = RaggedWorkload(eng, cfg, streams, passes, seed=99 + rank, pool=pool)
+        slots = wl.sch.slot.copy()
+        pcm = np.stack([pool[i % 32, :cfg.chunk_length] for i in range(streams)])
+        eng.stage(slots, pcm)
+        rs = np.random.Generator(np.random.PCG64(7 + rank))
+        n_reset = max(1, int(round(streams * 0.01 * cfg.segment_length / cfg.sample_rate)))
+
+        def run():
+            eng.run_staged(streams)
+            eng.reset_sessions(slots[rs.choice(streams, n_reset, replace=False)])
+        eng.run_staged(streams)                                  # mixed progress before the timed region: thirds at 0 / 16 / 32 rows
+        eng.reset_sessions(slots[: streams // 3])
+        eng.run_staged(streams)
+        eng.reset_sessions(slots[streams // 3: 2 * streams // 3])
+        audio_per_step = streams * cfg.segment_length / cfg.sample_rate
+        h2d = d2h = 0
     else:
         pcm = synth_pcm(streams, cfg.chunk_length, first_id=rank * streams)
         slots = [eng.open_session() for _ in range(streams)]
@@ -259,6 +368,30 @@ def run_ours(args):
             e2e_call()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+    elif ragged:
+        eng.reset_sessions(slots)                            # the device-resident leg ran on the scheduler's slots: back to fresh state
+        barrier()
+        for _ in range(2):
+            wl.run_sync()
+        for _ in range(lat_passes):
+            dt, n_run = wl.run_sync()
+            lat_ms.append(1e3 * dt)
+        wl.run_pipelined(2, streams // 2)
+        barrier()
+        c0 = (wl.run_chunks, wl.skipped_chunks, wl.endpoints)
+        t0 = time.perf_counter()
+        wl.run_pipelined(args.steps, streams // 2)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        run_c, skip_c, end_c = wl.run_chunks - c0[0], wl.skipped_chunks - c0[1], wl.endpoints - c0[2]
+        per_chunk_in = cfg.chunk_length * 2 + 4
+        per_chunk_out = cfg.seg_rows * 4 * 2 + 3 * 4 + 4 * 256 + 8
+        h2d, d2h = run_c * per_chunk_in // args.steps, run_c * per_chunk_out // args.steps
+        extra["ragged"] = {"sessions": streams, "ticks_in_flight": 2, "max_rows_per_tick": streams // 2,
+                           "decoded_chunks_per_pass": run_c / args.steps, "vad_skipped_chunks_per_pass": skip_c / args.steps,
+                           "endpoints_per_pass": end_c / args.steps,
+                           "e2e_counts": "audio-seconds of the chunks actually decoded (VAD-skipped chunks are excluded from e2e.value)"}
+        e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / args.steps
     else:
         for _ in range(2):                                   # fill both pinned staging buffers once (the receive path writes here)
             view = eng.pinned_pcm(np.int16)
@@ -285,12 +418,12 @@ def run_ours(args):
     clocks = sampler.result()
 
     value = world * args.steps * audio_per_step / (dev_ms / 1e3)
-    e2e_value = world * args.steps * audio_per_step / e2e_s
+    e2e_value = world * args.steps * (e2e_audio_per_step if ragged else audio_per_step) / e2e_s
 
     # ---- larger batches on the same GPU (device-resident leg only; explains where the headline sits on the curve)
     sweep = []
     if world == 1 and not fbank_only and not args.no_sweep:
-        for s_n in (1024, 4096):
+        for s_n in (256, 1024, 4096):
             if s_n == streams:
                 continue
             eng.close()
@@ -333,7 +466,7 @@ def run_ours(args):
             all_gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
             all_gemm_flop = streams * (flop_sc - 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
             roof = {"kernel": f"gemm_tc_kernel ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(args.workload if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                    "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(("streams4096" if ragged else args.workload) if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,
                     "all_gemms": {"ms_per_step": all_gemm_ms, "tflops": all_gemm_flop / (all_gemm_ms / 1e3) / 1e12}}
             extra["path_roofline"] = {"flop_per_stream_chunk": flop_sc,
@@ -353,10 +486,11 @@ def run_ours(args):
             "roofline": roof,
             "kernel_families_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in fam.items()},
             "chunk_latency_ms": ({"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)), "max": float(max(lat_ms)),
-                                  "what": "synchronous Engine.step of the whole batch from pinned host memory: H2D + kernels + D2H of ids"}
+                                  "what": ("synchronous SessionScheduler.tick over every ready session: VAD gate + pinned gather + H2D + kernels + D2H + bookkeeping + endpoint rules"
+                                           if ragged else "synchronous Engine.step of the whole batch from pinned host memory: H2D + kernels + D2H of ids")}
                                  if lat_ms else None),
             # real-time capacity: every stream needs one chunk per 640 ms; ticks of this batch size back to back
-            "realtime_streams_per_gpu": (int(streams * (1e3 * cfg.segment_length / cfg.sample_rate) / (1e3 * e2e_s / args.steps)) if not fbank_only else None),
+            "realtime_streams_per_gpu": (int(e2e_value / world) if not fbank_only else None),
         }
         line.update(extra)
         if world == 1 and not fbank_only and not args.no_sweep:

@@ -92,6 +92,8 @@ struct AsrEngine {
   int device = 0, num_sms = 148;
   int simt_gemm = 0;
   int no_pair = 0;
+  int fused_ln = 1;             // LayerNorm fused into the out_proj / FFN2 epilogues (gemm_ln.cu); ASR_B200_NO_FUSED_LN=1 -> separate passes
+  int fused_ln_min_streams = 160;   // below this batch the separate LN passes win (measured: 64 streams 1.30 vs 1.59 ms, 256: 2.00 vs 2.00, 1024: 5.99 vs 5.77)
   int pdl_max_streams = 1536;   // programmatic dependent launch below this batch size (see common.cuh)
   int staged_fmt = 0;
   cudaStream_t stream = nullptr;
@@ -334,6 +336,12 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
   return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 || bn == kPairTile ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
 }
 
+int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const LnEpilogue& ep) {
+  const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
+  ProfScope ps(e, cat);
+  return gemm_ln(a.tm, w.tm[2], p, ep, e->num_sms, e->stream);
+}
+
 // ------------------------------------------------------------------------------------------ the per-step kernel chain
 template <typename T>
 int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
@@ -356,6 +364,26 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     ap.rows = g.rows; ap.seg_rows = g.seg_rows; ap.rc_rows = g.rc_rows; ap.ring = g.ring; ap.left = g.left; ap.d = d; ap.n_heads = g.n_heads;
     { ProfScope ps(e, ASR_PROF_ATTN); if (attention_launch<T>(ap, n, e->stream)) return -1; }
 
+    const bool last = l == g.n_layers - 1;
+    if (e->fused_ln && n >= e->fused_ln_min_streams) {
+      // out_proj + residual (pre-LN input) + LN_ff -> x1 (fp32) and the FFN1 operand
+      LnEpilogue eo{L.bo, e->x.as<float>(), L.ln_ff_g, L.ln_ff_b, nullptr, nullptr, e->x1.as<float>(), e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, 0, 0, 0};
+      if (run_gemm_ln(e, ASR_PROF_GEMM_OUT, e->a_attn, L.o, M, eo)) return -1;
+      EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
+      if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1)) return -1;
+      // FFN2 + residual + LN_out -> x (fp32) and LN_in of the next layer -> QKV operand (last layer: segment rows -> CTC operand)
+      LnEpilogue e2{L.b2, e->x1.as<float>(), L.ln_out_g, L.ln_out_b, nullptr, nullptr, e->x.as<float>(), nullptr, 0, 0, 0, 0, 0};
+      if (last) {
+        e2.out_op = e->a_enc.buf.as<bf16>(); e2.op_ld = e->a_enc.ld; e2.op_lo_off = e->a_enc.lo_off;
+        e2.f32_normed = 1; e2.compact_rows = g.rows; e2.compact_seg = g.seg_rows;
+      } else {
+        const LayerW& Nx = e->layers[l + 1];
+        e2.g2 = Nx.ln_in_g; e2.b2 = Nx.ln_in_b;
+        e2.out_op = e->a_ln.buf.as<bf16>(); e2.op_ld = e->a_ln.ld; e2.op_lo_off = e->a_ln.lo_off;
+      }
+      if (run_gemm_ln(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
+      continue;
+    }
     EpiF32 eo{e->x1.as<float>(), L.bo, e->x.as<float>(), d, d};                          // out_proj + residual (pre-LN input)
     if (run_gemm(e, ASR_PROF_GEMM_OUT, e->a_attn, L.o, M, eo)) return -1;
     { ProfScope ps(e, ASR_PROF_LN); if (ln_to_operand(e->x1.as<float>(), L.ln_ff_g, L.ln_ff_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, d, e->stream)) return -1; }
@@ -364,7 +392,6 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     EpiF32 e2{e->x2.as<float>(), L.b2, e->x1.as<float>(), d, d};
     if (run_gemm(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
     ProfScope ps_ln(e, ASR_PROF_LN);
-    const bool last = l == g.n_layers - 1;
     if (last) {
       if (ln_out_fused(e->x2.as<float>(), L.ln_out_g, L.ln_out_b, e->x.as<float>(), nullptr, nullptr, e->a_enc.buf.as<bf16>(), e->a_enc.ld,
                        e->a_enc.lo_off, M, d, g.rows, g.seg_rows, e->stream)) return -1;
@@ -617,6 +644,9 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   e->simt_gemm = dbg && dbg[0] == '1';
   const char* np_ = getenv("ASR_B200_NO_PAIR_GEMM");
   e->no_pair = np_ && np_[0] == '1';
+  if (const char* nf = getenv("ASR_B200_NO_FUSED_LN")) e->fused_ln = !(nf[0] == '1');
+  if (e->simt_gemm || cfg->d_model != 512) e->fused_ln = 0;
+  if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
   if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
   int rc = -1;
   do {
@@ -1133,6 +1163,63 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
     rc = 0;
   } while (0);
   dA32.free(); dB32.free(); dA.free(); dB.free(); dC.free(); dbias.free();
+  return rc;
+}
+
+/* Diagnostic: the fused GEMM + residual + LayerNorm kernel on host data.  W: [512, K].  g2/b2 nullable.  out_op_f32: the bf16 operand
+ * output converted back to fp32, [M, 512] (or [M / compact_rows * compact_seg, 512] when compact_rows > 0). */
+int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res, const float* g1,
+                      const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows, int32_t compact_seg,
+                      float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int device) {
+  if (!A || !W || !bias || !res || !g1 || !b1 || !out_f32 || !out_op_f32 || M <= 0 || K <= 0 || K % 64) { set_error("asr_debug_gemm_ln: bad arguments"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int N = 512, ld = split ? 2 * K : K, lo = split ? K : 0, old_ = split ? 2 * N : N, olo = split ? N : 0;
+  const int Mp = (int)round_up(M, 128);
+  const int Mo = compact_rows > 0 ? M / compact_rows * compact_seg : M;
+  DevBuf dA32, dW32, dA, dW, dv, dres, dout, dop;
+  std::vector<bf16> hop;
+  int rc = -1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  do {
+    if (dA32.alloc(4 * (size_t)M * K) || dW32.alloc(4 * (size_t)N * K) || dA.alloc(2 * (size_t)Mp * ld) || dW.alloc(2 * (size_t)N * ld) ||
+        dv.alloc(4 * (size_t)N * 5) || dres.alloc(4 * (size_t)M * N) || dout.alloc(4 * (size_t)M * N) || dop.alloc(2 * (size_t)Mp * old_)) break;
+    bool ok = cudaMemcpy(dA32.p, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemcpy(dW32.p, W, 4 * (size_t)N * K, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(dres.p, res, 4 * (size_t)M * N, cudaMemcpyHostToDevice) == cudaSuccess;
+    const float* vecs[5] = {bias, g1, b1, g2, b2};
+    for (int i = 0; i < 5 && ok; ++i)
+      if (vecs[i]) ok = cudaMemcpy(dv.as<float>() + i * N, vecs[i], 4 * (size_t)N, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { set_error("H2D failed"); break; }
+    cudaMemset(dA.p, 0, dA.bytes); cudaMemset(dop.p, 0, dop.bytes);
+    if (convert_weight(dA32.as<float>(), dA.as<bf16>(), M, K, ld, lo, 0) || convert_weight(dW32.as<float>(), dW.as<bf16>(), N, K, ld, lo, 0)) break;
+    const GemmProblem p = make_problem(M, N, K, split);
+    CUtensorMap ta, tb;
+    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dW.p, ld, N, ld, 256)) break;
+    LnEpilogue ep{dv.as<float>(), dres.as<float>(), dv.as<float>() + N, dv.as<float>() + 2 * N, g2 ? dv.as<float>() + 3 * N : nullptr,
+                  b2 ? dv.as<float>() + 4 * N : nullptr, dout.as<float>(), dop.as<bf16>(), old_, olo, f32_normed, compact_rows, compact_seg};
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int n_it = iters > 0 ? iters : 1;
+    for (int it = 0; it < n_it + 1 && ok; ++it) {
+      if (it == 1) cudaEventRecord(e0, 0);
+      ok = !gemm_ln(ta, tb, p, ep, prop.multiProcessorCount, 0);
+    }
+    if (!ok) break;
+    cudaEventRecord(e1, 0);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { set_error("asr_debug_gemm_ln: kernel failed: %s", cudaGetErrorString(err)); break; }
+    if (ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_out = ms / n_it; }
+    hop.resize((size_t)Mo * old_);
+    if (cudaMemcpy(out_f32, dout.p, 4 * (size_t)M * N, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(hop.data(), dop.p, 2 * hop.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); break; }
+    for (int r = 0; r < Mo; ++r)
+      for (int c = 0; c < N; ++c)
+        out_op_f32[(size_t)r * N + c] = __bfloat162float(hop[(size_t)r * old_ + c]) + (olo ? __bfloat162float(hop[(size_t)r * old_ + olo + c]) : 0.f);
+    rc = 0;
+  } while (0);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  dA32.free(); dW32.free(); dA.free(); dW.free(); dv.free(); dres.free(); dout.free(); dop.free();
   return rc;
 }
 

@@ -15,6 +15,25 @@ int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p
 template <class Epi>
 int gemm_simt(const bf16* A, int lda, const bf16* B, int ldb, const GemmProblem& p, const Epi& epi, cudaStream_t st);
 
+// N = 512 GEMM with residual add + LayerNorm(s) fused into the epilogue (gemm_ln.cu).  With v = A W^T + bias + res:
+//   g2 == nullptr, f32_normed = 0 :  out_f32 = v,            out_op = bf16 LN(v; g1, b1)                       (out_proj -> FFN1 operand)
+//   g2 != nullptr                 :  out_f32 = LN(v; g1,b1), out_op = bf16 LN(out_f32; g2, b2)                 (FFN2 -> next layer's QKV operand)
+//   g2 == nullptr, f32_normed = 1 :  out_f32 = LN(v; g1,b1), out_op = bf16 out_f32                              (last FFN2 -> CTC operand)
+// compact_rows > 0: out_op keeps only rows t < compact_seg of every block of compact_rows rows, packed (segment rows without right context).
+struct LnEpilogue {
+  const float* bias;     // [512]
+  const float* res;      // [M, 512] fp32
+  const float* g1; const float* b1;
+  const float* g2; const float* b2;
+  float* out_f32;        // [M, 512]
+  bf16* out_op;          // [rows, op_ld] bf16 hi (+ lo at op_lo_off)
+  int op_ld, op_lo_off;
+  int f32_normed;
+  int compact_rows, compact_seg;
+};
+// tmB256: tensor map of the [512, ld] weight with a 256-row box.
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows);
 
 }  // namespace asr

@@ -1,0 +1,400 @@
+// GEMM (N = 512 = d_model) with the residual add and the following LayerNorm(s) fused into the epilogue.
+//
+// Replaces, per Emformer layer (TA:emformer.py:416-440):
+//   out_proj  : x1 = x + attn W_o^T + b_o                      -> fp32 x1  and  bf16 LN_ff(x1)        (A operand of FFN1)
+//   FFN2      : y  = LN_out(x1 + h W_2^T + b_2)                -> fp32 y   and  bf16 LN_in'(y)         (A operand of the next QKV)
+//   last FFN2 : y  = LN_out(...)                               -> fp32 y   and  bf16 y of the segment rows (A operand of the CTC head)
+// i.e. the separate LayerNorm passes (ln_to_operand / ln_out_fused, 41 launches and ~3.2 MB of HBM traffic per stream-chunk) and
+// the fp32 x2 round trip disappear.
+//
+// LayerNorm needs whole rows, a CTA's TMEM holds 128 x 512 fp32 only once.  To keep the accumulators double-buffered the row
+// is split over a cluster of two CTAs: both compute the same 128 rows, CTA r the columns [256 r, 256 r + 256).  The mainloop is
+// the one of gemm_tc_kernel<256> (TMA producer warp, single-thread tcgen05.mma issuer, 3-stage smem ring).  The 16 epilogue
+// warps work in up to three passes over their accumulator chunks (thread = row for the statistics, TMEM as the scratch):
+//   R1   tcgen05.ld -> + bias + residual (residual read with full-line accesses, transposed through smem into row layout)
+//        -> per-chunk (sum, M2) around the chunk mean (Chan et al. combination: two-pass accuracy) -> tcgen05.st v back
+//   X    row statistics exchange: 4 warps x 2 CTAs own pieces of a row; inside the CTA through shared memory + a named barrier,
+//        across the pair with st.async into the peer's shared memory signalling the peer's mbarrier (no cluster-scope fences)
+//   R1b  (two-LN form only) tcgen05.ld v -> y = LN_a(v) in row layout -> statistics of y -> tcgen05.st y -> exchange
+//   R2   tcgen05.ld -> 16-byte transpose through smem -> fp32 row + bf16 LN_b(row) stores, 4 rows x 128 B per instruction
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace asr {
+
+namespace {
+
+using namespace tc;
+
+constexpr int LN_N = 512;
+constexpr int LBN = 256;                                   // columns per CTA
+constexpr int L_STAGES = 3;
+constexpr int L_STAGE_BYTES = (BM + LBN) * BK * 2;         // 48 KB
+constexpr int L_EW = 16;                                   // epilogue warps: 4 per TMEM lane quarter, 2 chunks of 32 columns each
+constexpr int L_THREADS = 64 + 32 * L_EW;
+constexpr int L_LD = 36;                                   // fp32 row stride of the per-warp transpose tile (conflict-free both ways)
+constexpr int L_XPOSE_FLOATS = 32 * L_LD;
+constexpr int L_XPOSE_BYTES = L_EW * L_XPOSE_FLOATS * 4;
+constexpr int L_STATS_BYTES = 4 * BM * 8 + 2 * BM * 8;         // local[warp in quarter][row] + remote[set][row], float2 (sum, M2)
+constexpr int L_SMEM_BYTES = L_STAGES * L_STAGE_BYTES + L_XPOSE_BYTES + L_STATS_BYTES + 1024 + 256;
+static_assert(L_SMEM_BYTES <= 232448, "gemm_ln: shared memory budget");
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// (sum, M2 around the own mean) of 32 values held by one thread
+__device__ __forceinline__ void chunk_stats(const float (&v)[32], float& sum, float& m2) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};                        // four independent chains: the epilogue is latency-, not issue-bound
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) { s[0] += v[j]; s[1] += v[j + 1]; s[2] += v[j + 2]; s[3] += v[j + 3]; }
+  const float t = (s[0] + s[1]) + (s[2] + s[3]);
+  const float m = t * (1.0f / 32.0f);
+  float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float d = v[j + k] - m; q[k] = fmaf(d, d, q[k]); }
+  }
+  sum = t; m2 = (q[0] + q[1]) + (q[2] + q[3]);
+}
+
+struct RowStats { float mean, rstd; };
+
+// Everything one epilogue warp needs for the row-statistics exchange of its TMEM lane quarter.
+struct XchgCtx {
+  uint32_t local_part;     // shared::cta address of local[wq][row] (this thread's slot); the quarter's 4 slots are BM*8 bytes apart
+  uint32_t local_row;      // shared::cta address of local[0][row]
+  uint32_t remote_set0;    // shared::cta address of remote[0][row] (what the peer wrote for us); set 1 is BM*8 bytes further
+  uint32_t peer_remote0;   // shared::cluster address of the PEER's remote[0][row]
+  uint32_t bar0;           // shared::cta address of xbar[0][quarter]; set 1 is 4*8 bytes further
+  uint32_t peer_bar0;      // shared::cluster address of the peer's xbar[0][quarter]
+  int named_bar;           // 1 + quarter
+  int wq;
+  uint32_t rank;
+};
+
+// All 128 threads of a lane quarter (4 warps) in both CTAs call this once per round with their partial: sum over their 64 values
+// and M2 around that partial's own mean.  Returns mean and 1/sqrt(var + eps) of the whole 512-wide row (biased variance,
+// torch.nn.LayerNorm).  Two levels, Chan's pairwise combination at both (two-pass accuracy, fixed order => bit-reproducible):
+//   inside the CTA   partials through shared memory, two named-barrier syncs of the quarter's 128 threads
+//   across the CTAs  warp wq == 0 pushes the CTA's combined (sum, M2) into the peer's shared memory with st.async, which signals
+//                    the peer's mbarrier (complete_tx) — no cluster-scope fence, no L1 invalidation on the consumer side.
+// Two mbarriers / receive slots per quarter alternate by round, so a packet of round r+2 can never be counted in round r.
+__device__ __forceinline__ RowStats exchange_row_stats(float sum, float m2, const XchgCtx& X, int round) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(X.local_part), "f"(sum), "f"(m2) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");
+  float2 p[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p[w].x), "=f"(p[w].y) : "r"(X.local_row + (uint32_t)(w * BM) * 8u) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");          // everyone has read: the slots may be rewritten next round
+  const float s_cta = (p[0].x + p[1].x) + (p[2].x + p[3].x);
+  const float mean_cta = s_cta * (1.0f / 256.0f);
+  float q_cta = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) { const float d = p[w].x * (1.0f / 64.0f) - mean_cta; q_cta += p[w].y + 64.0f * d * d; }
+  const uint32_t set = (uint32_t)(round & 1), parity = (uint32_t)((round >> 1) & 1);
+  const uint32_t bar = X.bar0 + set * 32u;
+  if (X.wq == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 8;" ::"r"(bar) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(X.peer_remote0 + set * (uint32_t)(BM * 8)), "f"(s_cta), "f"(q_cta), "r"(X.peer_bar0 + set * 32u) : "memory");
+  }
+  mbar_wait(bar, parity);
+  float2 o;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(X.remote_set0 + set * (uint32_t)(BM * 8)) : "memory");
+  const float s0 = X.rank == 0 ? s_cta : o.x, s1 = X.rank == 0 ? o.x : s_cta;       // CTA 0 first in both CTAs: identical sums
+  const float q0 = X.rank == 0 ? q_cta : o.y, q1 = X.rank == 0 ? o.y : q_cta;
+  const float mean = (s0 + s1) * (1.0f / LN_N);
+  const float d0 = s0 * (1.0f / 256.0f) - mean, d1 = s1 * (1.0f / 256.0f) - mean;
+  const float m2_all = (q0 + 256.0f * d0 * d0) + (q1 + 256.0f * d1 * d1);
+  RowStats r;
+  r.mean = mean;
+  r.rstd = 1.0f / sqrtf(m2_all * (1.0f / LN_N) + 1e-5f);
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, LnEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xpose_base = smem_base + L_STAGES * L_STAGE_BYTES;
+  const uint32_t stats_base = xpose_base + L_XPOSE_BYTES;
+  const uint32_t bar_base = stats_base + L_STATS_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (L_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * L_STAGES + 2 + s); };
+  auto xq_bar = [&](int set, int q) { return bar_base + 8u * (2 * L_STAGES + 4 + 4 * set + q); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * L_STAGES + 12);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int kb_per_pass = p.K / BK;
+  const int total_kb = kb_per_pass * p.passes;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < L_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), L_EW); }
+    for (int q = 0; q < 8; ++q) mbar_init(xq_bar(q >> 2, q & 3), 32);       // the 32 lanes of the quarter's warp 0 arm 8 bytes each
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_barrier();                                       // the peer's barriers exist before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        for (int ps = 0; ps < p.passes; ++ps) {
+          for (int kb = 0; kb < kb_per_pass; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
+            const uint32_t sb = sa + BM * BK * 2;
+            mbar_expect_tx(full_bar(stage), (uint32_t)L_STAGE_BYTES);
+            tma_load_2d(sa, &tmA, p.a_koff[ps] + kb * BK, m_blk * BM, full_bar(stage));
+            tma_load_2d(sb, &tmB, p.b_koff[ps] + kb * BK, (int)rank * LBN, full_bar(stage));
+            if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(LBN);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * LBN);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + BM * BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == total_kb - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+    const int wq = ew >> 2;                                  // which of the 4 warps sharing the quarter: chunks wq and wq + 4
+    const int rsub = lane >> 3, csub = 4 * (lane & 7);
+    float* xpose = reinterpret_cast<float*>(smem_raw + (xpose_base - smem_u32(smem_raw))) + ew * L_XPOSE_FLOATS;
+    XchgCtx X;
+    {
+      const uint32_t row_off = (uint32_t)(quarter * 32 + lane) * 8u;
+      X.local_row = stats_base + row_off;
+      X.local_part = X.local_row + (uint32_t)(wq * BM) * 8u;
+      X.remote_set0 = stats_base + 4u * BM * 8u + row_off;
+      X.peer_remote0 = map_to_cta(X.remote_set0, rank ^ 1u);
+      X.bar0 = xq_bar(0, quarter);
+      X.peer_bar0 = map_to_cta(X.bar0, rank ^ 1u);
+      X.named_bar = 1 + quarter; X.wq = wq; X.rank = rank;
+    }
+    const int col_cta = (int)rank * LBN;
+    int acc = 0; uint32_t acc_phase = 0;
+    int round = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+      const int row0 = m_blk * BM + quarter * 32;
+      const int my_row = row0 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * LBN);
+      if (my_row < p.M) {                                    // residual lines of my row -> L2 while the MMAs of the tile run
+        const float* r = ep.res + (size_t)my_row * LN_N + col_cta;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + wq * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (wq + 4) * 32));
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+
+      float raw[32];
+      // ---------------- R1: v = acc + bias + residual, statistics of v
+      float s_a = 0.f, q_a = 0.f, s_b = 0.f, q_b = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int cc = wq + 4 * h;
+        const int col0 = col_cta + cc * 32;
+        tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + 4 * i + rsub;
+          const float4 r4 = row < p.M ? *reinterpret_cast<const float4*>(ep.res + (size_t)row * LN_N + col0 + csub) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(xpose + (4 * i + rsub) * L_LD + csub) = r4;
+        }
+        __syncwarp();
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 rr = *reinterpret_cast<const float4*>(xpose + lane * L_LD + j);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+          raw[j] += rr.x + bb.x; raw[j + 1] += rr.y + bb.y; raw[j + 2] += rr.z + bb.z; raw[j + 3] += rr.w + bb.w;
+        }
+        __syncwarp();
+        if (h == 0) chunk_stats(raw, s_a, q_a); else chunk_stats(raw, s_b, q_b);
+        tmem_st32(taddr + (uint32_t)(cc * 32), raw);
+      }
+      tmem_st_wait();
+      {
+        const float d = (s_a - s_b) * (1.0f / 32.0f);
+        q_a = q_a + q_b + 16.0f * d * d;                     // Chan: n_a n_b / (n_a + n_b) = 16
+        s_a += s_b;
+      }
+      RowStats st = exchange_row_stats(s_a, q_a, X, round++);
+
+      const float* g_fin = ep.g1;
+      const float* b_fin = ep.b1;
+      if (ep.g2) {
+        // ---------------- R1b: y = LN_a(v) in row layout, statistics of y
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int cc = wq + 4 * h;
+          const int col0 = col_cta + cc * 32;
+          tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(ep.g1 + col0 + j));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.b1 + col0 + j));
+            raw[j] = (raw[j] - st.mean) * st.rstd * gg.x + bb.x;
+            raw[j + 1] = (raw[j + 1] - st.mean) * st.rstd * gg.y + bb.y;
+            raw[j + 2] = (raw[j + 2] - st.mean) * st.rstd * gg.z + bb.z;
+            raw[j + 3] = (raw[j + 3] - st.mean) * st.rstd * gg.w + bb.w;
+          }
+          if (h == 0) chunk_stats(raw, s_a, q_a); else chunk_stats(raw, s_b, q_b);
+          tmem_st32(taddr + (uint32_t)(cc * 32), raw);
+        }
+        tmem_st_wait();
+        const float d = (s_a - s_b) * (1.0f / 32.0f);
+        q_a = q_a + q_b + 16.0f * d * d;
+        s_a += s_b;
+        st = exchange_row_stats(s_a, q_a, X, round++);
+        g_fin = ep.g2; b_fin = ep.b2;
+      }
+
+      // ---------------- R2: fp32 row + bf16 LayerNorm(row) with full-line stores
+      float mu[8], rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mu[i] = __shfl_sync(0xffffffffu, st.mean, 4 * i + rsub);
+        rs[i] = __shfl_sync(0xffffffffu, st.rstd, 4 * i + rsub);
+      }
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int cc = wq + 4 * h;
+        const int col = col_cta + cc * 32 + csub;
+        tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(xpose + lane * L_LD + j) = make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+        __syncwarp();
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g_fin + col));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b_fin + col));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + 4 * i + rsub;
+          const float4 t = *reinterpret_cast<const float4*>(xpose + (4 * i + rsub) * L_LD + csub);
+          float n[4];
+          n[0] = (t.x - mu[i]) * rs[i] * gg.x + bb.x;
+          n[1] = (t.y - mu[i]) * rs[i] * gg.y + bb.y;
+          n[2] = (t.z - mu[i]) * rs[i] * gg.z + bb.z;
+          n[3] = (t.w - mu[i]) * rs[i] * gg.w + bb.w;
+          if (row < p.M) {
+            *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * LN_N + col) = ep.f32_normed ? make_float4(n[0], n[1], n[2], n[3]) : t;
+            int orow = row;
+            if (ep.compact_rows) {                           // last layer: only the segment rows feed the CTC head (TA:emformer.py:803)
+              const int b = row / ep.compact_rows, tt = row - b * ep.compact_rows;
+              orow = tt < ep.compact_seg ? b * ep.compact_seg + tt : -1;
+            }
+            if (orow >= 0) {
+              bf16* o = ep.out_op + (size_t)orow * ep.op_ld + col;
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(n[0], n[1]), h23 = __floats2bfloat162_rn(n[2], n[3]);
+              *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              if (ep.op_lo_off) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                *reinterpret_cast<uint2*>(o + ep.op_lo_off) = make_uint2(pack_bf16x2(n[0] - f01.x, n[1] - f01.y), pack_bf16x2(n[2] - f23.x, n[3] - f23.y));
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_barrier();                                       // the peer may still read this CTA's statistics through DSMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
+  if (p.M <= 0) return 0;
+  if (p.N != LN_N) { set_error("gemm_ln: N = %d, the fused LayerNorm epilogue is built for d_model = %d", p.N, LN_N); return -1; }
+  if (p.K % BK != 0) { set_error("gemm_ln: K=%d not a multiple of %d", p.K, BK); return -1; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int clusters = m_tiles < num_sms / 2 ? m_tiles : num_sms / 2;
+  ASR_CUDA_OK(launch_pdl(gemm_ln_kernel, dim3(2 * clusters), dim3(L_THREADS), L_SMEM_BYTES, st, tmA, tmB256, p, ep));
+  return 0;
+}
+
+}  // namespace asr

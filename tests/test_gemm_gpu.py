@@ -63,3 +63,71 @@ def test_simt_crosscheck_gemm():
     for split in (0, 1):
         out = debug_gemm(A, B, None, impl=1, split=split)
         assert np.abs(out - _ref(A, B, None, split)).max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ GEMM + residual + LayerNorm epilogue
+def _ln(x, g, b):
+    x = x.astype(np.float64)
+    mu = x.mean(1, keepdims=True)
+    var = ((x - mu) ** 2).mean(1, keepdims=True)
+    return (x - mu) / np.sqrt(var + 1e-5) * g + b
+
+
+LN_CASES = [
+    # M, K, split, mode ("a": out_proj form, "b": two LayerNorms, "c": last layer, compact segment rows), row mean offset
+    (128, 64, 0, "a", 0.0),
+    (20, 512, 0, "a", 0.0),            # one stream: a single, mostly empty tile
+    (5120, 512, 0, "a", 0.0),          # out_proj at 256 streams: 40 row tiles
+    (5120, 2048, 0, "b", 0.0),         # FFN2 at 256 streams
+    (20000, 512, 0, "b", 3.0),         # more tiles than clusters (157 > 74): persistent loop, TMEM double buffering, stats ping-pong
+    (1333, 2048, 0, "b", -7.5),        # ragged M, rows with a large common offset (variance must not cancel)
+    (5120, 2048, 0, "c", 0.0),
+    (1000, 512, 1, "a", 1.0),          # EXACT: three passes, hi|lo operand output
+    (1000, 2048, 1, "b", 0.0),
+    (1000, 2048, 1, "c", 0.0),
+]
+
+
+@pytest.mark.parametrize("M,K,split,mode,offset", LN_CASES)
+def test_gemm_residual_layernorm_epilogue(M, K, split, mode, offset):
+    from asr_streaming_b200.engine import debug_gemm_ln
+    rng = np.random.default_rng(M + K + split + ord(mode))
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((512, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(512).astype(np.float32)
+    res = (rng.standard_normal((M, 512)) + offset).astype(np.float32)
+    g1, b1, g2, b2 = [(s * rng.standard_normal(512) + o).astype(np.float32) for s, o in ((0.2, 1.0), (0.3, 0.0), (0.2, 1.0), (0.3, 0.0))]
+    v = _ref(A, W, bias, split).astype(np.float64) + res
+    rows, seg = (20, 16) if mode == "c" else (0, 0)
+    if mode == "a":
+        out, op, _ = debug_gemm_ln(A, W, bias, res, g1, b1, split=split)
+        ref_out, ref_op = v, _ln(v, g1, b1)
+    elif mode == "b":
+        out, op, _ = debug_gemm_ln(A, W, bias, res, g1, b1, g2, b2, split=split)
+        ref_out = _ln(v, g1, b1)
+        ref_op = _ln(ref_out, g2, b2)
+    else:
+        out, op, _ = debug_gemm_ln(A, W, bias, res, g1, b1, f32_normed=True, compact_rows=rows, compact_seg=seg, split=split)
+        ref_out = _ln(v, g1, b1)
+        keep = (np.arange(M) % rows) < seg
+        ref_op = ref_out[keep][:op.shape[0]]
+    tol = 3e-4 * max(1.0, abs(offset))
+    assert np.abs(out - ref_out).max() < tol, f"fp32 output max-abs {np.abs(out - ref_out).max()}"
+    op_tol = 2e-4 if split else 0.02                      # bf16 operand rounding (values up to ~5)
+    assert np.abs(op - ref_op).max() < op_tol, f"operand output max-abs {np.abs(op - ref_op).max()}"
+
+
+def test_gemm_layernorm_rows_do_not_depend_on_their_position():
+    """The same input row must give bit-identical outputs wherever it sits in the batch (statistics are combined in a fixed order)."""
+    from asr_streaming_b200.engine import debug_gemm_ln
+    rng = np.random.default_rng(3)
+    M, K = 1000, 512
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((512, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(512).astype(np.float32)
+    res = rng.standard_normal((M, 512)).astype(np.float32)
+    g = np.ones(512, np.float32); b = np.zeros(512, np.float32)
+    perm = rng.permutation(M)
+    o1, p1, _ = debug_gemm_ln(A, W, bias, res, g, b, g, b)
+    o2, p2, _ = debug_gemm_ln(A[perm], W, bias, res[perm], g, b, g, b)
+    assert np.array_equal(o1[perm], o2) and np.array_equal(p1[perm], p2)

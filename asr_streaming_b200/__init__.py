@@ -12,6 +12,8 @@ from .engine import Engine, StepResult  # noqa: F401
 from .weights import pack_weights, weights_from_checkpoint, random_weights  # noqa: F401
 from .recognition import LightningASR, greedy_search, ids_to_text, set_vocab, SessionState  # noqa: F401
 from .scheduler import SessionScheduler, StreamSession, GpuRouter  # noqa: F401
+from .endpoint import EndpointRules, OnlineEndpointRule, detect_endpointing, load_endpointing_rule  # noqa: F401
+from .results import DecodedResult, create_hypotheses, interim_message, final_message, tick_messages  # noqa: F401
 
 __all__ = ["AudioConfig", "ModelConfig", "Engine", "StepResult", "LightningASR", "greedy_search", "SessionScheduler",
            "StreamSession", "GpuRouter", "pack_weights", "weights_from_checkpoint", "random_weights", "load_library",

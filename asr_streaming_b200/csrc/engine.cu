@@ -328,10 +328,13 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
   ProfScope ps(e, cat);
   if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
   int bn = pick_bn(e, M, w.N);
-  // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand ingest per SM) pay off when the mainloop dominates: measured
-  // on B200 (profiles/r01_gemm_sweep_transposed_epilogue.txt) the pair kernel wins at K = 2048 (FFN2: 136 vs 156 us) and loses
-  // at K = 512, where the tile time is set by the epilogue and coupling two CTAs' epilogues costs more than the ingest saves.
-  if (bn == 256 && !e->no_pair && w.K * (e->geo.split ? 3 : 1) >= 1024 && w.N % 256 == 0 && ((M + 255) / 256) * (w.N / 256) >= e->num_sms / 2)
+  // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand ingest per SM).  The 1-CTA 128 x 256 tile needs 96 B/clk/SM from L2
+  // at full tensor rate against a chip-wide cap of ~42 B/clk/SM, the pair 64 B/clk/SM.  Measured on B200
+  // (profiles/r01_gemm_sweep_*.txt): pair wins at K = 2048 (FFN2 127 vs 138 us) and, since the packed-math GELU epilogue stopped
+  // being the limiter, also at K = 512 for large M (FFN1 150 vs 157 us, QKV 116 vs 121 us); at small M the coupled epilogues lose.
+  const int k_eff = w.K * (e->geo.split ? 3 : 1);
+  const long pair_tiles = (long)((M + 255) / 256) * (w.N / 256);
+  if (bn == 256 && !e->no_pair && w.N % 256 == 0 && ((k_eff >= 1024 && pair_tiles >= e->num_sms / 2) || pair_tiles >= 4 * (e->num_sms / 2)))
     bn = kPairTile;
   return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 || bn == kPairTile ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
 }

@@ -97,6 +97,7 @@ class TickResult:
     final: np.ndarray = field(default_factory=lambda: np.zeros(0, bool))              # [n] endpoint fired after this chunk
     final_rule: List[Optional[str]] = field(default_factory=list)    # rule name per session (None if not final)
     final_tokens: Dict[int, List[int]] = field(default_factory=dict)  # session id -> tokens of the finished segment
+    final_utt_length: Dict[int, float] = field(default_factory=dict)  # session id -> seconds decoded in the finished segment (stream.py:132-134)
 
     @property
     def sessions(self) -> List[StreamSession]:
@@ -407,6 +408,7 @@ class SessionScheduler:
         for r, w in zip(frows, which[fired]):
             s = self._by_row[int(r)]
             res.final_tokens[s.id] = [int(t) for t in self.tok[r, :self.ntok[r]]]
+            res.final_utt_length[s.id] = float(self.chunk_processed[r] * self.cfg.segment_length / self.cfg.sample_rate)
             pos = np.nonzero(run_rows == r)[0]
             if pos.size:
                 res.final[pos[0]] = True

@@ -439,6 +439,43 @@ def test_native_pcm_peaks_matches_numpy():
     assert lib.asr_pcm_peaks(0, audio.ctypes.data, audio.shape[1], None, None, 0, 0, None) == 0
 
 
+def test_result_messages_have_the_reference_wire_format():
+    from asr_streaming_b200 import results as R
+    vocab = ["-", "|", "xin", "chào", "<<", ">>"]
+    m = R.interim_message("xin chào")
+    assert m == ('{"id": "", "status": 0, "msg": 0, "segment": 0, "result": {"hypotheses": [{"transcript": "xin chào", '
+                 '"transcript_normalized": "xin chào", "confidence": 0.0, "likelihood": 1.0, "word_alignment": []}], "final": false}, '
+                 '"segment_start": 0.0, "segment_length": 0.0, "total_length": 0.0, "message_type": 0, "word_start": 0.0, "word_end": 0.0, '
+                 '"snr": 0.0, "vol_noise": 0.0, "vol_speech": 0.0, "is_speaker": false}')
+    assert R.interim_message("  ") is None
+    f = R.final_message("7", 2, 6.4, 19.2, "xin chào")
+    assert f.startswith('{"id": "7", "status": 0, "msg": 0, "segment": 2, "result": {"hypotheses": [{"transcript": "xin chào"') and '"final": true' in f
+    assert '"segment_length": 6.4, "total_length": 19.2' in f and R.final_message("7", 2, 6.4, 19.2, "") is None
+    if os.path.isdir("/root/reference/streaming_decoder"):       # field-for-field against the reference source (importing it has side effects)
+        import ast, dataclasses
+        tree = ast.parse(open("/root/reference/streaming_decoder/utils.py").read())
+        cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "DecodedResult")
+        ref_fields = [n.target.id for n in cls.body if isinstance(n, ast.AnnAssign)]
+        assert ref_fields == [f.name for f in dataclasses.fields(R.DecodedResult)]
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "create_hypotheses")
+        keys = [n.targets[0].slice.value for n in fn.body if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Subscript)]
+        assert keys == list(R.create_hypotheses("x"))
+    # through the scheduler: interim after a decoded chunk, final when a rule fires
+    from asr_streaming_b200.endpoint import EndpointRules
+    cfg = A.ModelConfig(max_batch=4, max_sessions=4)
+    sch = A.SessionScheduler(TokenEngine(cfg), endpoint_rules=EndpointRules())
+    s = sch.open()
+    seq = [5] + [-1] * 3                       # a token in the first chunk, then silence-like chunks until rule1.x fires
+    msgs = []
+    for last in seq:
+        a = np.zeros(cfg.segment_length, np.int16); a[-1] = last
+        s.accept_waveform(a)
+        res = sch.tick()
+        msgs += R.tick_messages(sch, res, vocab).get(s.id, [])
+    assert len(msgs) >= 2 and '"final": false' in msgs[0] and '"final": true' in msgs[-1] and '"segment": 0' in msgs[-1]
+    assert s.segment == 1
+
+
 def test_partition_streams_covers_everything_once():
     from asr_streaming_b200.scheduler import partition_streams
     for n, w in ((32768, 8), (10, 3), (7, 8), (4096, 2)):

@@ -383,3 +383,70 @@ def test_reset_many_equals_fresh_sessions(engines):
         assert np.array_equal(ra.blank_frames[[1, 4]], rf.blank_frames)
     for s in a + fresh + keep:
         e.close_session(s)
+
+
+# ------------------------------------------------------------------------------------------------ fused GEMM + LayerNorm path
+@pytest.mark.parametrize("name", ["synth_noise", "testwav", "seq_reset_skip"])
+def test_fused_layernorm_path_matches_reference(name, packed_weights, golden, meta, monkeypatch):
+    """The engine takes the GEMM + residual + LayerNorm kernels (gemm_ln.cu) from 160 streams per step on; here they are forced
+    for a single stream so that the reference fixtures pin them too (both precisions), and compared with the separate-pass path."""
+    from asr_streaming_b200 import Engine, PRECISION_EXACT, PRECISION_FAST
+    case, mc = golden(name), meta["cases"][name]
+    monkeypatch.setenv("ASR_B200_FUSED_LN_MIN_STREAMS", "1")
+    with Engine(model_cfg(PRECISION_EXACT), packed_weights) as e:
+        em, ids, blanks = _run_case(e, case, mc)
+    assert np.abs(em - case["emission"]).max() < EXACT_TOL
+    assert np.array_equal(em.argmax(2), case["argmax"])
+    report(f"EXACT fused-LN {name}: logprob max-abs {np.abs(em - case['emission']).max():.3e}")
+    with Engine(model_cfg(PRECISION_FAST), packed_weights) as e:
+        em_f, _, _ = _run_case(e, case, mc)
+    monkeypatch.setenv("ASR_B200_NO_FUSED_LN", "1")
+    with Engine(model_cfg(PRECISION_FAST), packed_weights) as e:
+        em_u, _, _ = _run_case(e, case, mc)
+    assert np.abs(em_f - case["emission"]).max() < FAST_TOL
+    report(f"FAST fused-LN {name}: logprob max-abs {np.abs(em_f - case['emission']).max():.3e}; vs separate LN passes {np.abs(em_f - em_u).max():.3e}")
+    assert np.abs(em_f - em_u).max() < FAST_TOL
+
+
+def test_fused_layernorm_large_ragged_batch(packed_weights):
+    """200 streams in one step (above the fused threshold, M = 4000 is not a multiple of the 128-row tile) against the same
+    streams run one by one: per-stream results must not depend on the batch they ride in (FAST precision, bit-exact)."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(17)
+    n = 200
+    pcm = rng.integers(-4000, 4000, size=(3, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    with Engine(model_cfg(PRECISION_FAST, max_batch=256, max_sessions=512), packed_weights) as e:
+        big = [e.open_session() for _ in range(n)]
+        got = [e.step(big, pcm[t], want_logprobs=True).logprobs for t in range(3)]
+        for i in (0, 57, 199):
+            s = e.open_session()
+            for t in range(3):
+                one = e.step([s], pcm[t, i:i + 1], want_logprobs=True).logprobs[0]
+                assert np.abs(one - got[t][i]).max() < FAST_TOL, (i, t)  # different kernels (fused vs separate LN, bf16 operands): close, not identical
+        perm = rng.permutation(n)
+        other = [e.open_session() for _ in range(n)]
+        for t in range(3):
+            r = e.step([other[j] for j in perm], pcm[t][perm], want_logprobs=True).logprobs
+            assert np.array_equal(r, got[t][perm])                       # same kernels, different positions: bit-exact
+
+
+def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch):
+    """The persistent double-buffered attention kernel (taken from 148 streams per step on) forced for a small ragged batch:
+    same fragments and summation order as the CTA-per-stream kernel => bit-identical log-probs, at every left-context fill."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(23)
+    n = 37
+    pcm = rng.integers(-4000, 4000, size=(4, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    outs = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("ASR_B200_ATTN_STREAM_MIN", "1")
+        with Engine(model_cfg(PRECISION_FAST, max_batch=64, max_sessions=64), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n)]
+            got = []
+            for t in range(4):
+                if t == 2:
+                    e.reset_sessions(sl[5:20])                         # ragged: 0 / 32 valid left-context rows in one step
+                got.append(e.step(sl, pcm[t], want_logprobs=True).logprobs)
+            outs.append(np.stack(got))
+    assert np.array_equal(outs[0], outs[1])

@@ -110,7 +110,10 @@ struct AsrEngine {
   Operand a_fb, a_ln, a_attn, a_h, a_enc, a_ctc;
   // per-session state
   DevBuf kv_cache, past_len, prev_id, n_frames, last_tok;
-  size_t slot_stride = 0;
+  CUtensorMap tm_kv, tm_rc;      // head-major 3D views of the K/V cache / right-context scratch for the streaming attention kernel (bf16 only)
+  bool attn_tma = false;
+  size_t slot_stride = 0;        // elements between two sessions' rings inside one layer's slab
+  size_t layer_stride = 0;       // elements between two layers' slabs: K/V cache layout is [layer][slot][K|V][ring][d]
   std::vector<int> free_slots;
   std::vector<uint8_t> slot_open;
   // outputs
@@ -353,7 +356,7 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
   const int* slots = e->act_slots;
   for (int l = 0; l < n_layers_to_run; ++l) {
     const LayerW& L = e->layers[l];
-    T* cache_layer = e->kv_cache.as<T>() + (size_t)l * 2 * g.ring * d;
+    T* cache_layer = e->kv_cache.as<T>() + (size_t)l * e->layer_stride;
     EpiQKV<T> eq;
     eq.q = e->q.as<T>(); eq.cache_layer = cache_layer; eq.slot_stride = e->slot_stride; eq.rc = e->rc_kv.as<T>();
     eq.bias = L.bqkv; eq.slots = slots; eq.past_len = e->past_len.as<int>();
@@ -364,6 +367,7 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     AttnParams<T> ap;
     ap.q = e->q.as<T>(); ap.cache_layer = cache_layer; ap.slot_stride = e->slot_stride; ap.rc = e->rc_kv.as<T>();
     ap.slots = slots; ap.past_len = e->past_len.as<int>(); ap.out = e->a_attn.buf.as<bf16>(); ap.ld = e->a_attn.ld; ap.lo_off = e->a_attn.lo_off;
+    if (e->attn_tma) { ap.h_tm_cache = &e->tm_kv; ap.h_tm_rc = &e->tm_rc; ap.cache_row0 = (long long)l * (long long)(e->layer_stride / d); ap.slot_rows = (long long)(e->slot_stride / d); }
     ap.rows = g.rows; ap.seg_rows = g.seg_rows; ap.rc_rows = g.rc_rows; ap.ring = g.ring; ap.left = g.left; ap.d = d; ap.n_heads = g.n_heads;
     { ProfScope ps(e, ASR_PROF_ATTN); if (attention_launch<T>(ap, n, e->stream)) return -1; }
 
@@ -698,10 +702,23 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     if (make_operand(e, &e->a_fb, B * g.frames, g.n_mels) || make_operand(e, &e->a_ln, M, d) || make_operand(e, &e->a_attn, M, d) ||
         make_operand(e, &e->a_h, M, f) || make_operand(e, &e->a_enc, Mc, d) || make_operand(e, &e->a_ctc, Mc, g.ctc_hidden)) break;
     // ---- sessions
-    e->slot_stride = (size_t)g.n_layers * 2 * g.ring * d;
+    // Layer-major: the kernels of one layer touch one contiguous slab (max_sessions x 96 KB) instead of one 96 KB piece out of every
+    // session's 1.97 MB block (TLB reach, DRAM page locality).
     const size_t S = cfg->max_sessions;
-    if (e->kv_cache.alloc(esz * S * e->slot_stride) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S)) break;
+    e->slot_stride = (size_t)2 * g.ring * d;
+    e->layer_stride = S * e->slot_stride;
+    if (const char* sm = getenv("ASR_B200_KV_SLOT_MAJOR")) if (sm[0] == '1') {     // A/B switch: [slot][layer][K|V][ring][d]
+      e->layer_stride = (size_t)2 * g.ring * d;
+      e->slot_stride = (size_t)g.n_layers * e->layer_stride;
+    }
+    if (e->kv_cache.alloc(esz * S * g.n_layers * 2 * g.ring * d) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S)) break;
     if (cudaMemsetAsync(e->kv_cache.p, 0, e->kv_cache.bytes, e->stream) != cudaSuccess) { set_error("memset failed"); break; }
+    if (!g.split && d == 512 && g.n_heads == 8 && (g.seg_rows == 16 || g.seg_rows == 8) && g.rc_rows == 4) {
+      // not fatal: without the maps the CTA-per-stream attention kernel serves every batch size
+      e->attn_tma = !make_tmap_bf16_heads(&e->tm_kv, e->kv_cache.p, (uint64_t)S * g.n_layers * 2 * g.ring, 8, (uint32_t)g.seg_rows) &&
+                    !make_tmap_bf16_heads(&e->tm_rc, e->rc_kv.p, (uint64_t)B * 2 * g.rc_rows, 8, (uint32_t)g.rc_rows);
+      if (!e->attn_tma) fprintf(stderr, "asr_b200: streaming attention disabled: %s\n", asr_last_error());
+    }
     if (fill_i32(e->past_len.as<int>(), 0, S, e->stream) || fill_i32(e->n_frames.as<int>(), 0, S, e->stream) ||
         fill_i32(e->prev_id.as<int>(), -1, S, e->stream) || fill_i32(e->last_tok.as<int>(), -1, S, e->stream)) break;
     e->slot_open.assign(S, 0);
@@ -1118,7 +1135,7 @@ int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int32_t whic
   if (past_length) *past_length = pl;
   const size_t esz = g.split ? 4 : 2, d = g.d_model;
   std::vector<uint8_t> ring((size_t)g.ring * d * esz);
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(e->kv_cache.p) + ((size_t)slot * e->slot_stride + ((size_t)layer * 2 + which) * g.ring * d) * esz;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(e->kv_cache.p) + ((size_t)layer * e->layer_stride + (size_t)slot * e->slot_stride + (size_t)which * g.ring * d) * esz;
   ASR_CUDA_OK(cudaMemcpy(ring.data(), base, ring.size(), cudaMemcpyDeviceToHost));
   const int lv = std::min(pl, g.left);
   memset(out, 0, sizeof(float) * g.left * d);

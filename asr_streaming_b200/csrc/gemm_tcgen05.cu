@@ -469,4 +469,25 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_
   return 0;
 }
 
+// 3D view of a [rows, n_heads * 64] bf16 matrix as (64 dims, rows, heads) with a {64, box_rows, n_heads} box and 128B swizzle: one
+// TMA op lands box_rows full rows in shared memory head-major ([head][row][128 B]), the layout the attention warps want.
+int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t rows, uint32_t n_heads, uint32_t box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) { set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e)); return -1; }
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t gdim[3] = {64, rows, n_heads};
+  cuuint64_t gstr[2] = {(cuuint64_t)n_heads * 128, 128};            // bytes: row stride, head stride
+  cuuint32_t box[3] = {64, box_rows, n_heads};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3D) failed: CUresult %d (rows %llu heads %u box_rows %u)", (int)r, (unsigned long long)rows, n_heads, box_rows); return -1; }
+  return 0;
+}
+
 }  // namespace asr

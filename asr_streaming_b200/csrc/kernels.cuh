@@ -50,6 +50,12 @@ struct AttnParams {
   bf16* out;               // A operand [M, ld]
   int ld, lo_off;
   int rows, seg_rows, rc_rows, ring, left, d, n_heads;
+  // streaming bf16 kernel only (host pointers, read by the launcher): 3D head-major tensor maps of the whole K/V cache (box of
+  // seg_rows rows) and of the right-context scratch (box of rc_rows rows); cache_row0 = first cache row of this layer's slab.
+  const CUtensorMap* h_tm_cache = nullptr;
+  const CUtensorMap* h_tm_rc = nullptr;
+  long long cache_row0 = 0;
+  long long slot_rows = 0;   // cache rows per session inside a layer slab (2 * ring)
 };
 template <typename T> int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st);
 

@@ -400,18 +400,25 @@ __global__ void __launch_bounds__(AM_WARPS * 32, 2) attention_mma_kernel(AttnPar
 }
 
 // ------------------------------------------------------------------------------------------
-// Streaming variant for large batches: one persistent CTA per SM walks over its streams with the K/V staging area
-// double-buffered, so the HBM reads of stream i+1 (104 bulk copies of one 1 KB row each, issued by a producer warp,
-// completion counted on mbarriers: K and V separately) are in flight while the 8 head warps compute stream i.
-// The one-CTA-per-stream kernel above alternates a load phase and a compute phase with only two CTAs per SM to
-// overlap them (ncu: 30 % of DRAM peak, 46 % issue-active); here the memory pipe never drains.
-// Same math, same fragment layout, same summation order as attention_mma_kernel (bit-identical outputs).
+// Streaming variant (FAST precision, from 148 streams per step on): one persistent CTA per SM walks over its streams with the
+// K/V staging double-buffered and fed by TMA.  The ring advances by seg_rows = 16 rows per chunk, so a stream's cached keys are
+// 1..3 whole 16-row blocks (16 KB contiguous each) plus the 4 right-context rows: at most 4 TMA ops per K (and per V) through
+// a 3D (dim, row, head) tensor map whose box lands in shared memory head-major with the 128B swizzle — the B-fragment loads of
+// Q K^T and the ldmatrix.trans of V are bank-conflict-free without padding.  (A first version issued one 1 KB cp.async.bulk
+// per row: the load pipe alone then ran at 3.0 TB/s, 2880 copies per SM per launch at ~95 clk each.)  K and V halves have
+// their own full / empty mbarriers: K is released right after Q K^T so the K rows of the stream after next are already in
+// flight during softmax and P V.  16 head warps = (head, 16-row query tile): per-warp instruction latency, not issue rate,
+// bounds the math (ncu: 34 % issue-active with 8 warps).  Same fragments and summation order as attention_mma_kernel.
 // ------------------------------------------------------------------------------------------
 template <int ROWS> struct AsCfg {
   static constexpr int MT = (ROWS + 15) / 16;                 // 16-row query tiles per stream (20 rows -> 2, 12 rows -> 1)
-  static constexpr int HEAD_WARPS = AM_WARPS * MT;             // one warp per (head, query tile): the kernel is bound by per-warp
-  static constexpr int THREADS = (HEAD_WARPS + 1) * 32;        // instruction latency (ncu: 34 % issue-active with 8 warps), not by HBM
+  static constexpr int HEAD_WARPS = AM_WARPS * MT;
+  static constexpr int THREADS = (HEAD_WARPS + 1) * 32;
 };
+constexpr int AS_RC_ROWS = 4;                                  // right-context rows per chunk (context_size 16 / stride 4)
+constexpr int AS_RING_ROWS = 48;                               // upper bound of left context + segment rows staged per stream
+constexpr int AS_RC_OFF = AS_RING_ROWS * 1024;                 // right-context block [head][4 rows][128 B] behind the ring blocks
+constexpr int AS_HALF_BYTES = AS_RC_OFF + AS_RC_ROWS * 1024;   // K (or V) half of a buffer: 52 KB
 
 __device__ __forceinline__ void as_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -441,10 +448,19 @@ __device__ __forceinline__ void as_mbar_wait(uint32_t bar, uint32_t parity) {   
     }
   }
 }
-__device__ __forceinline__ void as_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void as_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// byte offset, inside a K (or V) half buffer, of the 128-byte row of (key, head); the first n_ring keys live in SEG-row blocks
+// ([block][head][SEG rows][128 B], one TMA box each), the right-context keys in the block behind them
+template <int SEG>
+__device__ __forceinline__ uint32_t as_row_off(int key, int n_ring, int head) {
+  return key < n_ring ? (uint32_t)((key / SEG) * (SEG * 1024) + head * (SEG * 128) + (key % SEG) * 128)
+                      : (uint32_t)(AS_RC_OFF + head * (AS_RC_ROWS * 128) + (key - n_ring) * 128);
+}
+// 128B swizzle: the 16-byte chunk index is XORed with bits [7,10) of the (1024-aligned) shared-memory offset
+__device__ __forceinline__ uint32_t as_swz(uint32_t row_off, int chunk) { return row_off + ((uint32_t)(chunk ^ ((row_off >> 7) & 7)) << 4); }
 
 // A fragments of one 16-row query tile (rows row_base + g, + 8), zero for rows >= ROWS
 template <int ROWS>
@@ -460,61 +476,62 @@ __device__ __forceinline__ void as_load_q(uint32_t (&qa)[4][4], const bf16* qb, 
 }
 
 template <int ROWS>
-__global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kernel(AttnParams<bf16> P, int n_streams) {
-  constexpr int HEAD_WARPS = AsCfg<ROWS>::HEAD_WARPS, THREADS = AsCfg<ROWS>::THREADS;
-  extern __shared__ __align__(16) uint8_t am_smem[];
-  __shared__ __align__(8) unsigned long long as_bars[6];       // kfull[2] | vfull[2] | empty[2]
+__global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1)
+attention_stream_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmRC, AttnParams<bf16> P, int n_streams) {
+  constexpr int HEAD_WARPS = AsCfg<ROWS>::HEAD_WARPS;
+  constexpr int SEG = ROWS - AS_RC_ROWS;                        // segment rows per chunk = rows per ring block (16, or 8 in low-latency mode)
+  constexpr int BLOCK_BYTES = SEG * 1024;
+  extern __shared__ uint8_t as_smem_raw[];
+  __shared__ __align__(8) unsigned long long as_bars[8];       // kfull[2] | vfull[2] | kempty[2] | vempty[2]
   __shared__ int as_meta[2];                                   // per buffer: valid left-context rows of its stream
+  __shared__ __align__(16) uint8_t s_zero[128];                // a zero row for keys >= n_keys in P V
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
-  const int kmax = P.left + P.seg_rows + P.rc_rows;
-  const size_t buf_bytes = (size_t)2 * kmax * AM_ROWB;          // K rows then V rows
-  uint8_t* s_zero = am_smem + 2 * buf_bytes;
+  const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(as_smem_raw) + 1023u) & ~1023u;    // swizzled TMA boxes need 1024 B alignment
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(as_bars);
   auto kfull = [&](int b) { return bar0 + 8u * b; };
   auto vfull = [&](int b) { return bar0 + 16u + 8u * b; };
-  auto empty = [&](int b) { return bar0 + 32u + 8u * b; };
+  auto kempty = [&](int b) { return bar0 + 32u + 8u * b; };
+  auto vempty = [&](int b) { return bar0 + 48u + 8u * b; };
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { as_mbar_init(kfull(b), 1); as_mbar_init(vfull(b), 1); as_mbar_init(empty(b), HEAD_WARPS); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRC) : "memory");
+    for (int b = 0; b < 2; ++b) {
+      as_mbar_init(kfull(b), 1); as_mbar_init(vfull(b), 1); as_mbar_init(kempty(b), HEAD_WARPS); as_mbar_init(vempty(b), HEAD_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < AM_ROWB / 16; i += THREADS) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 32) reinterpret_cast<uint32_t*>(s_zero)[tid] = 0u;
   __syncthreads();
   pdl_launch_dependents();
   pdl_wait();
 
   if (warp == HEAD_WARPS) {
-    // ===================== producer warp: bulk copies of whole K / V rows =====================
-    int it = 0;
-    for (int b = blockIdx.x; b < n_streams; b += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t par = (uint32_t)((it >> 1) & 1);
-      const int slot = P.slots[b];
-      const int pl = P.past_len[slot];
-      const int lv = pl < P.left ? pl : P.left;
-      const int n_keys = lv + P.seg_rows + P.rc_rows;
-      as_mbar_wait(empty(buf), par ^ 1u);                       // the head warps are done with this buffer (first pass: free)
-      if (lane == 0) {
-        as_meta[buf] = lv;
-        as_mbar_expect_tx(kfull(buf), (uint32_t)n_keys * (uint32_t)(P.d * 2));
-        as_mbar_expect_tx(vfull(buf), (uint32_t)n_keys * (uint32_t)(P.d * 2));
-      }
-      __syncwarp();
-      const bf16* cache_slot = P.cache_layer + (size_t)slot * P.slot_stride;
-      const bf16* rc_b = P.rc + (size_t)b * 2 * P.rc_rows * P.d;
-      uint8_t* base = am_smem + (size_t)buf * buf_bytes;
-      for (int i = lane; i < 2 * n_keys; i += 32) {             // K rows first: the head warps start on them while V is in flight
-        const int which = i >= n_keys;
-        const int r = i - which * n_keys;
-        const bf16* src;
-        if (r < lv + P.seg_rows) {
-          const int rr = (pl - lv + r + P.ring) % P.ring;
-          src = cache_slot + ((size_t)which * P.ring + rr) * P.d;
-        } else {
-          src = rc_b + ((size_t)which * P.rc_rows + (r - lv - P.seg_rows)) * P.d;
+    // ===================== producer: one lane, <= 8 TMA ops per stream =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int b = blockIdx.x; b < n_streams; b += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t par = (uint32_t)((it >> 1) & 1);
+        const int slot = P.slots[b];
+        const int pl = P.past_len[slot];
+        const int lv = pl < P.left ? pl : P.left;
+        const int nb = lv / SEG + 1;                              // ring blocks holding [valid left context | segment]
+        const int first_blk = (pl - lv) / SEG;
+        const int ring_blocks = P.ring / SEG;
+        const uint32_t bytes = (uint32_t)(nb * BLOCK_BYTES + AS_RC_ROWS * 1024);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {                 // K first: the head warps start on it while V is in flight
+          as_mbar_wait(which ? vempty(buf) : kempty(buf), par ^ 1u);   // the head warps are done with this half (first pass: free)
+          if (!which) as_meta[buf] = lv;
+          const uint32_t full = which ? vfull(buf) : kfull(buf);
+          as_mbar_expect_tx(full, bytes);
+          const uint32_t dst = smem0 + (uint32_t)((buf * 2 + which) * AS_HALF_BYTES);
+          const long long row0 = P.cache_row0 + (long long)slot * P.slot_rows + (long long)which * P.ring;
+          for (int j = 0; j < nb; ++j)
+            as_tma_3d(dst + (uint32_t)(j * BLOCK_BYTES), &tmKV, 0, (int)(row0 + ((first_blk + j) % ring_blocks) * SEG), 0, full);
+          as_tma_3d(dst + (uint32_t)AS_RC_OFF, &tmRC, 0, (b * 2 + which) * AS_RC_ROWS, 0, full);
         }
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + ((size_t)which * kmax + r) * AM_ROWB);
-        as_bulk_row(dst, src, (uint32_t)(P.d * 2), which ? vfull(buf) : kfull(buf));
       }
     }
     return;
@@ -526,15 +543,17 @@ __global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kern
   const bool second_half = row_base + 8 < ROWS;                 // rows row_base + 8 + g exist at all (warp-uniform)
   uint32_t qa[4][4];
   if (blockIdx.x < n_streams) as_load_q<ROWS>(qa, P.q + (size_t)blockIdx.x * ROWS * P.d + head * AT_DH, P.d, row_base, g, tig);
+  const uint32_t zero_addr = (uint32_t)__cvta_generic_to_shared(s_zero);
   int it = 0;
   for (int b = blockIdx.x; b < n_streams; b += gridDim.x, ++it) {
     const int buf = it & 1;
     const uint32_t par = (uint32_t)((it >> 1) & 1);
-    uint8_t* s_k = am_smem + (size_t)buf * buf_bytes;
-    uint8_t* s_v = s_k + (size_t)kmax * AM_ROWB;
+    const uint32_t s_k = smem0 + (uint32_t)(buf * 2 * AS_HALF_BYTES);
+    const uint32_t s_v = s_k + (uint32_t)AS_HALF_BYTES;
     as_mbar_wait(kfull(buf), par);
     const int lv = as_meta[buf];
-    const int n_keys = lv + P.seg_rows + P.rc_rows;
+    const int n_ring = lv + SEG;
+    const int n_keys = n_ring + AS_RC_ROWS;
 
     // ---- S = Q K^T
     float sc[8][4];
@@ -547,15 +566,18 @@ __global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kern
       if (nt * 8 < n_keys) {                                     // warp-uniform
         int key = nt * 8 + g;
         key = key < n_keys ? key : n_keys - 1;                    // clamp: garbage columns are masked below
-        const uint8_t* kr = s_k + (size_t)key * AM_ROWB + head * (AT_DH * 2) + tig * 4;
+        const uint32_t ro = as_row_off<SEG>(key, n_ring, head);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
+          uint32_t b0, b1;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(s_k + as_swz(ro, 2 * ks) + tig * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(s_k + as_swz(ro, 2 * ks + 1) + tig * 4));
           mma_bf16_16816(sc[nt], qa[ks], b0, b1);
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) as_mbar_arrive(kempty(buf));                 // this warp no longer reads the K half
     // the Q fragments are dead now: fetch the next stream's while softmax and P V run
     if (b + (int)gridDim.x < n_streams) as_load_q<ROWS>(qa, P.q + (size_t)(b + gridDim.x) * ROWS * P.d + head * AT_DH, P.d, row_base, g, tig);
 
@@ -615,13 +637,13 @@ __global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kern
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       if (kk * 16 < n_keys) {
+        // lane -> (matrix id = lane/8, row in matrix = lane%8): matrices 0,1 = keys +0..7, +8..15 at dims dn; 2,3 = same keys at dims dn+1
         const int mi = lane >> 3, ri = lane & 7;
         const int key = kk * 16 + (mi & 1) * 8 + ri;
-        const uint8_t* row = s_v + (size_t)key * AM_ROWB;
+        const uint32_t ro = as_row_off<SEG>(key < n_keys ? key : 0, n_ring, head);
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
-          const uint8_t* src = key < n_keys ? row + head * (AT_DH * 2) + (dp * 2 + (mi >> 1)) * 16 : s_zero;
-          const uint32_t addr = (uint32_t)__cvta_generic_to_shared(src);
+          const uint32_t addr = key < n_keys ? s_v + as_swz(ro, dp * 2 + (mi >> 1)) : zero_addr;
           uint32_t v0, v1, v2, v3;
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
           mma_bf16_16816(oc[2 * dp], pa[kk], v0, v1);
@@ -630,7 +652,7 @@ __global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kern
       }
     }
     __syncwarp();
-    if (lane == 0) as_mbar_arrive(empty(buf));                  // this warp no longer reads the buffer
+    if (lane == 0) as_mbar_arrive(vempty(buf));                 // this warp no longer reads the V half
     // ---- write the A operand of out_proj
 #pragma unroll
     for (int hr = 0; hr < 2; ++hr) {
@@ -647,15 +669,14 @@ __global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1) attention_stream_kern
 
 template <int ROWS>
 int attention_stream_launch(const AttnParams<bf16>& P, int n_streams, int num_sms, cudaStream_t st) {
-  const int kmax = P.left + P.seg_rows + P.rc_rows;
-  const size_t smem = (size_t)(4 * kmax + 1) * AM_ROWB;
-  static size_t attr = 0;
-  if (smem > attr) {
+  const size_t smem = (size_t)4 * AS_HALF_BYTES + 1024;
+  static bool attr = false;
+  if (!attr) {
     ASR_CUDA_OK(cudaFuncSetAttribute(attention_stream_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr = true;
   }
   const int grid = n_streams < num_sms ? n_streams : num_sms;
-  ASR_CUDA_OK(launch_pdl(attention_stream_kernel<ROWS>, dim3(grid), dim3(AsCfg<ROWS>::THREADS), smem, st, P, n_streams));
+  ASR_CUDA_OK(launch_pdl(attention_stream_kernel<ROWS>, dim3(grid), dim3(AsCfg<ROWS>::THREADS), smem, st, *P.h_tm_cache, *P.h_tm_rc, P, n_streams));
   return 0;
 }
 
@@ -812,7 +833,9 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
       const char* sm_env = getenv("ASR_B200_ATTN_STREAM_MIN");       // read per launch so a test can flip it inside one process
       const int stream_min = sm_env ? atoi(sm_env) : 148;       // measured on B200: wins from 256 streams per step on (1.98 vs 2.00 ms)
       static const int num_sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
-      if (n_streams >= stream_min) {                   // persistent, double-buffered streaming kernel for large batches
+      const bool tma_ok = P.h_tm_cache && P.h_tm_rc && P.rc_rows == AS_RC_ROWS && P.rows == P.seg_rows + P.rc_rows && P.ring <= AS_RING_ROWS &&
+                          P.ring % P.seg_rows == 0 && P.left % P.seg_rows == 0 && (P.seg_rows == 16 || P.seg_rows == 8);
+      if (n_streams >= stream_min && tma_ok) {         // persistent, double-buffered streaming kernel for large batches
         if (P.rows == 20) return attention_stream_launch<20>(P, n_streams, num_sms, st);
         if (P.rows == 12) return attention_stream_launch<12>(P, n_streams, num_sms, st);
       }

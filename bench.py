@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py — audio-seconds/second of the per-chunk hot path on B200 (contract: see DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload streams256|streams4096|streams10240|fbank1024]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ragged4096|streams256|streams1024|streams4096|streams10240|lowlat4096|fbank1024]
   python bench.py --impl reference ...      # the reference's CPU implementation (torch/torchaudio port) on the host cores
 
 A step = one pass of the hot path (PCM -> fbank -> 20-layer Emformer chunk forward with K/V rings -> CTC log-softmax ->
-greedy) over one batch of `streams` concurrent 640 ms stream-chunks per GPU.  `value` times K steps with the PCM batch
-already resident in HBM (CUDA events on the engine's own stream); `e2e` times K calls of the public step API with host
-int16 buffers, H2D of the PCM and D2H of the token ids inside the timed region.  N > 1: one process per GPU (torchrun),
-sessions partitioned per GPU, no data-path collective (weak scaling), time = max over ranks.
+greedy / prefix beam) over one batch of `streams` concurrent 640 ms stream-chunks per GPU.  `value` times K steps with the PCM
+batch already resident in HBM (CUDA events on the engine's own stream); `e2e` times the public API with host int16 buffers, H2D of
+the PCM and D2H of the token ids inside the timed region.  Default workload = BASELINE configs[3] (the largest single-GPU
+configuration): 4096 sessions at mixed progress driven by SessionScheduler (VAD gate, pinned gather, two ticks in flight, endpoint
+rules), prefix beam 10.  N > 1: one process per GPU (torchrun), sessions partitioned per GPU, no data-path collective (weak
+scaling), time = max over ranks.
 """
 from __future__ import annotations
 
@@ -304,7 +306,8 @@ def run_ours(args):
         # configs[3]: prefix beam 10 on every step, sessions at mixed progress, a trickle of endpoints (1 %/s per stream)
         eng.set_beam(10, 8)
         lat_passes = min(args.steps, 8)
-        passes = 2 + lat_passes + 2 + args.steps + 1
+        e2e_steps = min(args.steps, 24)                        # bounded host memory: every pass pre-loads 84 MB of PCM into the rings
+        passes = 2 + lat_passes + 2 + e2e_steps + 1
         pool = synth_pcm(32, cfg.buffer_length + passes * cfg.segment_length + 4096, first_id=rank * 32)
         wl = RaggedWorkload(eng, cfg, streams, passes, seed=99 + rank, pool=pool)
         slots = wl.sch.slot.copy()
@@ -380,18 +383,18 @@ def run_ours(args):
         barrier()
         c0 = (wl.run_chunks, wl.skipped_chunks, wl.endpoints)
         t0 = time.perf_counter()
-        wl.run_pipelined(args.steps, streams // 2)
+        wl.run_pipelined(e2e_steps, streams // 2)
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(time.perf_counter() - t0) * (args.steps / e2e_steps)      # normalised to K steps (e2e_steps of them were run)
         run_c, skip_c, end_c = wl.run_chunks - c0[0], wl.skipped_chunks - c0[1], wl.endpoints - c0[2]
         per_chunk_in = cfg.chunk_length * 2 + 4
         per_chunk_out = cfg.seg_rows * 4 * 2 + 3 * 4 + 4 * 256 + 8
-        h2d, d2h = run_c * per_chunk_in // args.steps, run_c * per_chunk_out // args.steps
-        extra["ragged"] = {"sessions": streams, "ticks_in_flight": 2, "max_rows_per_tick": streams // 2,
-                           "decoded_chunks_per_pass": run_c / args.steps, "vad_skipped_chunks_per_pass": skip_c / args.steps,
-                           "endpoints_per_pass": end_c / args.steps,
+        h2d, d2h = run_c * per_chunk_in // e2e_steps, run_c * per_chunk_out // e2e_steps
+        extra["ragged"] = {"sessions": streams, "ticks_in_flight": 2, "max_rows_per_tick": streams // 2, "e2e_steps_run": e2e_steps,
+                           "decoded_chunks_per_pass": run_c / e2e_steps, "vad_skipped_chunks_per_pass": skip_c / e2e_steps,
+                           "endpoints_per_pass": end_c / e2e_steps,
                            "e2e_counts": "audio-seconds of the chunks actually decoded (VAD-skipped chunks are excluded from e2e.value)"}
-        e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / args.steps
+        e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / e2e_steps
     else:
         for _ in range(2):                                   # fill both pinned staging buffers once (the receive path writes here)
             view = eng.pinned_pcm(np.int16)
@@ -465,7 +468,8 @@ def run_ours(args):
             ach = gemm_flops[dom] / (t / 1e3) / 1e12
             all_gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
             all_gemm_flop = streams * (flop_sc - 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
-            roof = {"kernel": f"gemm_tc_kernel ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            fused = streams >= 160 and dom in ("gemm_out_proj", "gemm_ffn2") and not os.environ.get("ASR_B200_NO_FUSED_LN")
+            roof = {"kernel": f"{'gemm_ln_kernel' if fused else 'gemm_tc_kernel'} ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(("streams4096" if ragged else args.workload) if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,
                     "all_gemms": {"ms_per_step": all_gemm_ms, "tflops": all_gemm_flop / (all_gemm_ms / 1e3) / 1e12}}
@@ -513,10 +517,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="streams256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ragged4096", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--ref-streams", type=int, default=16, help="streams per step in the CPU reference sample")

@@ -450,3 +450,17 @@ def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch
                 got.append(e.step(sl, pcm[t], want_logprobs=True).logprobs)
             outs.append(np.stack(got))
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_streaming_attention_low_latency_geometry(packed_weights, golden, meta, monkeypatch):
+    """Low-latency geometry (8 segment rows, 5-block ring) through the streaming attention kernel: 8-row TMA boxes."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    monkeypatch.setenv("ASR_B200_ATTN_STREAM_MIN", "1")
+    case, mc = golden("lowlat_noise"), meta["cases"]["lowlat_noise"]
+    with Engine(model_cfg(PRECISION_FAST, True), packed_weights) as e:
+        em, _, _ = _run_case(e, case, mc, O.LOW_LATENCY)
+    monkeypatch.setenv("ASR_B200_ATTN_STREAM_MIN", "100000")
+    with Engine(model_cfg(PRECISION_FAST, True), packed_weights) as e:
+        em_old, _, _ = _run_case(e, case, mc, O.LOW_LATENCY)
+    assert np.abs(em - case["emission"]).max() < FAST_TOL
+    assert np.array_equal(em, em_old)

@@ -69,6 +69,11 @@ SIGNATURES = {
     "asr_debug_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "asr_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int]),
+    "asr_convmod_weights_count": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "asr_convmod_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "asr_convmod_destroy": (C.c_int, [C.c_void_p]),
+    "asr_convmod_reset": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "asr_convmod_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "asr_debug_gemm_ln": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.POINTER(C.c_float), C.c_int]),
     "asr_debug_gemm_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int]),

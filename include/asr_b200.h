@@ -179,6 +179,18 @@ ASR_API int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_
 
 /* Mean milliseconds per launch of the tcgen05 GEMM on operands resident in HBM (microbenchmark; bn = 512 selects the CTA-pair
  * kernel).  epi_kind: 0 plain fp32 store, 1 bias + fp32 residual, 2 bias + GELU -> bf16. */
+/* ---- Streaming convolution module with per-session cache (csrc/convmod.cu): streaming form of ConvolutionBlock
+ * (lightspeech/layers/block.py:129-171: pre_norm -> pointwise_conv1 -> SiLU -> depthwise_conv(k) -> BatchNorm1d(eval) -> SiLU ->
+ * pointwise_conv2).  Output = the reference block's output on the whole sequence, delayed by (kernel-1)/2 frames.  Sessions are
+ * caller-numbered slots in [0, max_sessions).  weights: fp32 blob in the order documented at asr_convmod_create in convmod.cu. */
+typedef struct AsrConvModule AsrConvModule;
+ASR_API int asr_convmod_weights_count(int32_t d_model, int32_t kernel, uint64_t* n_floats);
+ASR_API int asr_convmod_create(int32_t d_model, int32_t kernel, int32_t rows_per_chunk, int32_t max_sessions, int32_t max_batch, int32_t precision,
+                               const float* weights, uint64_t n_floats, int32_t device, AsrConvModule** out);
+ASR_API int asr_convmod_destroy(AsrConvModule* m);
+ASR_API int asr_convmod_reset(AsrConvModule* m, int32_t n, const int32_t* slots);
+ASR_API int asr_convmod_step(AsrConvModule* m, int32_t n, const int32_t* slots, const float* x, float* y);
+
 /* Diagnostic: the GEMM (N = 512) with residual add + LayerNorm(s) fused into the epilogue (csrc/gemm_ln.cu) on host operands. */
 ASR_API int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res,
                               const float* g1, const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows,

@@ -92,6 +92,7 @@ struct AsrEngine {
   int device = 0, num_sms = 148;
   int simt_gemm = 0;
   int no_pair = 0;
+  int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
   int fused_ln = 1;             // LayerNorm fused into the out_proj / FFN2 epilogues (gemm_ln.cu); ASR_B200_NO_FUSED_LN=1 -> separate passes
   int fused_ln_min_streams = 160;   // below this batch the separate LN passes win (measured: 64 streams 1.30 vs 1.59 ms, 256: 2.00 vs 2.00, 1024: 5.99 vs 5.77)
   int pdl_max_streams = 1536;   // programmatic dependent launch below this batch size (see common.cuh)
@@ -345,7 +346,9 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
 int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const LnEpilogue& ep) {
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
   ProfScope ps(e, cat);
-  return gemm_ln(a.tm, w.tm[2], p, ep, e->num_sms, e->stream);
+  // CTA pairs when the mainloop is long enough to be L2-bound (FFN2, K = 2048) and there are enough 256-row tiles to fill the clusters
+  const bool pair = !e->no_pair_ln && w.K * (e->geo.split ? 3 : 1) >= 1024 && (M + 255) / 256 >= 34;
+  return gemm_ln(a.tm, w.tm[2], w.tm[1], p, ep, pair, e->num_sms, e->stream);
 }
 
 // ------------------------------------------------------------------------------------------ the per-step kernel chain
@@ -653,6 +656,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   e->no_pair = np_ && np_[0] == '1';
   if (const char* nf = getenv("ASR_B200_NO_FUSED_LN")) e->fused_ln = !(nf[0] == '1');
   if (e->simt_gemm || cfg->d_model != 512) e->fused_ln = 0;
+  if (const char* pl = getenv("ASR_B200_NO_PAIR_LN")) e->no_pair_ln = pl[0] == '1';
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
   if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
   int rc = -1;
@@ -1190,13 +1194,13 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
  * output converted back to fp32, [M, 512] (or [M / compact_rows * compact_seg, 512] when compact_rows > 0). */
 int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res, const float* g1,
                       const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows, int32_t compact_seg,
-                      float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int device) {
+                      float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int32_t pair, int device) {
   if (!A || !W || !bias || !res || !g1 || !b1 || !out_f32 || !out_op_f32 || M <= 0 || K <= 0 || K % 64) { set_error("asr_debug_gemm_ln: bad arguments"); return -1; }
   ASR_CUDA_OK(cudaSetDevice(device));
   cudaDeviceProp prop;
   ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   const int N = 512, ld = split ? 2 * K : K, lo = split ? K : 0, old_ = split ? 2 * N : N, olo = split ? N : 0;
-  const int Mp = (int)round_up(M, 128);
+  const int Mp = (int)round_up(M, 256);
   const int Mo = compact_rows > 0 ? M / compact_rows * compact_seg : M;
   DevBuf dA32, dW32, dA, dW, dv, dres, dout, dop;
   std::vector<bf16> hop;
@@ -1214,15 +1218,15 @@ int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const
     cudaMemset(dA.p, 0, dA.bytes); cudaMemset(dop.p, 0, dop.bytes);
     if (convert_weight(dA32.as<float>(), dA.as<bf16>(), M, K, ld, lo, 0) || convert_weight(dW32.as<float>(), dW.as<bf16>(), N, K, ld, lo, 0)) break;
     const GemmProblem p = make_problem(M, N, K, split);
-    CUtensorMap ta, tb;
-    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dW.p, ld, N, ld, 256)) break;
+    CUtensorMap ta, tb, tb128;
+    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dW.p, ld, N, ld, 256) || make_tmap_bf16_2d(&tb128, dW.p, ld, N, ld, 128)) break;
     LnEpilogue ep{dv.as<float>(), dres.as<float>(), dv.as<float>() + N, dv.as<float>() + 2 * N, g2 ? dv.as<float>() + 3 * N : nullptr,
                   b2 ? dv.as<float>() + 4 * N : nullptr, dout.as<float>(), dop.as<bf16>(), old_, olo, f32_normed, compact_rows, compact_seg};
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int n_it = iters > 0 ? iters : 1;
     for (int it = 0; it < n_it + 1 && ok; ++it) {
       if (it == 1) cudaEventRecord(e0, 0);
-      ok = !gemm_ln(ta, tb, p, ep, prop.multiProcessorCount, 0);
+      ok = !gemm_ln(ta, tb, tb128, p, ep, pair != 0, prop.multiProcessorCount, 0);
     }
     if (!ok) break;
     cudaEventRecord(e1, 0);

@@ -31,8 +31,9 @@ struct LnEpilogue {
   int f32_normed;
   int compact_rows, compact_seg;
 };
-// tmB256: tensor map of the [512, ld] weight with a 256-row box.
-int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st);
+// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- / 128-row boxes; pair selects the cta_group::2 shape (cluster of 4).
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, bool pair,
+            int num_sms, cudaStream_t st);
 
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t rows, uint32_t n_heads, uint32_t box_rows);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows);

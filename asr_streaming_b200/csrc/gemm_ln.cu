@@ -28,22 +28,26 @@ using namespace tc;
 
 constexpr int LN_N = 512;
 constexpr int LBN = 256;                                   // columns per CTA
-constexpr int L_STAGES = 3;
-constexpr int L_STAGE_BYTES = (BM + LBN) * BK * 2;         // 48 KB
+// Two shapes of the same kernel:
+//   PAIR = false  cluster of 2: CTA r = columns [256 r, +256) of the same 128 rows; 1-CTA MMA 128 x 256; stage = A 16 KB + B 32 KB
+//   PAIR = true   cluster of 4: ranks (2n + m) -> column half n, row half m of a 256-row tile; the two CTAs with equal n form a
+//                 cta_group::2 pair (MMA 256 x 256, each CTA stages its own 128 A rows and HALF of the pair's B rows: 32 KB per
+//                 stage, 64 instead of 96 B/clk/SM of L2 ingest at full tensor rate — the 1-CTA shape is L2-bound at K = 2048).
+//                 Statistics are exchanged between the CTAs with equal m (rank ^ 2).  148 SMs hold 34 such clusters (136 SMs).
+template <bool PAIR> struct LnCfg {
+  static constexpr int CLUSTER = PAIR ? 4 : 2;
+  static constexpr int STAGES = PAIR ? 4 : 3;
+  static constexpr int STAGE_BYTES = PAIR ? (BM + LBN / 2) * BK * 2 : (BM + LBN) * BK * 2;     // 32 KB / 48 KB
+};
 constexpr int L_EW = 16;                                   // epilogue warps: 4 per TMEM lane quarter, 2 chunks of 32 columns each
 constexpr int L_THREADS = 64 + 32 * L_EW;
 constexpr int L_LD = 36;                                   // fp32 row stride of the per-warp transpose tile (conflict-free both ways)
 constexpr int L_XPOSE_FLOATS = 32 * L_LD;
 constexpr int L_XPOSE_BYTES = L_EW * L_XPOSE_FLOATS * 4;
 constexpr int L_STATS_BYTES = 4 * BM * 8 + 2 * BM * 8;         // local[warp in quarter][row] + remote[set][row], float2 (sum, M2)
-constexpr int L_SMEM_BYTES = L_STAGES * L_STAGE_BYTES + L_XPOSE_BYTES + L_STATS_BYTES + 1024 + 256;
-static_assert(L_SMEM_BYTES <= 232448, "gemm_ln: shared memory budget");
+template <bool PAIR> constexpr int ln_smem_bytes() { return LnCfg<PAIR>::STAGES * LnCfg<PAIR>::STAGE_BYTES + L_XPOSE_BYTES + L_STATS_BYTES + 1024 + 256; }
+static_assert(ln_smem_bytes<false>() <= 232448 && ln_smem_bytes<true>() <= 232448, "gemm_ln: shared memory budget");
 
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
@@ -91,7 +95,7 @@ struct XchgCtx {
   uint32_t peer_bar0;      // shared::cluster address of the peer's xbar[0][quarter]
   int named_bar;           // 1 + quarter
   int wq;
-  uint32_t rank;
+  uint32_t rank;          // 0 / 1: which column half this CTA owns (CTA 0's partials are summed first in both CTAs)
 };
 
 // All 128 threads of a lane quarter (4 warps) in both CTAs call this once per round with their partial: sum over their 64 values
@@ -135,8 +139,10 @@ __device__ __forceinline__ RowStats exchange_row_stats(float sum, float m2, cons
   return r;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L_THREADS, 1)
+template <bool PAIR>
+__global__ void __launch_bounds__(L_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, LnEpilogue ep) {
+  constexpr int L_STAGES = LnCfg<PAIR>::STAGES, L_STAGE_BYTES = LnCfg<PAIR>::STAGE_BYTES, CLUSTER = LnCfg<PAIR>::CLUSTER;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xpose_base = smem_base + L_STAGES * L_STAGE_BYTES;
@@ -151,9 +157,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_rank();
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t nrank = PAIR ? rank >> 1 : rank;              // column half
+  const uint32_t mrank = PAIR ? rank & 1u : 0u;                // row half inside the pair's 256-row tile
+  const uint32_t xpeer = PAIR ? rank ^ 2u : rank ^ 1u;         // the CTA holding the other half of my rows
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
+  const int cluster_id = blockIdx.x / CLUSTER, n_clusters = gridDim.x / CLUSTER;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int kb_per_pass = p.K / BK;
   const int total_kb = kb_per_pass * p.passes;
 
@@ -161,16 +171,21 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < L_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), L_EW); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), PAIR ? 2 * L_EW : L_EW); }
     for (int q = 0; q < 8; ++q) mbar_init(xq_bar(q >> 2, q & 3), 32);       // the 32 lanes of the quarter's warp 0 arm 8 bytes each
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  cluster_barrier();                                       // the peer's barriers exist before any remote arrive
+  cluster_sync_all();                                       // the peer's barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
   pdl_launch_dependents();
@@ -181,45 +196,64 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        const int row_a = m_blk * TILE_M + (int)mrank * BM;
+        const int row_b = (int)nrank * LBN + (PAIR ? (int)mrank * (LBN / 2) : 0);
         for (int ps = 0; ps < p.passes; ++ps) {
           for (int kb = 0; kb < kb_per_pass; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
             const uint32_t sb = sa + BM * BK * 2;
-            mbar_expect_tx(full_bar(stage), (uint32_t)L_STAGE_BYTES);
-            tma_load_2d(sa, &tmA, p.a_koff[ps] + kb * BK, m_blk * BM, full_bar(stage));
-            tma_load_2d(sb, &tmB, p.b_koff[ps] + kb * BK, (int)rank * LBN, full_bar(stage));
+            if (PAIR) {
+              const uint32_t lbar = full_bar(stage) & kPeerBitMask;            // the pair leader's barrier collects both CTAs' bytes
+              if (mrank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)L_STAGE_BYTES);
+              tma_load_2d_pair(sa, &tmA, p.a_koff[ps] + kb * BK, row_a, lbar);
+              tma_load_2d_pair(sb, &tmB, p.b_koff[ps] + kb * BK, row_b, lbar);
+            } else {
+              mbar_expect_tx(full_bar(stage), (uint32_t)L_STAGE_BYTES);
+              tma_load_2d(sa, &tmA, p.a_koff[ps] + kb * BK, row_a, full_bar(stage));
+              tma_load_2d(sb, &tmB, p.b_koff[ps] + kb * BK, row_b, full_bar(stage));
+            }
             if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(LBN);
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * LBN);
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+    // ===================== MMA issuer (PAIR: the leader CTA of each pair only) =====================
+    constexpr uint32_t idesc = PAIR ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LBN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24)) : make_idesc(LBN);
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * nrank));
+    if (!PAIR || mrank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + BM * BK * 2);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * LBN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + BM * BK * 2);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));
-          if (kb == total_kb - 1) umma_commit(tfull_bar(acc));
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (PAIR) umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (PAIR) {
+              umma_commit_pair(empty_bar(stage), pair_mask);
+              if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc), pair_mask);
+            } else {
+              umma_commit(empty_bar(stage));
+              if (kb == total_kb - 1) umma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ===================== epilogue =====================
@@ -234,16 +268,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       X.local_row = stats_base + row_off;
       X.local_part = X.local_row + (uint32_t)(wq * BM) * 8u;
       X.remote_set0 = stats_base + 4u * BM * 8u + row_off;
-      X.peer_remote0 = map_to_cta(X.remote_set0, rank ^ 1u);
+      X.peer_remote0 = map_to_cta(X.remote_set0, xpeer);
       X.bar0 = xq_bar(0, quarter);
-      X.peer_bar0 = map_to_cta(X.bar0, rank ^ 1u);
-      X.named_bar = 1 + quarter; X.wq = wq; X.rank = rank;
+      X.peer_bar0 = map_to_cta(X.bar0, xpeer);
+      X.named_bar = 1 + quarter; X.wq = wq; X.rank = nrank;
     }
-    const int col_cta = (int)rank * LBN;
+    const int col_cta = (int)nrank * LBN;
     int acc = 0; uint32_t acc_phase = 0;
     int round = 0;
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
-      const int row0 = m_blk * BM + quarter * 32;
+      const int row0 = m_blk * TILE_M + (int)mrank * BM + quarter * 32;
       const int my_row = row0 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * LBN);
       if (my_row < p.M) {                                    // residual lines of my row -> L2 while the MMAs of the tile run
@@ -367,34 +401,62 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (!PAIR || mrank == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cta(tempty_bar(acc), rank & ~1u);       // the pair leader's MMA warp waits for both CTAs' epilogues
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
-  cluster_barrier();                                       // the peer may still read this CTA's statistics through DSMEM
+  cluster_sync_all();                                       // the peer may still read this CTA's statistics through DSMEM
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
 }  // namespace
 
-int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
+namespace {
+template <bool PAIR>
+int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
+  constexpr int CL = LnCfg<PAIR>::CLUSTER, TILE_M = PAIR ? 2 * BM : BM;
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<PAIR>()));
+    // how many clusters of this shape the device can hold at once (GPC boundaries: 148 SMs hold 74 pairs but only ~34 quads)
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(num_sms / CL * CL); q.blockDim = dim3(L_THREADS); q.dynamicSmemBytes = ln_smem_bytes<PAIR>();
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CL; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+    q.attrs = a; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel<PAIR>, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
+    max_clusters = n < num_sms / CL ? n : num_sms / CL;
+  }
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int clusters = m_tiles < max_clusters ? m_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL * clusters); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = ln_smem_bytes<PAIR>(); cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_kernel<PAIR>, tmA, tmB, p, ep));
+  return 0;
+}
+}  // namespace
+
+// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- and 128-row boxes.  pair = cta_group::2 shape (cluster of 4).
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, bool pair,
+            int num_sms, cudaStream_t st) {
   if (p.M <= 0) return 0;
   if (p.N != LN_N) { set_error("gemm_ln: N = %d, the fused LayerNorm epilogue is built for d_model = %d", p.N, LN_N); return -1; }
   if (p.K % BK != 0) { set_error("gemm_ln: K=%d not a multiple of %d", p.K, BK); return -1; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES));
-    attr_set = true;
-  }
-  const int m_tiles = (p.M + BM - 1) / BM;
-  const int clusters = m_tiles < num_sms / 2 ? m_tiles : num_sms / 2;
-  ASR_CUDA_OK(launch_pdl(gemm_ln_kernel, dim3(2 * clusters), dim3(L_THREADS), L_SMEM_BYTES, st, tmA, tmB256, p, ep));
-  return 0;
+  return pair ? launch_ln<true>(tmA, tmB128, p, ep, num_sms, st) : launch_ln<false>(tmA, tmB256, p, ep, num_sms, st);
 }
 
 }  // namespace asr

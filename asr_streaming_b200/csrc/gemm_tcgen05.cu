@@ -232,39 +232,6 @@ constexpr int P_BN = 256;
 constexpr int P_STAGES = 4;
 constexpr int P_STAGE_BYTES = (BM + P_BN / 2) * BK * 2;            // 32 KB per CTA
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + kStagingBytes + 1024 + 256;
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` (same offset) in both CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {      // arrive on CTA 0's copy of `bar`
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar) : "memory");
-}
-
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi) {
@@ -347,8 +314,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_pair(empty_bar(stage));
-            if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc));
+            umma_commit_pair(empty_bar(stage), 3);
+            if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc), 3);
           }
           __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
@@ -372,7 +339,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cta0(tempty_bar(acc));
+        else mbar_arrive_cta(tempty_bar(acc), 0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

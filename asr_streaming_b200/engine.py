@@ -303,7 +303,7 @@ def debug_gemm(A: np.ndarray, B: np.ndarray, bias: Optional[np.ndarray] = None, 
 
 def debug_gemm_ln(A: np.ndarray, W: np.ndarray, bias: np.ndarray, res: np.ndarray, g1: np.ndarray, b1: np.ndarray,
                   g2: Optional[np.ndarray] = None, b2: Optional[np.ndarray] = None, f32_normed: bool = False, compact_rows: int = 0,
-                  compact_seg: int = 0, split: int = 0, iters: int = 1, device: int = 0):
+                  compact_seg: int = 0, split: int = 0, iters: int = 1, pair: bool = False, device: int = 0):
     """(out_f32 [M,512], out_op [M or compacted,512] as fp32, ms per launch) of the GEMM + residual + LayerNorm kernel (gemm_ln.cu)."""
     lib = _lib.load_library()
     f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
@@ -315,5 +315,5 @@ def debug_gemm_ln(A: np.ndarray, W: np.ndarray, bias: np.ndarray, res: np.ndarra
     ms = C.c_float()
     p = lambda a: None if a is None else a.ctypes.data
     _lib.check(lib, lib.asr_debug_gemm_ln(M, K, split, p(A), p(W), p(bias), p(res), p(g1), p(b1), p(g2), p(b2), int(f32_normed), compact_rows,
-                                          compact_seg, p(out), p(op), iters, C.byref(ms), device), "asr_debug_gemm_ln")
+                                          compact_seg, p(out), p(op), iters, C.byref(ms), int(pair), device), "asr_debug_gemm_ln")
     return out, op, ms.value

@@ -194,7 +194,7 @@ ASR_API int asr_convmod_step(AsrConvModule* m, int32_t n, const int32_t* slots, 
 /* Diagnostic: the GEMM (N = 512) with residual add + LayerNorm(s) fused into the epilogue (csrc/gemm_ln.cu) on host operands. */
 ASR_API int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res,
                               const float* g1, const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows,
-                              int32_t compact_seg, float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int device);
+                              int32_t compact_seg, float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int32_t pair, int device);
 ASR_API int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, int32_t epi_kind, int32_t iters, float* ms_out, int device);
 
 #ifdef __cplusplus

@@ -88,9 +88,12 @@ LN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("pair", [False, True], ids=["cluster2", "pair_cluster4"])
 @pytest.mark.parametrize("M,K,split,mode,offset", LN_CASES)
-def test_gemm_residual_layernorm_epilogue(M, K, split, mode, offset):
-    from asr_streaming_b200.engine import debug_gemm_ln
+def test_gemm_residual_layernorm_epilogue(M, K, split, mode, offset, pair):
+    import functools
+    from asr_streaming_b200 import engine as E
+    debug_gemm_ln = functools.partial(E.debug_gemm_ln, pair=pair)
     rng = np.random.default_rng(M + K + split + ord(mode))
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = (rng.standard_normal((512, K)) / np.sqrt(K)).astype(np.float32)
@@ -128,6 +131,7 @@ def test_gemm_layernorm_rows_do_not_depend_on_their_position():
     res = rng.standard_normal((M, 512)).astype(np.float32)
     g = np.ones(512, np.float32); b = np.zeros(512, np.float32)
     perm = rng.permutation(M)
-    o1, p1, _ = debug_gemm_ln(A, W, bias, res, g, b, g, b)
-    o2, p2, _ = debug_gemm_ln(A[perm], W, bias, res[perm], g, b, g, b)
-    assert np.array_equal(o1[perm], o2) and np.array_equal(p1[perm], p2)
+    for pair in (False, True):
+        o1, p1, _ = debug_gemm_ln(A, W, bias, res, g, b, g, b, pair=pair)
+        o2, p2, _ = debug_gemm_ln(A[perm], W, bias, res[perm], g, b, g, b, pair=pair)
+        assert np.array_equal(o1[perm], o2) and np.array_equal(p1[perm], p2)

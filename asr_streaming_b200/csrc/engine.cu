@@ -68,6 +68,7 @@ struct WeightMat {            // one nn.Linear weight as a tcgen05 B operand
 struct LayerW {
   WeightMat qkv, o, w1, w2;
   const float *bqkv, *bo, *ln_in_g, *ln_in_b, *ln_ff_g, *ln_ff_b, *b1, *b2, *ln_out_g, *ln_out_b;
+  const float* ln_out_consts = nullptr;   // LnEpilogue::y_consts of layer_norm_output (device), see gemm.cuh
 };
 
 struct FbankPlan {
@@ -93,6 +94,8 @@ struct AsrEngine {
   int simt_gemm = 0;
   int no_pair = 0;
   int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
+  int no_fuse2 = 0;             // ASR_B200_NO_LN_FUSE2=1: second LayerNorm statistics by their own TMEM pass
+  int pair_ln_min_tiles = 34;   // 256-row tiles needed before gemm_ln takes the cta_group::2 shape (34 clusters of 4 fit on 148 SMs)
   int fused_ln = 1;             // LayerNorm fused into the out_proj / FFN2 epilogues (gemm_ln.cu); ASR_B200_NO_FUSED_LN=1 -> separate passes
   int fused_ln_min_streams = 160;   // below this batch the separate LN passes win (measured: 64 streams 1.30 vs 1.59 ms, 256: 2.00 vs 2.00, 1024: 5.99 vs 5.77)
   int pdl_max_streams = 1536;   // programmatic dependent launch below this batch size (see common.cuh)
@@ -100,7 +103,7 @@ struct AsrEngine {
   cudaStream_t stream = nullptr;
   std::mutex mu;
 
-  DevBuf w_f32, w_bf16;
+  DevBuf w_f32, w_bf16, ln_consts;
   WeightMat w_in, ctc1, ctc2;
   const float *ctc_b1 = nullptr, *ctc_b2 = nullptr;
   std::vector<LayerW> layers;
@@ -347,7 +350,7 @@ int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
   ProfScope ps(e, cat);
   // CTA pairs when the mainloop is long enough to be L2-bound (FFN2, K = 2048) and there are enough 256-row tiles to fill the clusters
-  const bool pair = !e->no_pair_ln && w.K * (e->geo.split ? 3 : 1) >= 1024 && (M + 255) / 256 >= 34;
+  const bool pair = !e->no_pair_ln && w.K * (e->geo.split ? 3 : 1) >= 1024 && (M + 255) / 256 >= e->pair_ln_min_tiles;
   return gemm_ln(a.tm, w.tm[2], w.tm[1], p, ep, pair, e->num_sms, e->stream);
 }
 
@@ -389,6 +392,7 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
       } else {
         const LayerW& Nx = e->layers[l + 1];
         e2.g2 = Nx.ln_in_g; e2.b2 = Nx.ln_in_b;
+        e2.y_consts = e->no_fuse2 ? nullptr : L.ln_out_consts;
         e2.out_op = e->a_ln.buf.as<bf16>(); e2.op_ld = e->a_ln.ld; e2.op_lo_off = e->a_ln.lo_off;
       }
       if (run_gemm_ln(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
@@ -616,7 +620,7 @@ void destroy_engine(AsrEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
+  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
@@ -657,6 +661,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* nf = getenv("ASR_B200_NO_FUSED_LN")) e->fused_ln = !(nf[0] == '1');
   if (e->simt_gemm || cfg->d_model != 512) e->fused_ln = 0;
   if (const char* pl = getenv("ASR_B200_NO_PAIR_LN")) e->no_pair_ln = pl[0] == '1';
+  if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
+  if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
   if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
   int rc = -1;
@@ -688,6 +694,33 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
       ok = ok && !make_weight(e, &L.w2, take((size_t)d * f), cur, d, f);
       L.b2 = take(d);
       L.ln_out_g = take(d); L.ln_out_b = take(d);
+    }
+    if (ok && d == 512) {
+      // constants that let gemm_ln derive the statistics of LN_out's output in one pass (LnEpilogue::y_consts), from the host blob
+      const int per = (d + 3 * (d / 32) + 2 + 3) / 4 * 4;          // float4 loads: keep every layer's block 16-byte aligned
+      std::vector<float> hc((size_t)g.n_layers * per);
+      for (int l = 0; l < g.n_layers; ++l) {
+        const float* gam = weights + (e->layers[l].ln_out_g - e->w_f32.as<float>());
+        const float* bet = weights + (e->layers[l].ln_out_b - e->w_f32.as<float>());
+        float* c = hc.data() + (size_t)l * per;
+        double mb = 0.0, vb = 0.0;
+        for (int j = 0; j < d; ++j) mb += bet[j];
+        mb /= d;
+        for (int j = 0; j < d; ++j) vb += (bet[j] - mb) * (bet[j] - mb);
+        vb /= d;
+        for (int ch = 0; ch < d / 32; ++ch) {
+          double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+          for (int j = ch * 32; j < ch * 32 + 32; ++j) {
+            const float gc = (float)(gam[j] * (bet[j] - mb));
+            c[j] = gc;
+            g1 += gam[j]; g2 += (double)gam[j] * gam[j]; g3 += gc;
+          }
+          c[d + ch] = (float)g1; c[d + d / 32 + ch] = (float)g2; c[d + 2 * (d / 32) + ch] = (float)g3;
+        }
+        c[d + 3 * (d / 32)] = (float)mb; c[d + 3 * (d / 32) + 1] = (float)vb;
+      }
+      if (upload(&e->ln_consts, hc.data(), hc.size() * 4)) break;
+      for (int l = 0; l < g.n_layers; ++l) e->layers[l].ln_out_consts = e->ln_consts.as<float>() + (size_t)l * per;
     }
     ok = ok && !make_weight(e, &e->ctc1, take((size_t)g.ctc_hidden * d), cur, g.ctc_hidden, d);
     e->ctc_b1 = take(g.ctc_hidden);
@@ -1202,7 +1235,7 @@ int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const
   const int N = 512, ld = split ? 2 * K : K, lo = split ? K : 0, old_ = split ? 2 * N : N, olo = split ? N : 0;
   const int Mp = (int)round_up(M, 256);
   const int Mo = compact_rows > 0 ? M / compact_rows * compact_seg : M;
-  DevBuf dA32, dW32, dA, dW, dv, dres, dout, dop;
+  DevBuf dA32, dW32, dA, dW, dv, dres, dout, dop, dyc;
   std::vector<bf16> hop;
   int rc = -1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1222,6 +1255,22 @@ int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const
     if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dW.p, ld, N, ld, 256) || make_tmap_bf16_2d(&tb128, dW.p, ld, N, ld, 128)) break;
     LnEpilogue ep{dv.as<float>(), dres.as<float>(), dv.as<float>() + N, dv.as<float>() + 2 * N, g2 ? dv.as<float>() + 3 * N : nullptr,
                   b2 ? dv.as<float>() + 4 * N : nullptr, dout.as<float>(), dop.as<bf16>(), old_, olo, f32_normed, compact_rows, compact_seg};
+    if (pair == 2 && g2) {                                   // pair = 2: cta_group::2 shape with the one-pass second-LN statistics
+      std::vector<float> c(N + 3 * (N / 32) + 2);
+      double mb = 0.0, vb = 0.0;
+      for (int j = 0; j < N; ++j) mb += b1[j];
+      mb /= N;
+      for (int j = 0; j < N; ++j) vb += (b1[j] - mb) * (b1[j] - mb);
+      vb /= N;
+      for (int ch = 0; ch < N / 32; ++ch) {
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int j = ch * 32; j < ch * 32 + 32; ++j) { c[j] = (float)(g1[j] * (b1[j] - mb)); s1 += g1[j]; s2 += (double)g1[j] * g1[j]; s3 += c[j]; }
+        c[N + ch] = (float)s1; c[N + N / 32 + ch] = (float)s2; c[N + 2 * (N / 32) + ch] = (float)s3;
+      }
+      c[N + 3 * (N / 32)] = (float)mb; c[N + 3 * (N / 32) + 1] = (float)vb;
+      if (dyc.alloc(4 * c.size()) || cudaMemcpy(dyc.p, c.data(), 4 * c.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); break; }
+      ep.y_consts = dyc.as<float>();
+    }
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int n_it = iters > 0 ? iters : 1;
     for (int it = 0; it < n_it + 1 && ok; ++it) {
@@ -1243,7 +1292,7 @@ int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const
   } while (0);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  dA32.free(); dW32.free(); dA.free(); dW.free(); dv.free(); dres.free(); dout.free(); dop.free();
+  dA32.free(); dW32.free(); dA.free(); dW.free(); dv.free(); dres.free(); dout.free(); dop.free(); dyc.free();
   return rc;
 }
 

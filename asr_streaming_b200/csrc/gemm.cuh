@@ -30,6 +30,10 @@ struct LnEpilogue {
   int op_ld, op_lo_off;
   int f32_normed;
   int compact_rows, compact_seg;
+  // optional (two-LN form, cta_group::2 shape): constants of the first LayerNorm that let its output statistics be derived from
+  // v in one pass: [0,512) gc = g1 (b1 - mean b1) | [512,528) sum g1 per 32-column chunk | [528,544) sum g1^2 | [544,560) sum gc |
+  // [560] mean b1 | [561] var b1 (biased).  nullptr: the second LayerNorm's statistics take their own pass over TMEM.
+  const float* y_consts = nullptr;
 };
 // tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- / 128-row boxes; pair selects the cta_group::2 shape (cluster of 4).
 int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, bool pair,

@@ -28,6 +28,8 @@ using namespace tc;
 
 constexpr int LN_N = 512;
 constexpr int LBN = 256;                                   // columns per CTA
+constexpr int L_STATS2_BYTES = 4 * BM * 8 + 2 * BM * 8;        // local[warp in quarter][row] + remote[set][row], float2 (sum, M2)
+constexpr int L_STATS4_BYTES = 4 * BM * 16 + 2 * BM * 16;      // same for the float4 payload of the derived second-LN statistics
 // Two shapes of the same kernel:
 //   PAIR = false  cluster of 2: CTA r = columns [256 r, +256) of the same 128 rows; 1-CTA MMA 128 x 256; stage = A 16 KB + B 32 KB
 //   PAIR = true   cluster of 4: ranks (2n + m) -> column half n, row half m of a 256-row tile; the two CTAs with equal n form a
@@ -38,14 +40,14 @@ template <bool PAIR> struct LnCfg {
   static constexpr int CLUSTER = PAIR ? 4 : 2;
   static constexpr int STAGES = PAIR ? 4 : 3;
   static constexpr int STAGE_BYTES = PAIR ? (BM + LBN / 2) * BK * 2 : (BM + LBN) * BK * 2;     // 32 KB / 48 KB
+  static constexpr int STATS_BYTES = L_STATS2_BYTES + (PAIR ? L_STATS4_BYTES : 0);             // the 3-stage 48 KB ring leaves no room for more
 };
 constexpr int L_EW = 16;                                   // epilogue warps: 4 per TMEM lane quarter, 2 chunks of 32 columns each
 constexpr int L_THREADS = 64 + 32 * L_EW;
 constexpr int L_LD = 36;                                   // fp32 row stride of the per-warp transpose tile (conflict-free both ways)
 constexpr int L_XPOSE_FLOATS = 32 * L_LD;
 constexpr int L_XPOSE_BYTES = L_EW * L_XPOSE_FLOATS * 4;
-constexpr int L_STATS_BYTES = 4 * BM * 8 + 2 * BM * 8;         // local[warp in quarter][row] + remote[set][row], float2 (sum, M2)
-template <bool PAIR> constexpr int ln_smem_bytes() { return LnCfg<PAIR>::STAGES * LnCfg<PAIR>::STAGE_BYTES + L_XPOSE_BYTES + L_STATS_BYTES + 1024 + 256; }
+template <bool PAIR> constexpr int ln_smem_bytes() { return LnCfg<PAIR>::STAGES * LnCfg<PAIR>::STAGE_BYTES + L_XPOSE_BYTES + LnCfg<PAIR>::STATS_BYTES + 1024 + 256; }
 static_assert(ln_smem_bytes<false>() <= 232448 && ln_smem_bytes<true>() <= 232448, "gemm_ln: shared memory budget");
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
@@ -93,6 +95,7 @@ struct XchgCtx {
   uint32_t peer_remote0;   // shared::cluster address of the PEER's remote[0][row]
   uint32_t bar0;           // shared::cta address of xbar[0][quarter]; set 1 is 4*8 bytes further
   uint32_t peer_bar0;      // shared::cluster address of the peer's xbar[0][quarter]
+  uint32_t local4_row, local4_part, remote4_set0, peer_remote4_0;   // the same four addresses for the float4 exchange (PAIR shape only)
   int named_bar;           // 1 + quarter
   int wq;
   uint32_t rank;          // 0 / 1: which column half this CTA owns (CTA 0's partials are summed first in both CTAs)
@@ -139,6 +142,59 @@ __device__ __forceinline__ RowStats exchange_row_stats(float sum, float m2, cons
   return r;
 }
 
+// Plain sums of three per-thread partials over the 8 owners of a row (same protocol and barriers as exchange_row_stats: it is just
+// another round).  Used for the statistics of y = LN_a(v) derived from v without a second pass over the data.
+__device__ __forceinline__ float3 exchange_sum3(float a, float b, float c, const XchgCtx& X, int round) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(X.local4_part), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");
+  float4 p[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p[w].x), "=f"(p[w].y), "=f"(p[w].z), "=f"(p[w].w)
+                 : "r"(X.local4_row + (uint32_t)(w * BM) * 16u) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");
+  const float a_cta = (p[0].x + p[1].x) + (p[2].x + p[3].x), b_cta = (p[0].y + p[1].y) + (p[2].y + p[3].y), c_cta = (p[0].z + p[1].z) + (p[2].z + p[3].z);
+  const uint32_t set = (uint32_t)(round & 1), parity = (uint32_t)((round >> 1) & 1);
+  const uint32_t bar = X.bar0 + set * 32u;
+  if (X.wq == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(bar) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(X.peer_remote4_0 + set * (uint32_t)(BM * 16)), "f"(a_cta), "f"(b_cta), "f"(c_cta), "f"(0.f), "r"(X.peer_bar0 + set * 32u) : "memory");
+  }
+  mbar_wait(bar, parity);
+  float4 o;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(X.remote4_set0 + set * (uint32_t)(BM * 16)) : "memory");
+  // CTA 0's sums first in both CTAs: identical results
+  return X.rank == 0 ? make_float3(a_cta + o.x, b_cta + o.y, c_cta + o.z) : make_float3(o.x + a_cta, o.y + b_cta, o.z + c_cta);
+}
+
+// Per 32-value chunk of one row: besides (sum, M2) also the chunk-centred weighted moments that give the statistics of
+// y = LN(v; g, b) once the row mean is known.  With w = v - m_c (m_c = chunk mean), gc = g (b - mean b):
+//   p1 = sum g w,  p2 = sum (g w)^2,  p3 = sum g^2 w,  p4 = sum gc w.
+struct ChunkMoments { float sum, m2, p1, p2, p3, p4; };
+__device__ __forceinline__ ChunkMoments chunk_moments(const float (&v)[32], const float* __restrict__ g, const float* __restrict__ gc) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) { s[0] += v[j]; s[1] += v[j + 1]; s[2] += v[j + 2]; s[3] += v[j + 3]; }
+  const float t = (s[0] + s[1]) + (s[2] + s[3]);
+  const float m = t * (1.0f / 32.0f);
+  float q[4] = {0.f, 0.f, 0.f, 0.f}, p1[2] = {0.f, 0.f}, p2[2] = {0.f, 0.f}, p3[2] = {0.f, 0.f}, p4[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + j)), c4 = __ldg(reinterpret_cast<const float4*>(gc + j));
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = v[j + k] - m, gw = gg[k] * d;
+      q[k] = fmaf(d, d, q[k]);
+      p1[k & 1] += gw; p2[k & 1] = fmaf(gw, gw, p2[k & 1]); p3[k & 1] = fmaf(gg[k], gw, p3[k & 1]); p4[k & 1] = fmaf(cc[k], d, p4[k & 1]);
+    }
+  }
+  ChunkMoments r;
+  r.sum = t; r.m2 = (q[0] + q[1]) + (q[2] + q[3]); r.p1 = p1[0] + p1[1]; r.p2 = p2[0] + p2[1]; r.p3 = p3[0] + p3[1]; r.p4 = p4[0] + p4[1];
+  return r;
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(L_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, LnEpilogue ep) {
@@ -147,7 +203,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xpose_base = smem_base + L_STAGES * L_STAGE_BYTES;
   const uint32_t stats_base = xpose_base + L_XPOSE_BYTES;
-  const uint32_t bar_base = stats_base + L_STATS_BYTES;
+  const uint32_t bar_base = stats_base + LnCfg<PAIR>::STATS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (L_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L_STAGES + s); };
@@ -269,6 +325,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       X.local_part = X.local_row + (uint32_t)(wq * BM) * 8u;
       X.remote_set0 = stats_base + 4u * BM * 8u + row_off;
       X.peer_remote0 = map_to_cta(X.remote_set0, xpeer);
+      if (PAIR) {
+        const uint32_t base4 = stats_base + (uint32_t)L_STATS2_BYTES, row4 = (uint32_t)(quarter * 32 + lane) * 16u;
+        X.local4_row = base4 + row4;
+        X.local4_part = X.local4_row + (uint32_t)(wq * BM) * 16u;
+        X.remote4_set0 = base4 + 4u * BM * 16u + row4;
+        X.peer_remote4_0 = map_to_cta(X.remote4_set0, xpeer);
+      } else {
+        X.local4_row = X.local4_part = X.remote4_set0 = X.peer_remote4_0 = 0;
+      }
       X.bar0 = xq_bar(0, quarter);
       X.peer_bar0 = map_to_cta(X.bar0, xpeer);
       X.named_bar = 1 + quarter; X.wq = wq; X.rank = nrank;
@@ -289,6 +354,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 
       float raw[32];
+      // PAIR shape with two LayerNorms: the statistics of y = LN_a(v) are derived from chunk-centred weighted moments of v
+      // gathered in R1 (ep.y_consts), so the pass that materialised y in TMEM (R1b) disappears.
+      const bool fuse2 = PAIR && ep.g2 != nullptr && ep.y_consts != nullptr;
+      float mom[2][4];                                       // [chunk][p1..p4]
       // ---------------- R1: v = acc + bias + residual, statistics of v
       float s_a = 0.f, q_a = 0.f, s_b = 0.f, q_b = 0.f;
 #pragma unroll 1
@@ -311,20 +380,47 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           raw[j] += rr.x + bb.x; raw[j + 1] += rr.y + bb.y; raw[j + 2] += rr.z + bb.z; raw[j + 3] += rr.w + bb.w;
         }
         __syncwarp();
-        if (h == 0) chunk_stats(raw, s_a, q_a); else chunk_stats(raw, s_b, q_b);
+        if (fuse2) {
+          const ChunkMoments cm = chunk_moments(raw, ep.g1 + col0, ep.y_consts + col0);
+          if (h == 0) { s_a = cm.sum; q_a = cm.m2; } else { s_b = cm.sum; q_b = cm.m2; }
+          mom[h][0] = cm.p1; mom[h][1] = cm.p2; mom[h][2] = cm.p3; mom[h][3] = cm.p4;
+        } else {
+          if (h == 0) chunk_stats(raw, s_a, q_a); else chunk_stats(raw, s_b, q_b);
+        }
         tmem_st32(taddr + (uint32_t)(cc * 32), raw);
       }
       tmem_st_wait();
+      const float mc_a = s_a * (1.0f / 32.0f), mc_b = s_b * (1.0f / 32.0f);      // chunk means (before the sums are merged)
       {
-        const float d = (s_a - s_b) * (1.0f / 32.0f);
+        const float d = mc_a - mc_b;
         q_a = q_a + q_b + 16.0f * d * d;                     // Chan: n_a n_b / (n_a + n_b) = 16
         s_a += s_b;
       }
       RowStats st = exchange_row_stats(s_a, q_a, X, round++);
+      RowStats st2 = st;                                     // statistics of y (two-LN forms)
 
       const float* g_fin = ep.g1;
       const float* b_fin = ep.b1;
-      if (ep.g2) {
+      if (fuse2) {
+        // with u = v - mean = w + delta (delta = chunk mean - row mean) and the per-chunk constants G1 = sum g, G2 = sum g^2, G3 = sum gc:
+        //   A1 = sum g u = p1 + delta G1;   A2 = sum (g u)^2 = p2 + 2 delta p3 + delta^2 G2;   A3 = sum gc u = p4 + delta G3
+        const float* yc = ep.y_consts + LN_N;
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int chunk = (int)nrank * 8 + wq + 4 * h;     // 32-column chunk index within the 512-wide row
+          const float dl = (h == 0 ? mc_a : mc_b) - st.mean;
+          a1 += mom[h][0] + dl * __ldg(yc + chunk);
+          a2 += mom[h][1] + 2.0f * dl * mom[h][2] + dl * dl * __ldg(yc + 16 + chunk);
+          a3 += mom[h][3] + dl * __ldg(yc + 32 + chunk);
+        }
+        const float3 A = exchange_sum3(a1, a2, a3, X, round++);
+        // y_j = r g_j u_j + b_j:  mean_y = r A1/N + mean(b);  var_y = r^2 (A2/N - (A1/N)^2) + 2 r A3/N + var(b)
+        const float mg = A.x * (1.0f / LN_N);
+        const float var_y = st.rstd * st.rstd * (A.y * (1.0f / LN_N) - mg * mg) + 2.0f * st.rstd * A.z * (1.0f / LN_N) + __ldg(yc + 49);
+        st2.mean = st.rstd * mg + __ldg(yc + 48);
+        st2.rstd = 1.0f / sqrtf(fmaxf(var_y, 0.f) + 1e-5f);
+      } else if (ep.g2) {
         // ---------------- R1b: y = LN_a(v) in row layout, statistics of y
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -359,6 +455,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mu[i] = __shfl_sync(0xffffffffu, st.mean, 4 * i + rsub);
         rs[i] = __shfl_sync(0xffffffffu, st.rstd, 4 * i + rsub);
       }
+      if (fuse2) { g_fin = ep.g2; b_fin = ep.b2; }
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int cc = wq + 4 * h;
@@ -370,15 +467,25 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const float4 gg = __ldg(reinterpret_cast<const float4*>(g_fin + col));
         const float4 bb = __ldg(reinterpret_cast<const float4*>(b_fin + col));
+        float4 g1v = gg, b1v = bb;
+        if (fuse2) { g1v = __ldg(reinterpret_cast<const float4*>(ep.g1 + col)); b1v = __ldg(reinterpret_cast<const float4*>(ep.b1 + col)); }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = row0 + 4 * i + rsub;
-          const float4 t = *reinterpret_cast<const float4*>(xpose + (4 * i + rsub) * L_LD + csub);
+          float4 t = *reinterpret_cast<const float4*>(xpose + (4 * i + rsub) * L_LD + csub);
           float n[4];
-          n[0] = (t.x - mu[i]) * rs[i] * gg.x + bb.x;
-          n[1] = (t.y - mu[i]) * rs[i] * gg.y + bb.y;
-          n[2] = (t.z - mu[i]) * rs[i] * gg.z + bb.z;
-          n[3] = (t.w - mu[i]) * rs[i] * gg.w + bb.w;
+          if (fuse2) {                                         // t = v: first LN here (its statistics are mu / rs), second with st2
+            t.x = (t.x - mu[i]) * rs[i] * g1v.x + b1v.x; t.y = (t.y - mu[i]) * rs[i] * g1v.y + b1v.y;
+            t.z = (t.z - mu[i]) * rs[i] * g1v.z + b1v.z; t.w = (t.w - mu[i]) * rs[i] * g1v.w + b1v.w;
+            const float m2 = __shfl_sync(0xffffffffu, st2.mean, 4 * i + rsub), r2 = __shfl_sync(0xffffffffu, st2.rstd, 4 * i + rsub);
+            n[0] = (t.x - m2) * r2 * gg.x + bb.x; n[1] = (t.y - m2) * r2 * gg.y + bb.y;
+            n[2] = (t.z - m2) * r2 * gg.z + bb.z; n[3] = (t.w - m2) * r2 * gg.w + bb.w;
+          } else {
+            n[0] = (t.x - mu[i]) * rs[i] * gg.x + bb.x;
+            n[1] = (t.y - mu[i]) * rs[i] * gg.y + bb.y;
+            n[2] = (t.z - mu[i]) * rs[i] * gg.z + bb.z;
+            n[3] = (t.w - mu[i]) * rs[i] * gg.w + bb.w;
+          }
           if (row < p.M) {
             *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * LN_N + col) = ep.f32_normed ? make_float4(n[0], n[1], n[2], n[3]) : t;
             int orow = row;

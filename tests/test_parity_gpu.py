@@ -408,6 +408,23 @@ def test_fused_layernorm_path_matches_reference(name, packed_weights, golden, me
     assert np.abs(em_f - em_u).max() < FAST_TOL
 
 
+@pytest.mark.parametrize("name", ["synth_noise", "seq_reset_skip"])
+def test_fused_layernorm_pair_shape_matches_reference(name, packed_weights, golden, meta, monkeypatch):
+    """FFN2 in the cta_group::2 shape (cluster of 4) with the one-pass statistics of the second LayerNorm, forced for one stream."""
+    from asr_streaming_b200 import Engine, PRECISION_EXACT, PRECISION_FAST
+    case, mc = golden(name), meta["cases"][name]
+    monkeypatch.setenv("ASR_B200_FUSED_LN_MIN_STREAMS", "1")
+    monkeypatch.setenv("ASR_B200_PAIR_LN_MIN_TILES", "1")
+    with Engine(model_cfg(PRECISION_EXACT), packed_weights) as e:
+        em, ids, blanks = _run_case(e, case, mc)
+    report(f"EXACT fused-LN pair shape {name}: logprob max-abs {np.abs(em - case['emission']).max():.3e}")
+    assert np.abs(em - case["emission"]).max() < EXACT_TOL
+    assert np.array_equal(em.argmax(2), case["argmax"])
+    with Engine(model_cfg(PRECISION_FAST), packed_weights) as e:
+        em_f, _, _ = _run_case(e, case, mc)
+    assert np.abs(em_f - case["emission"]).max() < FAST_TOL
+
+
 def test_fused_layernorm_large_ragged_batch(packed_weights):
     """200 streams in one step (above the fused threshold, M = 4000 is not a multiple of the 128-row tile) against the same
     streams run one by one: per-stream results must not depend on the batch they ride in (FAST precision, bit-exact)."""

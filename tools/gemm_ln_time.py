@@ -15,7 +15,7 @@ for M in sizes:
         W = (rng.standard_normal((512, K)) / np.sqrt(K)).astype(np.float32)
         v = rng.standard_normal(512).astype(np.float32)
         res = rng.standard_normal((M, 512)).astype(np.float32)
-        for pair in (False, True):
+        for pair in (0, 1, 2) if two else (0, 1):
             _, _, ms = debug_gemm_ln(A, W, v, res, v, v, v if two else None, v if two else None, iters=20, pair=pair)
-            print(f"M={M:6d} K={K:4d} {'two LN' if two else 'one LN'} {'pair/cluster4' if pair else 'cluster2     '}: {1e3 * ms:8.1f} us  "
+            print(f"M={M:6d} K={K:4d} {'two LN' if two else 'one LN'} {('cluster2', 'pair/cluster4', 'pair + 1-pass LN2')[pair]:18s}: {1e3 * ms:8.1f} us  "
                   f"{2 * M * 512 * K / ms / 1e9:7.1f} TFLOP/s", flush=True)

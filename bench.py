@@ -201,6 +201,8 @@ class RaggedWorkload:
         self.sch.wr[:] = cfg.buffer_length                          # nothing has "arrived" yet: feed_pass() releases 640 ms at a time
         self.fed = 0
         self.run_chunks = self.skipped_chunks = self.endpoints = 0
+        self.t_submit = self.t_collect = self.t_after = 0.0       # host seconds spent in submit_tick / collect_tick / scripted endpoints
+        self.n_ticks = 0
 
     def feed_pass(self):
         """The next 640 ms of every stream arrive (the samples are already in the rings; only the write pointers move)."""
@@ -227,11 +229,19 @@ class RaggedWorkload:
         for _ in range(n_passes):
             self.feed_pass()
             while True:
+                t0 = time.perf_counter()
                 p = self.sch.submit_tick(gate=self.gate, max_rows=max_rows)
+                self.t_submit += time.perf_counter() - t0
                 if p.rows.size == 0 and not p.res.skipped:
                     break                                           # nothing left to launch in this pass; `prev` stays in flight
+                self.n_ticks += 1
                 if prev is not None:
-                    self._after(self.sch.collect_tick(prev))
+                    t0 = time.perf_counter()
+                    res = self.sch.collect_tick(prev)
+                    t1 = time.perf_counter()
+                    self._after(res)
+                    self.t_collect += t1 - t0
+                    self.t_after += time.perf_counter() - t1
                     prev = None
                 if p.rows.size:
                     prev = p
@@ -382,6 +392,7 @@ def run_ours(args):
         wl.run_pipelined(2, streams // 2)
         barrier()
         c0 = (wl.run_chunks, wl.skipped_chunks, wl.endpoints)
+        h0 = (wl.t_submit, wl.t_collect, wl.t_after, wl.n_ticks)
         t0 = time.perf_counter()
         wl.run_pipelined(e2e_steps, streams // 2)
         barrier()
@@ -393,6 +404,9 @@ def run_ours(args):
         extra["ragged"] = {"sessions": streams, "ticks_in_flight": 2, "max_rows_per_tick": streams // 2, "e2e_steps_run": e2e_steps,
                            "decoded_chunks_per_pass": run_c / e2e_steps, "vad_skipped_chunks_per_pass": skip_c / e2e_steps,
                            "endpoints_per_pass": end_c / e2e_steps,
+                           "host_ms_per_tick": {"submit_tick (ready + gate + gather + enqueue)": 1e3 * (wl.t_submit - h0[0]) / max(1, wl.n_ticks - h0[3]),
+                                                "collect_tick (wait + bookkeeping + rules)": 1e3 * (wl.t_collect - h0[1]) / max(1, wl.n_ticks - h0[3]),
+                                                "scripted endpoints": 1e3 * (wl.t_after - h0[2]) / max(1, wl.n_ticks - h0[3])},
                            "e2e_counts": "audio-seconds of the chunks actually decoded (VAD-skipped chunks are excluded from e2e.value)"}
         e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / e2e_steps
     else:

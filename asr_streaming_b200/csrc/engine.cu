@@ -96,8 +96,10 @@ struct AsrEngine {
   int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
   int no_fuse2 = 0;             // ASR_B200_NO_LN_FUSE2=1: second LayerNorm statistics by their own TMEM pass
   int pair_ln_min_tiles = 34;   // 256-row tiles needed before gemm_ln takes the cta_group::2 shape (34 clusters of 4 fit on 148 SMs)
+  int quad_ln_max_tiles = 34;   // 128-row tiles up to which gemm_ln takes the four-column-quarter shape: more would need a second wave of clusters (measured: 3200 rows 11.7 vs 15.2 us, 5120 rows 16.6 vs 15.9 us)
   int fused_ln = 1;             // LayerNorm fused into the out_proj / FFN2 epilogues (gemm_ln.cu); ASR_B200_NO_FUSED_LN=1 -> separate passes
-  int fused_ln_min_streams = 160;   // below this batch the separate LN passes win (measured: 64 streams 1.30 vs 1.59 ms, 256: 2.00 vs 2.00, 1024: 5.99 vs 5.77)
+  int fused_ln_min_streams = 96;    // below this batch the separate LN passes win (measured with the quad shape: 64 streams 1.31 vs 1.33 ms,
+                                    // 128: 1.53 vs 1.48, 1024: 5.99 vs 5.77)
   int pdl_max_streams = 1536;   // programmatic dependent launch below this batch size (see common.cuh)
   int staged_fmt = 0;
   cudaStream_t stream = nullptr;
@@ -350,8 +352,10 @@ int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
   ProfScope ps(e, cat);
   // CTA pairs when the mainloop is long enough to be L2-bound (FFN2, K = 2048) and there are enough 256-row tiles to fill the clusters
-  const bool pair = !e->no_pair_ln && w.K * (e->geo.split ? 3 : 1) >= 1024 && (M + 255) / 256 >= e->pair_ln_min_tiles;
-  return gemm_ln(a.tm, w.tm[2], w.tm[1], p, ep, pair, e->num_sms, e->stream);
+  int shape = 0;
+  if (!e->no_pair_ln && w.K * (e->geo.split ? 3 : 1) >= 1024 && (M + 255) / 256 >= e->pair_ln_min_tiles) shape = 1;
+  else if ((M + 127) / 128 <= e->quad_ln_max_tiles) shape = 2;       // few row tiles: four column quarters put twice the CTAs to work
+  return gemm_ln(a.tm, w.tm[2], w.tm[1], p, ep, shape, e->num_sms, e->stream);
 }
 
 // ------------------------------------------------------------------------------------------ the per-step kernel chain
@@ -663,6 +667,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* pl = getenv("ASR_B200_NO_PAIR_LN")) e->no_pair_ln = pl[0] == '1';
   if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
   if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
+  if (const char* qt = getenv("ASR_B200_QUAD_LN_MAX_TILES")) e->quad_ln_max_tiles = atoi(qt);
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
   if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
   int rc = -1;
@@ -1275,7 +1280,7 @@ int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const
     const int n_it = iters > 0 ? iters : 1;
     for (int it = 0; it < n_it + 1 && ok; ++it) {
       if (it == 1) cudaEventRecord(e0, 0);
-      ok = !gemm_ln(ta, tb, tb128, p, ep, pair != 0, prop.multiProcessorCount, 0);
+      ok = !gemm_ln(ta, tb, tb128, p, ep, pair == 3 ? 2 : (pair != 0), prop.multiProcessorCount, 0);
     }
     if (!ok) break;
     cudaEventRecord(e1, 0);

@@ -35,8 +35,9 @@ struct LnEpilogue {
   // [560] mean b1 | [561] var b1 (biased).  nullptr: the second LayerNorm's statistics take their own pass over TMEM.
   const float* y_consts = nullptr;
 };
-// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- / 128-row boxes; pair selects the cta_group::2 shape (cluster of 4).
-int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, bool pair,
+// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- / 128-row boxes.  shape 0: cluster of 2 column halves;
+// 1: cta_group::2 pairs x 2 column halves (large M, long K); 2: cluster of 4 column quarters (small M).
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, int shape,
             int num_sms, cudaStream_t st);
 
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t rows, uint32_t n_heads, uint32_t box_rows);

@@ -27,28 +27,34 @@ namespace {
 using namespace tc;
 
 constexpr int LN_N = 512;
-constexpr int LBN = 256;                                   // columns per CTA
-constexpr int L_STATS2_BYTES = 4 * BM * 8 + 2 * BM * 8;        // local[warp in quarter][row] + remote[set][row], float2 (sum, M2)
-constexpr int L_STATS4_BYTES = 4 * BM * 16 + 2 * BM * 16;      // same for the float4 payload of the derived second-LN statistics
-// Two shapes of the same kernel:
-//   PAIR = false  cluster of 2: CTA r = columns [256 r, +256) of the same 128 rows; 1-CTA MMA 128 x 256; stage = A 16 KB + B 32 KB
-//   PAIR = true   cluster of 4: ranks (2n + m) -> column half n, row half m of a 256-row tile; the two CTAs with equal n form a
-//                 cta_group::2 pair (MMA 256 x 256, each CTA stages its own 128 A rows and HALF of the pair's B rows: 32 KB per
-//                 stage, 64 instead of 96 B/clk/SM of L2 ingest at full tensor rate — the 1-CTA shape is L2-bound at K = 2048).
-//                 Statistics are exchanged between the CTAs with equal m (rank ^ 2).  148 SMs hold 34 such clusters (136 SMs).
-template <bool PAIR> struct LnCfg {
-  static constexpr int CLUSTER = PAIR ? 4 : 2;
-  static constexpr int STAGES = PAIR ? 4 : 3;
-  static constexpr int STAGE_BYTES = PAIR ? (BM + LBN / 2) * BK * 2 : (BM + LBN) * BK * 2;     // 32 KB / 48 KB
-  static constexpr int STATS_BYTES = L_STATS2_BYTES + (PAIR ? L_STATS4_BYTES : 0);             // the 3-stage 48 KB ring leaves no room for more
+constexpr int L_STATS4_BYTES = 4 * BM * 16 + 2 * BM * 16;      // float4 payload of the derived second-LN statistics (PAIR shape only)
+// Three shapes of the same kernel (SHAPE):
+//   0  cluster of 2: CTA r = columns [256 r, +256) of the same 128 rows; 1-CTA MMA 128 x 256; stage = A 16 KB + B 32 KB, 3 stages
+//   1  cluster of 4 (PAIR): ranks (2n + m) -> column half n, row half m of a 256-row tile; the two CTAs with equal n form a
+//      cta_group::2 pair (MMA 256 x 256, each CTA stages its own 128 A rows and HALF of the pair's B rows: 32 KB per stage, 64
+//      instead of 96 B/clk/SM of L2 ingest at full tensor rate).  Statistics are exchanged between the CTAs with equal m (rank ^ 2).
+//      148 SMs hold 34 such clusters (136 SMs).  For long K and large M (FFN2 from ~440 streams per step on).
+//   2  cluster of 4 (QUAD): CTA r = columns [128 r, +128) of the same 128 rows, one 32-column chunk per epilogue warp.  For small M:
+//      a 256-stream step has only 40 row tiles, i.e. 80 CTAs in shape 0 — this shape puts 160 CTAs on the 148 SMs and halves the
+//      epilogue's critical path per tile.
+template <int SHAPE> struct LnCfg {
+  static constexpr bool PAIR = SHAPE == 1;
+  static constexpr int NSPLIT = SHAPE == 2 ? 4 : 2;           // CTAs that share a row
+  static constexpr int BN = LN_N / NSPLIT;                    // columns per CTA: 256 / 256 / 128
+  static constexpr int CHUNKS = BN / 128;                     // 32-column chunks per epilogue warp: 2 / 2 / 1
+  static constexpr int CLUSTER = PAIR ? 4 : NSPLIT;
+  static constexpr int STAGES = SHAPE == 0 ? 3 : 4;
+  static constexpr int STAGE_BYTES = PAIR ? (BM + BN / 2) * BK * 2 : (BM + BN) * BK * 2;       // 48 KB / 32 KB / 32 KB
+  static constexpr int STATS2_BYTES = 4 * BM * 8 + 2 * (NSPLIT - 1) * BM * 8;                  // local[warp in quarter][row] + remote[set][peer][row], float2
+  static constexpr int STATS_BYTES = STATS2_BYTES + (PAIR ? L_STATS4_BYTES : 0);
 };
 constexpr int L_EW = 16;                                   // epilogue warps: 4 per TMEM lane quarter, 2 chunks of 32 columns each
 constexpr int L_THREADS = 64 + 32 * L_EW;
 constexpr int L_LD = 36;                                   // fp32 row stride of the per-warp transpose tile (conflict-free both ways)
 constexpr int L_XPOSE_FLOATS = 32 * L_LD;
 constexpr int L_XPOSE_BYTES = L_EW * L_XPOSE_FLOATS * 4;
-template <bool PAIR> constexpr int ln_smem_bytes() { return LnCfg<PAIR>::STAGES * LnCfg<PAIR>::STAGE_BYTES + L_XPOSE_BYTES + LnCfg<PAIR>::STATS_BYTES + 1024 + 256; }
-static_assert(ln_smem_bytes<false>() <= 232448 && ln_smem_bytes<true>() <= 232448, "gemm_ln: shared memory budget");
+template <int SHAPE> constexpr int ln_smem_bytes() { return LnCfg<SHAPE>::STAGES * LnCfg<SHAPE>::STAGE_BYTES + L_XPOSE_BYTES + LnCfg<SHAPE>::STATS_BYTES + 1024 + 256; }
+static_assert(ln_smem_bytes<0>() <= 232448 && ln_smem_bytes<1>() <= 232448 && ln_smem_bytes<2>() <= 232448, "gemm_ln: shared memory budget");
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
   uint32_t r;
@@ -89,26 +95,29 @@ struct RowStats { float mean, rstd; };
 
 // Everything one epilogue warp needs for the row-statistics exchange of its TMEM lane quarter.
 struct XchgCtx {
-  uint32_t local_part;     // shared::cta address of local[wq][row] (this thread's slot); the quarter's 4 slots are BM*8 bytes apart
-  uint32_t local_row;      // shared::cta address of local[0][row]
-  uint32_t remote_set0;    // shared::cta address of remote[0][row] (what the peer wrote for us); set 1 is BM*8 bytes further
-  uint32_t peer_remote0;   // shared::cluster address of the PEER's remote[0][row]
-  uint32_t bar0;           // shared::cta address of xbar[0][quarter]; set 1 is 4*8 bytes further
-  uint32_t peer_bar0;      // shared::cluster address of the peer's xbar[0][quarter]
-  uint32_t local4_row, local4_part, remote4_set0, peer_remote4_0;   // the same four addresses for the float4 exchange (PAIR shape only)
-  int named_bar;           // 1 + quarter
+  uint32_t local_part;       // shared::cta address of local[wq][row] (this thread's slot); the quarter's 4 slots are BM*8 bytes apart
+  uint32_t local_row;        // shared::cta address of local[0][row]
+  uint32_t remote_set0;      // shared::cta address of remote[set 0][slot 0][row] (what the peers wrote for us); slot stride BM*8, set stride slots*BM*8
+  uint32_t peer_dst0[3];     // shared::cluster address, in peer i's memory, of remote[set 0][my slot there][row]
+  uint32_t bar0;             // shared::cta address of xbar[0][quarter]; set 1 is 4*8 bytes further
+  uint32_t peer_bar0[3];     // shared::cluster address of peer i's xbar[0][quarter]
+  uint32_t local4_row, local4_part, remote4_set0, peer_remote4_0;   // the float4 exchange (PAIR shape only, one peer)
+  int named_bar;             // 1 + quarter
   int wq;
-  uint32_t rank;          // 0 / 1: which column half this CTA owns (CTA 0's partials are summed first in both CTAs)
+  uint32_t rank;             // 0 .. NSPLIT-1: which column slice this CTA owns (partials are summed in slice order in every CTA)
 };
 
-// All 128 threads of a lane quarter (4 warps) in both CTAs call this once per round with their partial: sum over their 64 values
-// and M2 around that partial's own mean.  Returns mean and 1/sqrt(var + eps) of the whole 512-wide row (biased variance,
-// torch.nn.LayerNorm).  Two levels, Chan's pairwise combination at both (two-pass accuracy, fixed order => bit-reproducible):
+// All 128 threads of a lane quarter (4 warps) in all NSPLIT CTAs that share the rows call this once per round with their partial:
+// sum over their N_T values and M2 around that partial's own mean.  Returns mean and 1/sqrt(var + eps) of the whole 512-wide row
+// (biased variance, torch.nn.LayerNorm).  Two levels, Chan's pairwise combination at both (two-pass accuracy, fixed order =>
+// bit-reproducible):
 //   inside the CTA   partials through shared memory, two named-barrier syncs of the quarter's 128 threads
-//   across the CTAs  warp wq == 0 pushes the CTA's combined (sum, M2) into the peer's shared memory with st.async, which signals
+//   across the CTAs  warp wq == 0 pushes the CTA's combined (sum, M2) into every peer's shared memory with st.async, which signals
 //                    the peer's mbarrier (complete_tx) — no cluster-scope fence, no L1 invalidation on the consumer side.
 // Two mbarriers / receive slots per quarter alternate by round, so a packet of round r+2 can never be counted in round r.
+template <int NSPLIT, int N_T>
 __device__ __forceinline__ RowStats exchange_row_stats(float sum, float m2, const XchgCtx& X, int round) {
+  constexpr float N_CTA = 4.0f * N_T;
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(X.local_part), "f"(sum), "f"(m2) : "memory");
   asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");
   float2 p[4];
@@ -117,25 +126,37 @@ __device__ __forceinline__ RowStats exchange_row_stats(float sum, float m2, cons
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p[w].x), "=f"(p[w].y) : "r"(X.local_row + (uint32_t)(w * BM) * 8u) : "memory");
   asm volatile("bar.sync %0, 128;" ::"r"(X.named_bar) : "memory");          // everyone has read: the slots may be rewritten next round
   const float s_cta = (p[0].x + p[1].x) + (p[2].x + p[3].x);
-  const float mean_cta = s_cta * (1.0f / 256.0f);
+  const float mean_cta = s_cta * (1.0f / N_CTA);
   float q_cta = 0.f;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) { const float d = p[w].x * (1.0f / 64.0f) - mean_cta; q_cta += p[w].y + 64.0f * d * d; }
+  for (int w = 0; w < 4; ++w) { const float d = p[w].x * (1.0f / N_T) - mean_cta; q_cta += p[w].y + (float)N_T * d * d; }
   const uint32_t set = (uint32_t)(round & 1), parity = (uint32_t)((round >> 1) & 1);
   const uint32_t bar = X.bar0 + set * 32u;
+  constexpr uint32_t SET_STRIDE = (uint32_t)((NSPLIT - 1) * BM * 8);
   if (X.wq == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 8;" ::"r"(bar) : "memory");
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
-                 ::"r"(X.peer_remote0 + set * (uint32_t)(BM * 8)), "f"(s_cta), "f"(q_cta), "r"(X.peer_bar0 + set * 32u) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(8 * (NSPLIT - 1))) : "memory");
+#pragma unroll
+    for (int i = 0; i < NSPLIT - 1; ++i)
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                   ::"r"(X.peer_dst0[i] + set * SET_STRIDE), "f"(s_cta), "f"(q_cta), "r"(X.peer_bar0[i] + set * 32u) : "memory");
   }
   mbar_wait(bar, parity);
-  float2 o;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(X.remote_set0 + set * (uint32_t)(BM * 8)) : "memory");
-  const float s0 = X.rank == 0 ? s_cta : o.x, s1 = X.rank == 0 ? o.x : s_cta;       // CTA 0 first in both CTAs: identical sums
-  const float q0 = X.rank == 0 ? q_cta : o.y, q1 = X.rank == 0 ? o.y : q_cta;
-  const float mean = (s0 + s1) * (1.0f / LN_N);
-  const float d0 = s0 * (1.0f / 256.0f) - mean, d1 = s1 * (1.0f / 256.0f) - mean;
-  const float m2_all = (q0 + 256.0f * d0 * d0) + (q1 + 256.0f * d1 * d1);
+  float sv[NSPLIT], qv[NSPLIT];                                   // per column slice, in slice order
+#pragma unroll
+  for (int r = 0; r < NSPLIT; ++r) {
+    if (r == (int)X.rank) { sv[r] = s_cta; qv[r] = q_cta; }
+    else {
+      const int slot = r < (int)X.rank ? r : r - 1;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sv[r]), "=f"(qv[r]) : "r"(X.remote_set0 + set * SET_STRIDE + (uint32_t)(slot * BM * 8)) : "memory");
+    }
+  }
+  float tot = 0.f;
+#pragma unroll
+  for (int r = 0; r < NSPLIT; ++r) tot += sv[r];
+  const float mean = tot * (1.0f / LN_N);
+  float m2_all = 0.f;
+#pragma unroll
+  for (int r = 0; r < NSPLIT; ++r) { const float d = sv[r] * (1.0f / N_CTA) - mean; m2_all += qv[r] + N_CTA * d * d; }
   RowStats r;
   r.mean = mean;
   r.rstd = 1.0f / sqrtf(m2_all * (1.0f / LN_N) + 1e-5f);
@@ -159,7 +180,7 @@ __device__ __forceinline__ float3 exchange_sum3(float a, float b, float c, const
   if (X.wq == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(bar) : "memory");
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(X.peer_remote4_0 + set * (uint32_t)(BM * 16)), "f"(a_cta), "f"(b_cta), "f"(c_cta), "f"(0.f), "r"(X.peer_bar0 + set * 32u) : "memory");
+                 ::"r"(X.peer_remote4_0 + set * (uint32_t)(BM * 16)), "f"(a_cta), "f"(b_cta), "f"(c_cta), "f"(0.f), "r"(X.peer_bar0[0] + set * 32u) : "memory");
   }
   mbar_wait(bar, parity);
   float4 o;
@@ -195,15 +216,19 @@ __device__ __forceinline__ ChunkMoments chunk_moments(const float (&v)[32], cons
   return r;
 }
 
-template <bool PAIR>
+template <int SHAPE>
 __global__ void __launch_bounds__(L_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, LnEpilogue ep) {
-  constexpr int L_STAGES = LnCfg<PAIR>::STAGES, L_STAGE_BYTES = LnCfg<PAIR>::STAGE_BYTES, CLUSTER = LnCfg<PAIR>::CLUSTER;
+  using Cfg = LnCfg<SHAPE>;
+  constexpr bool PAIR = Cfg::PAIR;
+  constexpr int L_STAGES = Cfg::STAGES, L_STAGE_BYTES = Cfg::STAGE_BYTES, CLUSTER = Cfg::CLUSTER, LBN = Cfg::BN, NSPLIT = Cfg::NSPLIT;
+  constexpr int CHUNKS = Cfg::CHUNKS, N_T = 32 * CHUNKS;
+  constexpr uint32_t TMEM_COLS = 2 * LBN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xpose_base = smem_base + L_STAGES * L_STAGE_BYTES;
   const uint32_t stats_base = xpose_base + L_XPOSE_BYTES;
-  const uint32_t bar_base = stats_base + LnCfg<PAIR>::STATS_BYTES;
+  const uint32_t bar_base = stats_base + Cfg::STATS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (L_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L_STAGES + s); };
@@ -214,9 +239,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t nrank = PAIR ? rank >> 1 : rank;              // column half
+  const uint32_t nrank = PAIR ? rank >> 1 : rank;              // column slice
   const uint32_t mrank = PAIR ? rank & 1u : 0u;                // row half inside the pair's 256-row tile
-  const uint32_t xpeer = PAIR ? rank ^ 2u : rank ^ 1u;         // the CTA holding the other half of my rows
   constexpr int TILE_M = PAIR ? 2 * BM : BM;
   const int cluster_id = blockIdx.x / CLUSTER, n_clusters = gridDim.x / CLUSTER;
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
@@ -233,10 +257,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
@@ -324,18 +348,26 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       X.local_row = stats_base + row_off;
       X.local_part = X.local_row + (uint32_t)(wq * BM) * 8u;
       X.remote_set0 = stats_base + 4u * BM * 8u + row_off;
-      X.peer_remote0 = map_to_cta(X.remote_set0, xpeer);
+      X.bar0 = xq_bar(0, quarter);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { X.peer_dst0[i] = 0; X.peer_bar0[i] = 0; }
+#pragma unroll
+      for (int i = 0; i < NSPLIT - 1; ++i) {
+        const uint32_t pn = (uint32_t)i < nrank ? (uint32_t)i : (uint32_t)i + 1u;       // the peer's column slice
+        const uint32_t pr = PAIR ? (pn << 1) | mrank : pn;                              // its cluster rank
+        const uint32_t my_slot = nrank < pn ? nrank : nrank - 1u;                       // where my partial lives in its receive area
+        X.peer_dst0[i] = map_to_cta(X.remote_set0 + my_slot * (uint32_t)(BM * 8), pr);
+        X.peer_bar0[i] = map_to_cta(X.bar0, pr);
+      }
       if (PAIR) {
-        const uint32_t base4 = stats_base + (uint32_t)L_STATS2_BYTES, row4 = (uint32_t)(quarter * 32 + lane) * 16u;
+        const uint32_t base4 = stats_base + (uint32_t)Cfg::STATS2_BYTES, row4 = (uint32_t)(quarter * 32 + lane) * 16u;
         X.local4_row = base4 + row4;
         X.local4_part = X.local4_row + (uint32_t)(wq * BM) * 16u;
         X.remote4_set0 = base4 + 4u * BM * 16u + row4;
-        X.peer_remote4_0 = map_to_cta(X.remote4_set0, xpeer);
+        X.peer_remote4_0 = map_to_cta(X.remote4_set0, rank ^ 2u);
       } else {
         X.local4_row = X.local4_part = X.remote4_set0 = X.peer_remote4_0 = 0;
       }
-      X.bar0 = xq_bar(0, quarter);
-      X.peer_bar0 = map_to_cta(X.bar0, xpeer);
       X.named_bar = 1 + quarter; X.wq = wq; X.rank = nrank;
     }
     const int col_cta = (int)nrank * LBN;
@@ -348,7 +380,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (my_row < p.M) {                                    // residual lines of my row -> L2 while the MMAs of the tile run
         const float* r = ep.res + (size_t)my_row * LN_N + col_cta;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(r + wq * 32));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (wq + 4) * 32));
+        if (CHUNKS == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (wq + 4) * 32));
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -361,7 +393,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- R1: v = acc + bias + residual, statistics of v
       float s_a = 0.f, q_a = 0.f, s_b = 0.f, q_b = 0.f;
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < CHUNKS; ++h) {
         const int cc = wq + 4 * h;
         const int col0 = col_cta + cc * 32;
         tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
@@ -391,12 +423,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tmem_st_wait();
       const float mc_a = s_a * (1.0f / 32.0f), mc_b = s_b * (1.0f / 32.0f);      // chunk means (before the sums are merged)
-      {
+      if (CHUNKS == 2) {
         const float d = mc_a - mc_b;
         q_a = q_a + q_b + 16.0f * d * d;                     // Chan: n_a n_b / (n_a + n_b) = 16
         s_a += s_b;
       }
-      RowStats st = exchange_row_stats(s_a, q_a, X, round++);
+      RowStats st = exchange_row_stats<NSPLIT, N_T>(s_a, q_a, X, round++);
       RowStats st2 = st;                                     // statistics of y (two-LN forms)
 
       const float* g_fin = ep.g1;
@@ -407,8 +439,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* yc = ep.y_consts + LN_N;
         float a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int chunk = (int)nrank * 8 + wq + 4 * h;     // 32-column chunk index within the 512-wide row
+        for (int h = 0; h < CHUNKS; ++h) {
+          const int chunk = (int)nrank * (LBN / 32) + wq + 4 * h;     // 32-column chunk index within the 512-wide row
           const float dl = (h == 0 ? mc_a : mc_b) - st.mean;
           a1 += mom[h][0] + dl * __ldg(yc + chunk);
           a2 += mom[h][1] + 2.0f * dl * mom[h][2] + dl * dl * __ldg(yc + 16 + chunk);
@@ -423,7 +455,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (ep.g2) {
         // ---------------- R1b: y = LN_a(v) in row layout, statistics of y
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < CHUNKS; ++h) {
           const int cc = wq + 4 * h;
           const int col0 = col_cta + cc * 32;
           tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
@@ -441,10 +473,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_st32(taddr + (uint32_t)(cc * 32), raw);
         }
         tmem_st_wait();
-        const float d = (s_a - s_b) * (1.0f / 32.0f);
-        q_a = q_a + q_b + 16.0f * d * d;
-        s_a += s_b;
-        st = exchange_row_stats(s_a, q_a, X, round++);
+        if (CHUNKS == 2) {
+          const float d = (s_a - s_b) * (1.0f / 32.0f);
+          q_a = q_a + q_b + 16.0f * d * d;
+          s_a += s_b;
+        }
+        st = exchange_row_stats<NSPLIT, N_T>(s_a, q_a, X, round++);
         g_fin = ep.g2; b_fin = ep.b2;
       }
 
@@ -457,7 +491,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (fuse2) { g_fin = ep.g2; b_fin = ep.b2; }
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < CHUNKS; ++h) {
         const int cc = wq + 4 * h;
         const int col = col_cta + cc * 32 + csub;
         tmem_ld32(taddr + (uint32_t)(cc * 32), raw);
@@ -520,50 +554,53 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   cluster_sync_all();                                       // the peer may still read this CTA's statistics through DSMEM
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
 }  // namespace
 
 namespace {
-template <bool PAIR>
+template <int SHAPE>
 int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
-  constexpr int CL = LnCfg<PAIR>::CLUSTER, TILE_M = PAIR ? 2 * BM : BM;
+  constexpr int CL = LnCfg<SHAPE>::CLUSTER, TILE_M = LnCfg<SHAPE>::PAIR ? 2 * BM : BM;
   static int max_clusters = 0;
   if (!max_clusters) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<PAIR>()));
+    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<SHAPE>()));
     // how many clusters of this shape the device can hold at once (GPC boundaries: 148 SMs hold 74 pairs but only ~34 quads)
     cudaLaunchConfig_t q = {};
-    q.gridDim = dim3(num_sms / CL * CL); q.blockDim = dim3(L_THREADS); q.dynamicSmemBytes = ln_smem_bytes<PAIR>();
+    q.gridDim = dim3(num_sms / CL * CL); q.blockDim = dim3(L_THREADS); q.dynamicSmemBytes = ln_smem_bytes<SHAPE>();
     cudaLaunchAttribute a[1];
     a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CL; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel<PAIR>, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel<SHAPE>, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
     max_clusters = n < num_sms / CL ? n : num_sms / CL;
   }
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int clusters = m_tiles < max_clusters ? m_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL * clusters); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = ln_smem_bytes<PAIR>(); cfg.stream = st;
+  cfg.gridDim = dim3(CL * clusters); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = ln_smem_bytes<SHAPE>(); cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_kernel<PAIR>, tmA, tmB, p, ep));
+  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_kernel<SHAPE>, tmA, tmB, p, ep));
   return 0;
 }
 }  // namespace
 
-// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- and 128-row boxes.  pair = cta_group::2 shape (cluster of 4).
-int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, bool pair,
+// tmB256 / tmB128: tensor maps of the [512, ld] weight with 256- and 128-row boxes.  shape: see LnCfg (0 pair of column halves,
+// 1 cta_group::2 quads, 2 four column quarters).
+int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, int shape,
             int num_sms, cudaStream_t st) {
   if (p.M <= 0) return 0;
   if (p.N != LN_N) { set_error("gemm_ln: N = %d, the fused LayerNorm epilogue is built for d_model = %d", p.N, LN_N); return -1; }
   if (p.K % BK != 0) { set_error("gemm_ln: K=%d not a multiple of %d", p.K, BK); return -1; }
-  return pair ? launch_ln<true>(tmA, tmB128, p, ep, num_sms, st) : launch_ln<false>(tmA, tmB256, p, ep, num_sms, st);
+  if (shape == 1) return launch_ln<1>(tmA, tmB128, p, ep, num_sms, st);
+  if (shape == 2) return launch_ln<2>(tmA, tmB128, p, ep, num_sms, st);
+  return launch_ln<0>(tmA, tmB256, p, ep, num_sms, st);
 }
 
 }  // namespace asr

@@ -305,7 +305,8 @@ def debug_gemm_ln(A: np.ndarray, W: np.ndarray, bias: np.ndarray, res: np.ndarra
                   g2: Optional[np.ndarray] = None, b2: Optional[np.ndarray] = None, f32_normed: bool = False, compact_rows: int = 0,
                   compact_seg: int = 0, split: int = 0, iters: int = 1, pair: int = 0, device: int = 0):
     """(out_f32 [M,512], out_op [M or compacted,512] as fp32, ms per launch) of the GEMM + residual + LayerNorm kernel (gemm_ln.cu).
-    pair: 0 = cluster of 2, 1 = cta_group::2 shape (cluster of 4), 2 = that shape with the one-pass second-LN statistics."""
+    pair: 0 = cluster of 2, 1 = cta_group::2 shape (cluster of 4), 2 = that shape with the one-pass second-LN statistics,
+    3 = cluster of 4 column quarters (small M)."""
     lib = _lib.load_library()
     f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
     A, W, bias, res, g1, b1, g2, b2 = map(f, (A, W, bias, res, g1, b1, g2, b2))

@@ -482,7 +482,7 @@ def run_ours(args):
             ach = gemm_flops[dom] / (t / 1e3) / 1e12
             all_gemm_ms = sum(v["ms_per_step"] for k, v in fam.items() if k.startswith("gemm"))
             all_gemm_flop = streams * (flop_sc - 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
-            fused = streams >= 160 and dom in ("gemm_out_proj", "gemm_ffn2") and not os.environ.get("ASR_B200_NO_FUSED_LN")
+            fused = streams >= 96 and dom in ("gemm_out_proj", "gemm_ffn2") and not os.environ.get("ASR_B200_NO_FUSED_LN")
             roof = {"kernel": f"{'gemm_ln_kernel' if fused else 'gemm_tc_kernel'} ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(args.workload if not args.streams else "", dom), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,

@@ -88,7 +88,7 @@ LN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("pair", [0, 1, 2], ids=["cluster2", "pair_cluster4", "pair_onepass_ln2"])
+@pytest.mark.parametrize("pair", [0, 1, 2, 3], ids=["cluster2", "pair_cluster4", "pair_onepass_ln2", "quad_columns"])
 @pytest.mark.parametrize("M,K,split,mode,offset", LN_CASES)
 def test_gemm_residual_layernorm_epilogue(M, K, split, mode, offset, pair):
     import functools
@@ -131,7 +131,7 @@ def test_gemm_layernorm_rows_do_not_depend_on_their_position():
     res = rng.standard_normal((M, 512)).astype(np.float32)
     g = (1.0 + 0.2 * rng.standard_normal(512)).astype(np.float32); b = (0.3 * rng.standard_normal(512)).astype(np.float32)
     perm = rng.permutation(M)
-    for pair in (0, 1, 2):
+    for pair in (0, 1, 2, 3):
         o1, p1, _ = debug_gemm_ln(A, W, bias, res, g, b, g, b, pair=pair)
         o2, p2, _ = debug_gemm_ln(A[perm], W, bias, res[perm], g, b, g, b, pair=pair)
         assert np.array_equal(o1[perm], o2) and np.array_equal(p1[perm], p2)

@@ -388,7 +388,7 @@ def test_reset_many_equals_fresh_sessions(engines):
 # ------------------------------------------------------------------------------------------------ fused GEMM + LayerNorm path
 @pytest.mark.parametrize("name", ["synth_noise", "testwav", "seq_reset_skip"])
 def test_fused_layernorm_path_matches_reference(name, packed_weights, golden, meta, monkeypatch):
-    """The engine takes the GEMM + residual + LayerNorm kernels (gemm_ln.cu) from 160 streams per step on; here they are forced
+    """The engine takes the GEMM + residual + LayerNorm kernels (gemm_ln.cu) from 96 streams per step on; here they are forced
     for a single stream so that the reference fixtures pin them too (both precisions), and compared with the separate-pass path."""
     from asr_streaming_b200 import Engine, PRECISION_EXACT, PRECISION_FAST
     case, mc = golden(name), meta["cases"][name]

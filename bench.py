@@ -516,8 +516,10 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, ms, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=args.ref_streams, threads=threads)
+            v2, _, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=4, threads=2)      # the reference's deployment setting (TORCH_THREAD=2, docker-compose.yml:22)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.ref_streams} streams x 2 steps of the same workload, batch 1 per stream, {threads} torch threads"}
+                                    "sample": f"{args.ref_streams} streams x 2 steps of the same workload, batch 1 per stream, {threads} torch threads",
+                                    "value_2_threads": v2}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

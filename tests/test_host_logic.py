@@ -483,3 +483,40 @@ def test_partition_streams_covers_everything_once():
         flat = [i for p in parts for i in p]
         assert flat == list(range(n))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_scheduler_chunk_windows_property():
+    """Property (hypothesis): for ANY split of an utterance into websocket messages, chunk k handed to the engine is the window
+    [k*10240 - 3200, k*10240 + 10240) of the utterance with 3200 leading zeros (stream.py:23, :159), messages of
+    <= 100 samples are dropped (stream.py:82), and the ring buffer compaction never corrupts a window."""
+    from hypothesis import given, settings, strategies as st
+    cfg = A.ModelConfig(max_batch=4, max_sessions=4)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=20000), min_size=1, max_size=30), st.integers(min_value=0, max_value=2**31 - 1))
+    def run(sizes, seed):
+        eng = FakeEngine(cfg)
+        sch = A.SessionScheduler(eng, backlog_chunks=3)
+        s = sch.open()
+        rng = np.random.default_rng(seed)
+        kept = [np.zeros(cfg.buffer_length, np.int16)]
+        for n in sizes:
+            msg = rng.integers(-3000, 3000, size=n).astype(np.int16)
+            room = sch.CAP - s.length_of_segment
+            if n > room:                                   # the server would apply back-pressure; drain first
+                while sch.tick().rows.size:
+                    pass
+            s.accept_waveform(msg)
+            if n > 100:
+                kept.append(msg)
+            if rng.random() < 0.5:
+                sch.tick()
+        while sch.tick().rows.size:
+            pass
+        utt = np.concatenate(kept)
+        n_chunks = (utt.size - cfg.chunk_length) // cfg.segment_length + 1 if utt.size >= cfg.chunk_length else 0
+        assert len(eng.calls) == n_chunks and s.chunk_processed == n_chunks
+        for k, (_, pcm) in enumerate(eng.calls):
+            assert np.array_equal(pcm[0], utt[k * cfg.segment_length:k * cfg.segment_length + cfg.chunk_length])
+
+    run()

@@ -39,8 +39,10 @@ inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 template <class F>
 void parallel_rows(int n, int max_threads, F&& work) {          // work(first, last) over [0, n) on a few host threads
+  // ASR_B200_HOST_THREADS caps the helper threads (one process per GPU on a shared host: cores / ranks)
+  static const int env_cap = [] { const char* v = getenv("ASR_B200_HOST_THREADS"); return v ? std::max(1, atoi(v)) : 1 << 20; }();
   const int hw = (int)std::thread::hardware_concurrency();
-  const int nt = std::max(1, std::min({max_threads, hw > 0 ? hw : 1, n / 64 + 1}));
+  const int nt = std::max(1, std::min({max_threads, env_cap, hw > 0 ? hw : 1, n / 64 + 1}));
   if (nt == 1) { work(0, n); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { work((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); });

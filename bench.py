@@ -264,6 +264,8 @@ def run_ours(args):
     import torch
     from asr_streaming_b200 import Engine, ModelConfig, PRECISION_EXACT, PRECISION_FAST, pack_weights, random_weights
     rank, world, local = dist_env()
+    if world > 1:                                           # ranks share the host: split its cores between their gather / gate threads
+        os.environ.setdefault("ASR_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 8) // world)))
     # Only the final JSON line may reach stdout: NCCL / torchrun chatter is routed to stderr for the duration of the run.
     sys.stdout.flush()
     real_stdout = os.dup(1)

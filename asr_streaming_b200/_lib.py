@@ -51,6 +51,10 @@ SIGNATURES = {
     "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
     "asr_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "asr_collect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
+    "asr_submit_rings": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "asr_wait_inputs": (C.c_int, [C.c_void_p]),
+    "asr_host_alloc": (C.c_void_p, [C.c_uint64]),
+    "asr_host_free": (C.c_int, [C.c_void_p]),
     "asr_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "asr_run_staged": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "asr_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),

@@ -136,6 +136,7 @@ struct AsrEngine {
   size_t h_stage_bytes = 0;
   size_t h_out_off = 0;
   DevBuf d_pcm2, d_slots2;
+  DevBuf d_src_off[2];          // asr_submit_rings: element offsets of the step's chunks inside the pinned session rings
   void* act_pcm = nullptr;      // input buffers the kernels of the step being enqueued read
   int* act_slots = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -583,6 +584,43 @@ int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int 
   return 0;
 }
 
+// Same as submit_step, but the batch is assembled by the GPU: the chunks are read straight out of the sessions' pinned audio rings
+// (zero-copy over PCIe, gather_rings_kernel on the copy stream) — no host-side gather, no staging copy.
+int submit_rings(AsrEngine* e, int n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
+                 bool want_lp, int* ticket) {
+  const int b = e->cur_buf;
+  if (e->pend[b].active) { set_error("two steps are already in flight: asr_collect the oldest ticket first"); return -1; }
+  if (check_step_args(e, n, slots)) return -1;
+  if (n && (!base || !rows || !offsets)) { set_error("null argument"); return -1; }
+  const auto t0 = std::chrono::steady_clock::now();
+  if (n) {
+    ASR_CUDA_OK(cudaSetDevice(e->device));
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, base) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      set_error("asr_submit_rings: the audio rings must live in pinned host memory (asr_host_alloc)"); return -1;
+    }
+    const int16_t* base_dev = reinterpret_cast<const int16_t*>(pa.devicePointer);
+    uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_buf[b]);
+    long long* h_off = reinterpret_cast<long long*>(hs);                         // the PCM area of the staging buffer is unused on this path
+    for (int i = 0; i < n; ++i) h_off[i] = (long long)rows[i] * row_stride + offsets[i];
+    memcpy(hs + slots_off(e), slots, 4 * (size_t)n);
+    ASR_CUDA_OK(cudaMemcpyAsync(e->d_src_off[b].p, h_off, 8 * (size_t)n, cudaMemcpyHostToDevice, e->copy_stream));
+    ASR_CUDA_OK(cudaMemcpyAsync(dev_slots(e, b), hs + slots_off(e), 4 * (size_t)n, cudaMemcpyHostToDevice, e->copy_stream));
+    if (gather_rings_launch(base_dev, e->d_src_off[b].as<long long>(), reinterpret_cast<int16_t*>(dev_pcm(e, b)), n, e->geo.chunk_len, e->copy_stream)) return -1;
+    ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
+    ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+    use_buffer(e, b);
+    if (run_pipeline(e, n, ASR_PCM_I16, e->geo.n_layers, true, want_lp)) return -1;
+    if (enqueue_d2h(e, b, n, want_lp)) return -1;
+    ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
+  }
+  e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
+  e->cur_buf ^= 1;
+  if (ticket) *ticket = b;
+  return 0;
+}
+
 int collect_step(AsrEngine* e, int ticket, const AsrStepOut* out) {
   if (ticket < 0 || ticket > 1 || !e->pend[ticket].active) { set_error("asr_collect: ticket %d is not in flight", ticket); return -1; }
   auto& pd = e->pend[ticket];
@@ -626,7 +664,7 @@ void destroy_engine(AsrEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
+  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
@@ -739,7 +777,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     // ---- activations
     const int B = cfg->max_batch, M = B * g.rows, Mc = B * g.seg_rows;
     const size_t esz = g.split ? 4 : 2;
-    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
+    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->d_src_off[0].alloc(8 * (size_t)B) || e->d_src_off[1].alloc(8 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
         e->x2.alloc(4 * (size_t)M * d) || e->q.alloc(4 * (size_t)M * d) || e->rc_kv.alloc(esz * (size_t)B * 2 * g.rc_rows * d) ||
         e->logits.alloc(4 * (size_t)Mc * g.vocab) || e->d_logprobs.alloc(4 * (size_t)Mc * g.vocab) || e->d_argmax.alloc(4 * (size_t)Mc) ||
         e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B)) break;
@@ -978,6 +1016,37 @@ int asr_submit(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, i
   if (!e || !ticket) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   return submit_step(e, n, slots, pcm, fmt, want_logprobs != 0, ticket);
+}
+
+int asr_submit_rings(AsrEngine* e, int32_t n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows,
+                     const int64_t* offsets, int32_t want_logprobs, int32_t* ticket) {
+  if (!e || !ticket) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  return submit_rings(e, n, slots, base, row_stride, rows, offsets, want_logprobs != 0, ticket);
+}
+
+/* Blocks until the input transfers (H2D copies / ring gathers) of every submitted step have completed: after it returns the caller may
+ * overwrite the host memory those steps read from. */
+int asr_wait_inputs(AsrEngine* e) {
+  if (!e) { set_error("null engine"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->copy_stream));
+  return 0;
+}
+
+/* Pinned, device-mapped host memory for the scheduler's session audio rings (asr_submit_rings reads them over PCIe). */
+void* asr_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    set_error("cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+int asr_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) { set_error("cudaFreeHost failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+  return 0;
 }
 
 int asr_collect(AsrEngine* e, int32_t ticket, const AsrStepOut* out) {

@@ -105,6 +105,8 @@ int beam_reset_launch(const BeamParams& P, int slot /* -1: all */, int n_slots_a
 // fp32 [n] -> bf16 hi (+ lo) weight conversion at engine creation
 int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int lo_off, cudaStream_t st);
 int fill_i32(int* p, int v, size_t n, cudaStream_t st);
+// device-side batch assembly from pinned host rings (zero-copy reads): dst[i] = base[src_off[i] .. + chunk_len)
+int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st);
 // endpoint on many sessions at once: past_len = n_frames = 0, prev_id = last_tok = -1 for the listed slots
 int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, cudaStream_t st);
 // per-utterance CMVN over the frames of one call (TA:compliance/kaldi.py:603-606, subtract_mean)

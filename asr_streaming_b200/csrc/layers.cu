@@ -800,6 +800,21 @@ __global__ void reset_slots_kernel(const int* __restrict__ slots, int n, int* pa
   }
 }
 
+// Batch assembly on the device: chunk i = chunk_len int16 samples at base + src_off[i] (pinned, mapped host memory: the sessions'
+// audio rings, read over PCIe) -> row i of the step's PCM buffer.  One CTA per chunk, 16-byte loads when the source is aligned.
+__global__ void __launch_bounds__(256) gather_rings_kernel(const int16_t* __restrict__ base, const long long* __restrict__ src_off,
+                                                           int16_t* __restrict__ dst, int chunk_len) {
+  const int16_t* s = base + src_off[blockIdx.x];
+  int16_t* d = dst + (size_t)blockIdx.x * chunk_len;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0 && (chunk_len & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (int i = threadIdx.x; i < chunk_len / 8; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < chunk_len; i += blockDim.x) d[i] = s[i];
+  }
+}
+
 __global__ void fill_i32_kernel(int* p, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -873,6 +888,13 @@ int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cuda
 int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, cudaStream_t st) {
   if (n <= 0) return 0;
   reset_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(slots, n, past_len, n_frames, prev_id, last_tok);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gather_rings_kernel<<<n, 256, 0, st>>>(base_dev, src_off, dst, chunk_len);
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -64,6 +64,7 @@ class Engine:
         self._h = h
         self.S = cfg.seg_rows
         self.beam = 0
+        self._host_blocks = []
 
     def set_beam(self, beam: int, cand_k: int = 8) -> None:
         """Enable CTC prefix beam search (beam <= 16, cand_k <= 8) as part of every step; 0 disables."""
@@ -75,6 +76,9 @@ class Engine:
         if getattr(self, "_h", None):
             self.lib.asr_engine_destroy(self._h)
             self._h = None
+            for p in getattr(self, "_host_blocks", []):
+                self.lib.asr_host_free(p)
+            self._host_blocks = []
 
     def __del__(self):
         try:
@@ -184,6 +188,35 @@ class Engine:
         t = C.c_int32()
         _lib.check(self.lib, self.lib.asr_submit(self._h, n, sl.ctypes.data, a.ctypes.data, fmt, int(want_logprobs), C.byref(t)), "asr_submit")
         return (t.value, n, want_logprobs)
+
+    def submit_rings(self, slots: Sequence[int], audio: np.ndarray, rows: np.ndarray, offsets: np.ndarray, want_logprobs: bool = False):
+        """submit() with the batch assembled by the GPU: chunk i = audio[rows[i], offsets[i] : offsets[i] + chunk_length], read by a
+        gather kernel straight out of ``audio`` (which must come from ``host_alloc``) — no host-side copy."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, np.int32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = int(sl.size)
+        assert audio.dtype == np.int16 and audio.ndim == 2 and audio.flags.c_contiguous and rows.size == n and offsets.size == n
+        t = C.c_int32()
+        _lib.check(self.lib, self.lib.asr_submit_rings(self._h, n, sl.ctypes.data, audio.ctypes.data, audio.shape[1], rows.ctypes.data,
+                                                       offsets.ctypes.data, int(want_logprobs), C.byref(t)), "asr_submit_rings")
+        return (t.value, n, want_logprobs)
+
+    def wait_inputs(self) -> None:
+        """Returns once every submitted step has read its inputs (the host memory they came from may be rewritten)."""
+        _lib.check(self.lib, self.lib.asr_wait_inputs(self._h), "asr_wait_inputs")
+
+    def host_alloc(self, shape, dtype=np.int16) -> np.ndarray:
+        """Zero-filled numpy array in pinned, device-mapped host memory (for the scheduler's audio rings); freed with the engine."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.lib.asr_host_alloc(nbytes)
+        if not ptr:
+            raise _lib.AsrLibraryError("asr_host_alloc failed: " + (self.lib.asr_last_error() or b"").decode("utf-8", "replace"))
+        self._host_blocks.append(ptr)
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+        a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        a[...] = 0
+        return a
 
     def collect(self, ticket) -> StepResult:
         t, n, want = ticket

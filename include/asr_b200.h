@@ -128,6 +128,15 @@ ASR_API int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* 
  * in flight, so the input copy of step k+1 overlaps the kernels of step k.  Steps execute in submission order. */
 ASR_API int asr_submit(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t want_logprobs, int32_t* ticket);
 ASR_API int asr_collect(AsrEngine* e, int32_t ticket, const AsrStepOut* out);
+/* asr_submit with the batch assembled by the GPU: chunk i is read straight out of the sessions' audio rings at
+ * base[rows[i]*row_stride + offsets[i]] (int16; `base` must be pinned host memory from asr_host_alloc) by a gather kernel on the copy
+ * stream — replaces the torch.cat / slicing of Stream.audio_stream (stream.py:78-87, :159-160) without a host-side copy.  The rings
+ * may be appended to at any time; rewriting a region a submitted step reads (buffer compaction) needs asr_wait_inputs first. */
+ASR_API int asr_submit_rings(AsrEngine* e, int32_t n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows,
+                             const int64_t* offsets, int32_t want_logprobs, int32_t* ticket);
+ASR_API int asr_wait_inputs(AsrEngine* e);
+ASR_API void* asr_host_alloc(uint64_t bytes);
+ASR_API int asr_host_free(void* p);
 
 /* Same, split for pipelining / device-resident timing: stage = H2D of inputs; run = kernels only (async on the
  * engine stream); fetch = D2H of results + synchronise. */

@@ -318,7 +318,8 @@ def test_pipelined_submit_collect_equals_sync(engines):
 
 
 # ------------------------------------------------------------------------------------------------ scheduler on the real engine
-def test_scheduler_ticks_match_reference_texts(engines, golden, meta):
+@pytest.mark.parametrize("device_gather", [False, True], ids=["host_gather", "device_gather"])
+def test_scheduler_ticks_match_reference_texts(engines, golden, meta, device_gather):
     """Websocket-style delivery (ragged message sizes, streams joining at different times) through SessionScheduler.tick:
     native pinned gather (asr_gather_pcm) + one asr_step per tick.  Every stream's text / trailing-blank after each of
     its chunks must equal the reference's batch-1 greedy_search on the accumulated emission (fixtures)."""
@@ -326,7 +327,7 @@ def test_scheduler_ticks_match_reference_texts(engines, golden, meta):
     e = engines(engines.EXACT)
     names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale", "edge_dc"]
     cases = [golden(n) for n in names]
-    sch = SessionScheduler(e, capacity=16, backlog_chunks=3)
+    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, device_gather=device_gather)   # device: asr_submit_rings reads the pinned rings
     rng = np.random.default_rng(5)
     sess = [sch.open() for _ in names]
     pos = [0] * len(names)

@@ -520,3 +520,29 @@ def test_scheduler_chunk_windows_property():
             assert np.array_equal(pcm[0], utt[k * cfg.segment_length:k * cfg.segment_length + cfg.chunk_length])
 
     run()
+
+
+def test_weights_from_checkpoint_reads_the_reference_layout(tmp_path, oracle_weights):
+    """A checkpoint file in the reference's layout ({'hyper_parameters', 'state_dict': {'encoder', 'decoder'}},
+    recognition.py:149-159) packs to the same blob as the state dict itself; when the reference tree is present the file is also
+    produced by the reference's own modules' state_dict()."""
+    import torch
+    enc = {k[len("encoder."):]: torch.from_numpy(v) for k, v in oracle_weights.items() if k.startswith("encoder.")}
+    dec = {k[len("decoder."):]: torch.from_numpy(v) for k, v in oracle_weights.items() if k.startswith("decoder.")}
+    path = tmp_path / "model.ckpt"
+    torch.save({"hyper_parameters": {"encoder": {}, "decoder": {}}, "state_dict": {"encoder": enc, "decoder": dec}}, path)
+    blob = A.weights_from_checkpoint(str(path), A.ModelConfig())
+    assert np.array_equal(blob, A.pack_weights(oracle_weights))
+    from oracle import ref_import
+    if ref_import.available():
+        ref_import.load_reference()
+        from lightspeech.modules.encoder import StreamingAcousticEncoder      # encoder.py:73-147
+        from lightspeech.modules.decoder import CTCDecoder                     # decoder.py:60-70
+        e = StreamingAcousticEncoder(input_dim=128, d_model=512, segment_length=64, left_context_length=128, right_context_length=16,
+                                     ffn_dim=2048, num_layers=20, subsampling_factor=4, num_heads=8, dropout=0.1, activation="gelu",
+                                     max_memory_size=0, tanh_on_mem=True)
+        d = CTCDecoder(512, 512, 804)
+        e.load_state_dict(enc, strict=True)
+        d.load_state_dict(dec, strict=True)
+        torch.save({"hyper_parameters": {}, "state_dict": {"encoder": e.state_dict(), "decoder": d.state_dict()}}, path)
+        assert np.array_equal(A.weights_from_checkpoint(str(path), A.ModelConfig()), blob)

@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -16,18 +15,35 @@ FBANK_MELSPEC128, FBANK_KALDI80 = 0, 1
 BEAM_MAX_LEN = 256
 
 
-@dataclass
 class StepResult:
-    """Per-step outputs for n streams (S = segment rows)."""
-    argmax_ids: np.ndarray                 # [n, S] int32
-    new_tokens: List[np.ndarray]           # n arrays of the ids appended this chunk (collapsed, blank-free)
-    blank_frames: np.ndarray               # [n] int32
-    has_token: np.ndarray                  # [n] bool
-    logprobs: Optional[np.ndarray]         # [n, S, V] float32 or None
-    beam_tokens: Optional[List[np.ndarray]] = None   # n arrays: best prefix-beam hypothesis of the utterance so far
-    beam_score: Optional[np.ndarray] = None          # [n] log-probability of that hypothesis
-    n_new: Optional[np.ndarray] = None               # [n] int32: len(new_tokens[i])
-    new_tokens_padded: Optional[np.ndarray] = None   # [n, S] int32, row i valid in [:n_new[i]] (struct-of-arrays form)
+    """Per-step outputs for n streams (S = segment rows).  ``new_tokens`` / ``beam_tokens`` (lists of per-stream arrays) are built on
+    first access from the padded arrays the device returned: a tick over thousands of sessions never pays for them unless asked."""
+
+    def __init__(self, argmax_ids, new_tokens, blank_frames, has_token, logprobs, beam_tokens=None, beam_score=None, n_new=None,
+                 new_tokens_padded=None, beam_tokens_padded=None, beam_len=None):
+        self.argmax_ids = argmax_ids                 # [n, S] int32
+        self._new_tokens = new_tokens                # n arrays of the ids appended this chunk (collapsed, blank-free) or None (lazy)
+        self.blank_frames = blank_frames             # [n] int32
+        self.has_token = has_token                   # [n] bool
+        self.logprobs = logprobs                     # [n, S, V] float32 or None
+        self._beam_tokens = beam_tokens              # n arrays: best prefix-beam hypothesis of the utterance so far, or None (lazy / no beam)
+        self.beam_score = beam_score                 # [n] log-probability of that hypothesis
+        self.n_new = n_new                           # [n] int32: len(new_tokens[i])
+        self.new_tokens_padded = new_tokens_padded   # [n, S] int32, row i valid in [:n_new[i]] (struct-of-arrays form)
+        self.beam_tokens_padded = beam_tokens_padded  # [n, BEAM_MAX_LEN] int32, row i valid in [:beam_len[i]]
+        self.beam_len = beam_len
+
+    @property
+    def new_tokens(self) -> List[np.ndarray]:
+        if self._new_tokens is None:
+            self._new_tokens = [self.new_tokens_padded[i, :self.n_new[i]].copy() for i in range(len(self.n_new))]
+        return self._new_tokens
+
+    @property
+    def beam_tokens(self) -> Optional[List[np.ndarray]]:
+        if self._beam_tokens is None and self.beam_tokens_padded is not None:
+            self._beam_tokens = [self.beam_tokens_padded[i, :self.beam_len[i]].copy() for i in range(len(self.beam_len))]
+        return self._beam_tokens
 
     def last_blank(self, i: int) -> float:
         """The reference's ``last_blank`` (recognition.py:38-43): python float 0.04*T when the segment has no
@@ -163,12 +179,10 @@ class Engine:
 
     @staticmethod
     def _result(bufs, n) -> StepResult:
-        new = [bufs["newtok"][i, :bufs["nnew"][i]].copy() for i in range(n)]
-        r = StepResult(bufs["argmax"], new, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"],
+        r = StepResult(bufs["argmax"], None, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"],
                        n_new=bufs["nnew"], new_tokens_padded=bufs["newtok"])
         if "btok" in bufs:
-            r.beam_tokens = [bufs["btok"][i, :bufs["blen"][i]].copy() for i in range(n)]
-            r.beam_score = bufs["bscore"]
+            r.beam_tokens_padded, r.beam_len, r.beam_score = bufs["btok"], bufs["blen"], bufs["bscore"]
         return r
 
     def step(self, slots: Sequence[int], pcm: np.ndarray, want_logprobs: bool = False) -> StepResult:

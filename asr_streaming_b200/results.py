@@ -85,8 +85,9 @@ def tick_messages(sched, res, vocab=None) -> Dict[int, List[str]]:
         s = sched._by_row[int(r)]
         if res.final.size and res.final[j]:
             toks = res.final_tokens.get(s.id, [])
-            if res.beam_tokens is not None:
-                toks = [int(t) for t in res.beam_tokens[j]]
+            bt = res.beam_row(j)
+            if bt is not None:
+                toks = [int(t) for t in bt]
             utt = float(res.final_utt_length.get(s.id, 0.0))
             total = float(sched.chunk_processed_total[r]) * seg_s
             m = final_message(str(s.id), int(sched.segment[r]) - 1, utt, total, ids_to_text(toks, vocab))

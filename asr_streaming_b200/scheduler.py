@@ -93,12 +93,27 @@ class TickResult:
     n_new: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))          # [n]
     new_tokens: np.ndarray = field(default_factory=lambda: np.zeros((0, 0), np.int32))  # [n, S], valid [:n_new]
     logprobs: Optional[np.ndarray] = None                            # [n, S, V] when requested
-    beam_tokens: Optional[List[np.ndarray]] = None
+    step: object = None                                              # the engine's StepResult (argmax ids, beam hypotheses, ...)
     skipped: List[StreamSession] = field(default_factory=list)       # VAD-gated chunks (not run)
     final: np.ndarray = field(default_factory=lambda: np.zeros(0, bool))              # [n] endpoint fired after this chunk
     final_rule: List[Optional[str]] = field(default_factory=list)    # rule name per session (None if not final)
     final_tokens: Dict[int, List[int]] = field(default_factory=dict)  # session id -> tokens of the finished segment
     final_utt_length: Dict[int, float] = field(default_factory=dict)  # session id -> seconds decoded in the finished segment (stream.py:132-134)
+
+    @property
+    def beam_tokens(self) -> Optional[List[np.ndarray]]:
+        """Best prefix-beam hypothesis per served stream (None without beam); built on first access."""
+        return self.step.beam_tokens if self.step is not None else None
+
+    def beam_row(self, j: int) -> Optional[np.ndarray]:
+        """Best prefix-beam hypothesis of served stream j without materialising the others."""
+        st = self.step
+        if st is None:
+            return None
+        if getattr(st, "beam_tokens_padded", None) is not None:
+            return st.beam_tokens_padded[j, :st.beam_len[j]]
+        bt = st.beam_tokens
+        return None if bt is None else bt[j]
 
     @property
     def sessions(self) -> List[StreamSession]:
@@ -389,7 +404,7 @@ class SessionScheduler:
         self.trailing[rows] = np.where(has, lb, self.trailing[rows] + self._chunk_s)
         self.contain_token[rows] |= has
         res.rows = rows
-        res.n_new, res.new_tokens, res.logprobs, res.beam_tokens = n_new, new_tok, out.logprobs, out.beam_tokens
+        res.n_new, res.new_tokens, res.logprobs, res.step = n_new, new_tok, out.logprobs, out
         res.final = np.zeros(n, bool)
         res.final_rule = [None] * n
         self._endpoints(rows, res, rows)

@@ -482,3 +482,34 @@ def test_streaming_attention_low_latency_geometry(packed_weights, golden, meta, 
         em_old, _, _ = _run_case(e, case, mc, O.LOW_LATENCY)
     assert np.abs(em - case["emission"]).max() < FAST_TOL
     assert np.array_equal(em, em_old)
+
+
+def test_full_size_batch_is_consistent_with_small_batches(packed_weights):
+    """BASELINE configs[3] size: 4096 streams in one step (M = 81,920 rows: cta_group::2 GEMMs, gemm_ln in its pair shape with the
+    one-pass second LayerNorm, TMA streaming attention).  Size-independent properties: streams fed the same audio give bit-identical
+    results wherever they sit in the batch, and every stream agrees with the same audio run in a batch of 8 (other kernel shapes:
+    separate LayerNorm passes, CTA-per-stream attention) within the FAST tolerance, step after step (left context 0 / 16 / 32)."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(31)
+    n, kinds, T = 4096, 8, 4
+    base = rng.integers(-4000, 4000, size=(T, kinds, O.CANONICAL.chunk_length)).astype(np.int16)
+    which = rng.integers(0, kinds, size=n)
+    which[:kinds] = np.arange(kinds)
+    with Engine(model_cfg(PRECISION_FAST, max_batch=kinds, max_sessions=kinds), packed_weights) as small:
+        ss = [small.open_session() for _ in range(kinds)]
+        ref = [small.step(ss, base[t], want_logprobs=True) for t in range(T)]
+    with Engine(model_cfg(PRECISION_FAST, max_batch=n, max_sessions=n), packed_weights) as big:
+        sl = [big.open_session() for _ in range(n)]
+        for t in range(T):
+            r = big.step(sl, base[t][which], want_logprobs=(t == T - 1))
+            for k in range(kinds):
+                rows = np.nonzero(which == k)[0]
+                assert (r.argmax_ids[rows] == r.argmax_ids[rows[0]]).all(), (t, k)          # same audio, same kernels: identical
+                assert np.array_equal(r.blank_frames[rows], np.full(rows.size, r.blank_frames[rows[0]]))
+            if t == T - 1:
+                lp = r.logprobs[:kinds]
+                err = np.abs(lp - ref[t].logprobs).max()
+                report(f"FAST 4096-stream step vs batch of 8 (different kernel shapes): logprob max-abs {err:.3e}")
+                assert err < FAST_TOL
+                safe = margins(ref[t].logprobs) > 2 * FAST_TOL
+                assert np.array_equal(r.argmax_ids[:kinds][safe], ref[t].argmax_ids[safe])

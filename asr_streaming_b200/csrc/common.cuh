@@ -49,6 +49,19 @@ struct Geo {
 
 void set_error(const char* fmt, ...);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a process that drives several GPUs (GpuRouter: one Engine per
+// device) must set it once on each.  `done` is a per-call-site table indexed by device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device_index() { int d = 0; cudaGetDevice(&d); return (d < 0 || d >= kMaxDevices) ? 0 : d; }
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, size_t bytes, size_t (&done)[kMaxDevices]) {
+  const int d = current_device_index();
+  if (done[d] >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done[d] = bytes;
+  return e;
+}
+
 // Programmatic dependent launch: every kernel of the per-step chain is launched with programmaticStreamSerialization, calls
 // pdl_launch_dependents() early (the next kernel's CTAs may be scheduled as soon as SM resources free up and run their
 // prologue: barrier init, TMEM allocation, tensor-map prefetch, table loads) and pdl_wait() before its first access to memory

@@ -177,11 +177,8 @@ template <int NC, typename PcmT, bool KALDI>
 int launch(const FbankParams& P, int n_streams, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (NC + NC + 2) + sizeof(float) * ((P.frame_len + 3) & ~3) + sizeof(float2) * kWarps * 2 * NC +
                       ((P.n_samples * sizeof(PcmT) + 15) & ~(size_t)15);
-  static size_t attr = 0;
-  if (smem > attr) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<NC, PcmT, KALDI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(fbank_kernel<NC, PcmT, KALDI>, smem, attr_done));
   ASR_CUDA_OK(launch_pdl(fbank_kernel<NC, PcmT, KALDI>, dim3(n_streams), dim3(kWarps * 32), smem, st, P));
   return 0;
 }

@@ -565,7 +565,8 @@ namespace {
 template <int SHAPE>
 int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
   constexpr int CL = LnCfg<SHAPE>::CLUSTER, TILE_M = LnCfg<SHAPE>::PAIR ? 2 * BM : BM;
-  static int max_clusters = 0;
+  static int max_clusters_dev[kMaxDevices] = {0};
+  int& max_clusters = max_clusters_dev[current_device_index()];
   if (!max_clusters) {
     ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<SHAPE>()));
     // how many clusters of this shape the device can hold at once (GPC boundaries: 148 SMs hold 74 pairs but only ~34 quads)

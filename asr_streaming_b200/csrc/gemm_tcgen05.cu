@@ -355,11 +355,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 template <class Epi>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    attr_set = true;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2_kernel<Epi>, (size_t)P_SMEM_BYTES, attr_done));
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P_BN - 1) / P_BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
   ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi>, dim3(2 * pairs), dim3(kThreads), P_SMEM_BYTES, st, tmA, tmB128, p, epi));
@@ -369,11 +366,8 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmPro
 template <int BN, class Epi>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
   using Cfg = TileCfg<BN, EpiWarps<Epi>::value>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc_kernel<BN, Epi>, (size_t)Cfg::kSmemBytes, attr_done));
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   ASR_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, Epi>, dim3(grid), dim3(Cfg::kThreadsCta), Cfg::kSmemBytes, st, tmA, tmB, p, epi));

@@ -670,11 +670,8 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
 template <int ROWS>
 int attention_stream_launch(const AttnParams<bf16>& P, int n_streams, int num_sms, cudaStream_t st) {
   const size_t smem = (size_t)4 * AS_HALF_BYTES + 1024;
-  static bool attr = false;
-  if (!attr) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(attention_stream_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(attention_stream_kernel<ROWS>, smem, attr_done));
   const int grid = n_streams < num_sms ? n_streams : num_sms;
   ASR_CUDA_OK(launch_pdl(attention_stream_kernel<ROWS>, dim3(grid), dim3(AsCfg<ROWS>::THREADS), smem, st, *P.h_tm_cache, *P.h_tm_rc, P, n_streams));
   return 0;
@@ -684,11 +681,8 @@ template <int ROWS>
 int attention_mma_launch(const AttnParams<bf16>& P, int n_streams, cudaStream_t st) {
   const int kmax = P.left + P.seg_rows + P.rc_rows;
   const size_t smem = (size_t)(2 * kmax + 1) * AM_ROWB;
-  static size_t attr = 0;
-  if (smem > attr) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(attention_mma_kernel<ROWS>, smem, attr_done));
   ASR_CUDA_OK(launch_pdl(attention_mma_kernel<ROWS>, dim3(n_streams), dim3(AM_WARPS * 32), smem, st, P));
   return 0;
 }
@@ -697,11 +691,8 @@ template <typename T, int ROWS>
 int attention_launch_rows(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
   static_assert(ROWS % 4 == 0, "ROWS must be a multiple of 4");
   const size_t smem = sizeof(float) * AT_WARPS * (ROWS * AT_DH + AT_MAXK * AT_KST + AT_MAXK * ROWS);
-  static bool attr = false;
-  if (!attr) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(attention_kernel<T, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(attention_kernel<T, ROWS>, smem, attr_done));
   dim3 grid(n_streams, P.n_heads / AT_WARPS);
   ASR_CUDA_OK(launch_pdl(attention_kernel<T, ROWS>, grid, dim3(AT_WARPS * 32), smem, st, P));
   return 0;
@@ -847,7 +838,8 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
     if (P.n_heads == AM_WARPS && P.d == 512 && P.lo_off == 0 && !getenv("ASR_B200_DEBUG_SIMT_ATTENTION")) {
       const char* sm_env = getenv("ASR_B200_ATTN_STREAM_MIN");       // read per launch so a test can flip it inside one process
       const int stream_min = sm_env ? atoi(sm_env) : 148;       // measured on B200: wins from 256 streams per step on (1.98 vs 2.00 ms)
-      static const int num_sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+      int num_sms = 148;
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, current_device_index());
       const bool tma_ok = P.h_tm_cache && P.h_tm_rc && P.rc_rows == AS_RC_ROWS && P.rows == P.seg_rows + P.rc_rows && P.ring <= AS_RING_ROWS &&
                           P.ring % P.seg_rows == 0 && P.left % P.seg_rows == 0 && (P.seg_rows == 16 || P.seg_rows == 8);
       if (n_streams >= stream_min && tma_ok) {         // persistent, double-buffered streaming kernel for large batches

@@ -456,6 +456,8 @@ class GpuRouter:
     def __init__(self, cfg: ModelConfig, weights: np.ndarray, devices: Sequence[int], **sched_kw):
         from .engine import Engine
         self.schedulers = [SessionScheduler(Engine(cfg, weights, d), **sched_kw) for d in devices]
+        for g, sc in enumerate(self.schedulers):
+            sc._next_id = g << 32                      # session ids stay unique across the GPUs of the box
 
     def open(self) -> StreamSession:
         g = min(range(len(self.schedulers)), key=lambda i: len(self.schedulers[i].sessions))

@@ -513,3 +513,29 @@ def test_full_size_batch_is_consistent_with_small_batches(packed_weights):
                 assert err < FAST_TOL
                 safe = margins(ref[t].logprobs) > 2 * FAST_TOL
                 assert np.array_equal(r.argmax_ids[:kinds][safe], ref[t].argmax_ids[safe])
+
+
+def test_gpu_router_two_devices(packed_weights, golden, meta):
+    """One Engine + scheduler per GPU inside one process (GpuRouter): sessions placed least-loaded, ticks on one host thread per
+    GPU, results equal to the reference fixtures on both devices.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from asr_streaming_b200 import GpuRouter, ids_to_text
+    names = ["synth_noise", "testwav", "synth_tone", "edge_dc"]
+    cases = [golden(n) for n in names]
+    from asr_streaming_b200 import PRECISION_EXACT
+    router = GpuRouter(model_cfg(PRECISION_EXACT, max_batch=8, max_sessions=8), packed_weights, [0, 1])
+    sess = [router.open() for _ in names]
+    assert sorted(s.gpu for s in sess) == [0, 0, 1, 1] and len({s.id for s in sess}) == 4
+    chunks = [chunks_i16(c["pcm"]) for c in cases]
+    for k in range(max(len(c) for c in chunks)):
+        for i, s in enumerate(sess):
+            if k < len(chunks[i]):
+                s.accept_waveform(chunks[i][k][O.CANONICAL.buffer_length:])      # the 10,240 new samples of chunk k
+        router.tick()
+        for i, s in enumerate(sess):
+            if k < len(chunks[i]):
+                assert ids_to_text(s.tokens, meta["vocab"]) == meta["cases"][names[i]]["texts"][k], (names[i], k)
+    for s in sess:
+        router.close(s)

@@ -539,3 +539,37 @@ def test_gpu_router_two_devices(packed_weights, golden, meta):
                 assert ids_to_text(s.tokens, meta["vocab"]) == meta["cases"][names[i]]["texts"][k], (names[i], k)
     for s in sess:
         router.close(s)
+
+
+def test_lightning_asr_v1_batched_call_pattern(packed_weights, golden, meta):
+    """The v1 batcher's call pattern (streaming_decoder_v1/streaming_asr.py:94-112): ONE model.stream() for a list of streams at
+    different progress, then per stream `emission[idx]`, torch.cat onto its accumulated emission and greedy_search.  The reference's
+    batched infer is wrong for mixed progress (TA:emformer.py:392 reads element 0's past_length); here every stream must equal its
+    own batch-1 fixture."""
+    import torch
+    from asr_streaming_b200 import LightningASR, PRECISION_EXACT, greedy_search
+    names = ["synth_noise", "testwav", "synth_tone"]
+    cases = [golden(n) for n in names]
+    model = LightningASR(weights=packed_weights, cfg=model_cfg(PRECISION_EXACT, max_batch=4, max_sessions=8), vocab=meta["vocab"])
+    state_init = model.init_state()
+    audio = [torch.cat([torch.zeros(3200), torch.from_numpy(to_float(c["pcm"]))]) for c in cases]
+    states = [state_init] * 3
+    emissions = [torch.Tensor([]) for _ in names]
+    done = [0, 0, 0]
+    start = [0, 2, 1]
+    for tick in range(20):
+        idx = [i for i in range(3) if tick >= start[i] and audio[i].numel() >= 13440]
+        if not idx:
+            continue
+        em, length, new_states = model.stream([audio[i][None, :13440] for i in idx], 16000, [states[i] for i in idx])
+        for j, i in enumerate(idx):
+            states[i] = new_states[j]
+            emissions[i] = torch.cat((emissions[i], em[j]), dim=0)
+            text, last_blank = greedy_search(emissions[i])
+            mc = meta["cases"][names[i]]
+            assert text == mc["texts"][done[i]], (names[i], done[i])
+            assert abs(last_blank - cases[i]["last_blank"][done[i]]) < 1e-7
+            assert np.abs(em[j].numpy() - cases[i]["emission"][done[i]]).max() < EXACT_TOL
+            done[i] += 1
+            audio[i] = audio[i][10240:]
+    assert done == [meta["cases"][n]["n_chunks"] for n in names]

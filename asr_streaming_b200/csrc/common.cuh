@@ -341,8 +341,19 @@ struct EpiQKV {
       const float x0 = (v[i][0] + b4.x) * sc, x1 = (v[i][1] + b4.y) * sc, x2 = (v[i][2] + b4.z) * sc, x3 = (v[i][3] + b4.w) * sc;
       if (row < M) {
         T* dst = reinterpret_cast<T*>(ctx[i]) + lc;
-        if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
-        else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+        if (sizeof(T) == 4) {
+          if (sec == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+          } else {
+            // EXACT K/V rows are stored pre-split, [hi d bf16 | lo d bf16] in the 4d bytes of the row: x = hi + lo to 2^-17, which is
+            // what the three-MMA attention (layers.cu: attention_exact_kernel) consumes without any conversion
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            bf16* sp = reinterpret_cast<bf16*>(ctx[i]) + lc;
+            *reinterpret_cast<uint2*>(sp) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(sp + d) = make_uint2(pack_bf16x2(x0 - f01.x, x1 - f01.y), pack_bf16x2(x2 - f23.x, x3 - f23.y));
+          }
+        } else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
       }
     }
   }

@@ -795,6 +795,12 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     }
     if (e->kv_cache.alloc(esz * S * g.n_layers * 2 * g.ring * d) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S)) break;
     if (cudaMemsetAsync(e->kv_cache.p, 0, e->kv_cache.bytes, e->stream) != cudaSuccess) { set_error("memset failed"); break; }
+    if (g.split && d == 512 && g.n_heads == 8 && (g.seg_rows == 16 || g.seg_rows == 8) && g.rc_rows == 4) {
+      // EXACT: ring rows pre-split [hi 512 | lo 512] bf16 = 16 head-sized pieces per row (attention_exact_kernel)
+      e->attn_tma = !make_tmap_bf16_heads(&e->tm_kv, e->kv_cache.p, (uint64_t)S * g.n_layers * 2 * g.ring, 16, (uint32_t)g.seg_rows) &&
+                    !make_tmap_bf16_heads(&e->tm_rc, e->rc_kv.p, (uint64_t)B * 2 * g.rc_rows, 16, (uint32_t)g.rc_rows);
+      if (!e->attn_tma) fprintf(stderr, "asr_b200: tensor-core EXACT attention disabled: %s\n", asr_last_error());
+    }
     if (!g.split && d == 512 && g.n_heads == 8 && (g.seg_rows == 16 || g.seg_rows == 8) && g.rc_rows == 4) {
       // not fatal: without the maps the CTA-per-stream attention kernel serves every batch size
       e->attn_tma = !make_tmap_bf16_heads(&e->tm_kv, e->kv_cache.p, (uint64_t)S * g.n_layers * 2 * g.ring, 8, (uint32_t)g.seg_rows) &&
@@ -1255,8 +1261,15 @@ int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int32_t whic
   for (int i = 0; i < lv; ++i) {                       // reference layout: right-aligned, oldest first (TA:emformer.py:395-396)
     const int rr = ((pl - lv + i) % g.ring + g.ring) % g.ring;
     float* o = out + (size_t)(g.left - lv + i) * d;
-    if (g.split) memcpy(o, ring.data() + (size_t)rr * d * 4, d * 4);
-    else {
+    if (g.split) {                                      // pre-split rows [hi d | lo d] bf16: x = hi + lo
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(ring.data()) + (size_t)rr * 2 * d;
+      for (size_t c = 0; c < d; ++c) {
+        uint32_t uh = (uint32_t)h[c] << 16, ul = (uint32_t)h[d + c] << 16;
+        float fh, fl;
+        memcpy(&fh, &uh, 4); memcpy(&fl, &ul, 4);
+        o[c] = fh + fl;
+      }
+    } else {
       const uint16_t* h = reinterpret_cast<const uint16_t*>(ring.data()) + (size_t)rr * d;
       for (size_t c = 0; c < d; ++c) { uint32_t u = (uint32_t)h[c] << 16; memcpy(o + c, &u, 4); }
     }

@@ -121,11 +121,16 @@ __device__ __forceinline__ void stage_rows(const AttnParams<T>& P, const T* cach
     } else {
       src = rc_b + ((size_t)which * P.rc_rows + (j - lv - P.seg_rows)) * P.d;
     }
-    const int4 raw = *reinterpret_cast<const int4*>(src + head * AT_DH + c);
     float* o = dst + j * AT_KST + c;
     if (sizeof(T) == 4) {
-      *reinterpret_cast<int4*>(o) = raw;
+      // EXACT ring rows are pre-split [hi d bf16 | lo d bf16] (see EpiQKV::store): x = hi + lo
+      const bf16* sp = reinterpret_cast<const bf16*>(src) + head * AT_DH + c;
+      const uint2 hi = *reinterpret_cast<const uint2*>(sp), lo = *reinterpret_cast<const uint2*>(sp + P.d);
+      const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.x)), h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.y));
+      const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo.x)), l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo.y));
+      *reinterpret_cast<float4*>(o) = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
     } else {
+      const int4 raw = *reinterpret_cast<const int4*>(src + head * AT_DH + c);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); o[2 * e] = f.x; o[2 * e + 1] = f.y; }
@@ -677,6 +682,251 @@ int attention_stream_launch(const AttnParams<bf16>& P, int n_streams, int num_sm
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// EXACT-precision chunk attention on the tensor cores.  In EXACT mode the K/V ring rows are stored PRE-SPLIT by the QKV epilogue:
+// [hi 512 bf16 | lo 512 bf16] with x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) — the same 4 bytes per element as fp32, relative
+// error 2^-17.  Seen through the head-major tensor map a row is 16 pieces of 128 B (pieces 0-7: hi of head p, 8-15: lo of head
+// p - 8), so this kernel is attention_stream_kernel with three MMAs per fragment pair (hi*hi + lo*hi + hi*lo, fp32 accumulation —
+// the EXACT GEMMs' scheme), fragments read with the same LDS.32 / ldmatrix.trans, no conversion of K or V at all; q (fp32) and
+// the probabilities are split in registers.  ONE staging buffer (rows are twice as wide: K 104 KB + V 104 KB): K and V keep their
+// own full / empty barriers, so the next stream's K arrives during softmax and P V of this one and its V during the next Q K^T.
+// Replaces the CUDA-core kernel (1.47 ms per launch at 4096 streams: half of an EXACT step) from 148 streams per step on.
+// ------------------------------------------------------------------------------------------
+constexpr int AX_RC_OFF = AS_RING_ROWS * 2048;                 // split rows: 2 KB each
+constexpr int AX_HALF_BYTES = AX_RC_OFF + AS_RC_ROWS * 2048;   // K (or V): 104 KB
+
+// byte offset of piece p (hi: head, lo: 8 + head) of key's row inside the K (or V) buffer
+template <int SEG>
+__device__ __forceinline__ uint32_t ax_row_off(int key, int n_ring, int piece) {
+  return key < n_ring ? (uint32_t)((key / SEG) * (SEG * 2048) + piece * (SEG * 128) + (key % SEG) * 128)
+                      : (uint32_t)(AX_RC_OFF + piece * (AS_RC_ROWS * 128) + (key - n_ring) * 128);
+}
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+}
+
+template <int ROWS>
+__device__ __forceinline__ void ax_load_q(uint32_t (&qh)[4][4], uint32_t (&ql)[4][4], const float* qb, int d, int row_base, int g, int tig) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int r0 = row_base + g, r1 = r0 + 8, c0 = ks * 16 + 2 * tig;
+    const float2 z = make_float2(0.f, 0.f);
+    const float2 a0 = r0 < ROWS ? *reinterpret_cast<const float2*>(qb + (size_t)r0 * d + c0) : z;
+    const float2 a1 = r1 < ROWS ? *reinterpret_cast<const float2*>(qb + (size_t)r1 * d + c0) : z;
+    const float2 a2 = r0 < ROWS ? *reinterpret_cast<const float2*>(qb + (size_t)r0 * d + c0 + 8) : z;
+    const float2 a3 = r1 < ROWS ? *reinterpret_cast<const float2*>(qb + (size_t)r1 * d + c0 + 8) : z;
+    split2(a0.x, a0.y, qh[ks][0], ql[ks][0]); split2(a1.x, a1.y, qh[ks][1], ql[ks][1]);
+    split2(a2.x, a2.y, qh[ks][2], ql[ks][2]); split2(a3.x, a3.y, qh[ks][3], ql[ks][3]);
+  }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(AsCfg<ROWS>::THREADS, 1)
+attention_exact_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmRC, AttnParams<float> P, int n_streams) {
+  constexpr int HEAD_WARPS = AsCfg<ROWS>::HEAD_WARPS;
+  constexpr int SEG = ROWS - AS_RC_ROWS;
+  constexpr int BLOCK_BYTES = SEG * 2048;
+  extern __shared__ uint8_t as_smem_raw[];
+  __shared__ __align__(8) unsigned long long ax_bars[4];       // kfull | vfull | kempty | vempty
+  __shared__ int ax_meta;
+  __shared__ __align__(16) uint8_t ax_zero[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const uint32_t smem0 = ((uint32_t)__cvta_generic_to_shared(as_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(ax_bars);
+  const uint32_t kfull = bar0, vfull = bar0 + 8u, kempty = bar0 + 16u, vempty = bar0 + 24u;
+  const uint32_t zero_addr = (uint32_t)__cvta_generic_to_shared(ax_zero);
+  if (tid < 4) reinterpret_cast<uint32_t*>(ax_zero)[tid] = 0u;
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRC) : "memory");
+    as_mbar_init(kfull, 1); as_mbar_init(vfull, 1); as_mbar_init(kempty, HEAD_WARPS); as_mbar_init(vempty, HEAD_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == HEAD_WARPS) {
+    // ===================== producer: one lane, <= 8 TMA ops per stream =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int b = blockIdx.x; b < n_streams; b += gridDim.x, ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        const int slot = P.slots[b];
+        const int pl = P.past_len[slot];
+        const int lv = pl < P.left ? pl : P.left;
+        const int nb = lv / SEG + 1;
+        const int first_blk = (pl - lv) / SEG;
+        const int ring_blocks = P.ring / SEG;
+        const uint32_t bytes = (uint32_t)(nb * BLOCK_BYTES + AS_RC_ROWS * 2048);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          as_mbar_wait(which ? vempty : kempty, par ^ 1u);
+          if (!which) ax_meta = lv;
+          const uint32_t full = which ? vfull : kfull;
+          as_mbar_expect_tx(full, bytes);
+          const uint32_t dst = smem0 + (uint32_t)(which * AX_HALF_BYTES);
+          const long long row0 = P.cache_row0 + (long long)slot * P.slot_rows + (long long)which * P.ring;
+          for (int j = 0; j < nb; ++j)
+            as_tma_3d(dst + (uint32_t)(j * BLOCK_BYTES), &tmKV, 0, (int)(row0 + ((first_blk + j) % ring_blocks) * SEG), 0, full);
+          as_tma_3d(dst + (uint32_t)AX_RC_OFF, &tmRC, 0, (b * 2 + which) * AS_RC_ROWS, 0, full);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== head warps: warp = (query tile, head) =====================
+  const int head = warp % AM_WARPS;
+  const int row_base = (warp / AM_WARPS) * 16;
+  const bool second_half = row_base + 8 < ROWS;
+  const uint32_t s_k = smem0, s_v = smem0 + (uint32_t)AX_HALF_BYTES;
+  int it = 0;
+  for (int b = blockIdx.x; b < n_streams; b += gridDim.x, ++it) {
+    const uint32_t par = (uint32_t)(it & 1);
+    // q split into 32 fragment registers: loaded per stream (not prefetched across P V — the 544-thread CTA has 96 registers a thread)
+    uint32_t qh[4][4], ql[4][4];
+    ax_load_q<ROWS>(qh, ql, P.q + (size_t)b * ROWS * P.d + head * AT_DH, P.d, row_base, g, tig);
+    as_mbar_wait(kfull, par);
+    const int lv = ax_meta;
+    const int n_ring = lv + SEG;
+    const int n_keys = n_ring + AS_RC_ROWS;
+
+    // ---- S = Q K^T, three MMAs per fragment pair
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt * 8 < n_keys) {
+        int key = nt * 8 + g;
+        key = key < n_keys ? key : n_keys - 1;                    // clamp: garbage columns are masked below
+        const uint32_t rh = ax_row_off<SEG>(key, n_ring, head), rl = ax_row_off<SEG>(key, n_ring, head + 8);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t h0, h1, l0, l1;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(h0) : "r"(s_k + as_swz(rh, 2 * ks) + tig * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(h1) : "r"(s_k + as_swz(rh, 2 * ks + 1) + tig * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(l0) : "r"(s_k + as_swz(rl, 2 * ks) + tig * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(l1) : "r"(s_k + as_swz(rl, 2 * ks + 1) + tig * 4));
+          mma_bf16_16816(sc[nt], ql[ks], h0, h1);                 // small terms first
+          mma_bf16_16816(sc[nt], qh[ks], l0, l1);
+          mma_bf16_16816(sc[nt], qh[ks], h0, h1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) as_mbar_arrive(kempty);
+
+    // ---- softmax over keys, fp32
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      if (hr == 1 && !second_half) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { sc[nt][2] = 0.f; sc[nt][3] = 0.f; }
+        continue;
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool valid = nt * 8 + 2 * tig + e < n_keys;
+          float& x = sc[nt][2 * hr + e];
+          x = valid ? x : -INFINITY;
+          m = fmaxf(m, x);
+        }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& x = sc[nt][2 * hr + e];
+          x = expf(x - m);
+          sum += x;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][2 * hr] *= inv;
+        sc[nt][2 * hr + 1] *= inv;
+      }
+    }
+    // ---- O = P V, three MMAs per fragment pair; B fragments of V (hi and lo) via ldmatrix.x4.trans
+    as_mbar_wait(vfull, par);
+    float oc[8][4];
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oc[dn][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk * 16 < n_keys) {
+        uint32_t ph[4], pl_[4];
+        split2(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl_[0]);
+        split2(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl_[1]);
+        split2(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl_[2]);
+        split2(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl_[3]);
+        const int mi = lane >> 3, ri = lane & 7;
+        const int key = kk * 16 + (mi & 1) * 8 + ri;
+        const bool kv = key < n_keys;
+        const uint32_t rh = ax_row_off<SEG>(kv ? key : 0, n_ring, head), rl = ax_row_off<SEG>(kv ? key : 0, n_ring, head + 8);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          const uint32_t ah = kv ? s_v + as_swz(rh, dp * 2 + (mi >> 1)) : zero_addr;
+          const uint32_t al = kv ? s_v + as_swz(rl, dp * 2 + (mi >> 1)) : zero_addr;
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(ah));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(al));
+          mma_bf16_16816(oc[2 * dp], pl_, h0, h1);
+          mma_bf16_16816(oc[2 * dp], ph, l0, l1);
+          mma_bf16_16816(oc[2 * dp], ph, h0, h1);
+          mma_bf16_16816(oc[2 * dp + 1], pl_, h2, h3);
+          mma_bf16_16816(oc[2 * dp + 1], ph, l2, l3);
+          mma_bf16_16816(oc[2 * dp + 1], ph, h2, h3);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) as_mbar_arrive(vempty);
+    // ---- write the A operand of out_proj (hi | lo halves)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r = row_base + hr * 8 + g;
+      if (r < ROWS) {
+        bf16* o = P.out + ((size_t)b * ROWS + r) * P.ld + head * AT_DH + 2 * tig;
+#pragma unroll
+        for (int dn = 0; dn < 8; ++dn) {
+          uint32_t hi, lo;
+          split2(oc[dn][2 * hr], oc[dn][2 * hr + 1], hi, lo);
+          *reinterpret_cast<uint32_t*>(o + dn * 8) = hi;
+          if (P.lo_off) *reinterpret_cast<uint32_t*>(o + P.lo_off + dn * 8) = lo;
+        }
+      }
+    }
+  }
+}
+
+template <int ROWS>
+int attention_exact_launch(const AttnParams<float>& P, int n_streams, int num_sms, cudaStream_t st) {
+  const size_t smem = (size_t)2 * AX_HALF_BYTES + 1024;
+  static size_t attr_done[kMaxDevices] = {0};
+  ASR_CUDA_OK(ensure_dyn_smem(attention_exact_kernel<ROWS>, smem, attr_done));
+  const int grid = n_streams < num_sms ? n_streams : num_sms;
+  ASR_CUDA_OK(launch_pdl(attention_exact_kernel<ROWS>, dim3(grid), dim3(AsCfg<ROWS>::THREADS), smem, st, *P.h_tm_cache, *P.h_tm_rc, P, n_streams));
+  return 0;
+}
+
 template <int ROWS>
 int attention_mma_launch(const AttnParams<bf16>& P, int n_streams, cudaStream_t st) {
   const int kmax = P.left + P.seg_rows + P.rc_rows;
@@ -848,6 +1098,18 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
       }
       if (P.rows == 20) return attention_mma_launch<20>(P, n_streams, st);
       if (P.rows == 12) return attention_mma_launch<12>(P, n_streams, st);
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    const char* sm_env = getenv("ASR_B200_ATTN_STREAM_MIN");
+    const int stream_min = sm_env ? atoi(sm_env) : 148;
+    const bool tma_ok = P.h_tm_cache && P.h_tm_rc && P.n_heads == AM_WARPS && P.d == 512 && P.rc_rows == AS_RC_ROWS && P.rows == P.seg_rows + P.rc_rows &&
+                        P.ring <= AS_RING_ROWS && P.ring % P.seg_rows == 0 && P.left % P.seg_rows == 0 && (P.seg_rows == 16 || P.seg_rows == 8);
+    if (n_streams >= stream_min && tma_ok && !getenv("ASR_B200_DEBUG_SIMT_ATTENTION")) {
+      int num_sms = 148;
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, current_device_index());
+      if (P.rows == 20) return attention_exact_launch<20>(P, n_streams, num_sms, st);
+      if (P.rows == 12) return attention_exact_launch<12>(P, n_streams, num_sms, st);
     }
   }
   if (P.rows == 20) return attention_launch_rows<T, 20>(P, n_streams, st);

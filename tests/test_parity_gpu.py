@@ -470,6 +470,39 @@ def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_exact_tensor_core_attention_matches_fp32_kernel(packed_weights, golden, meta, monkeypatch):
+    """EXACT precision: the split-bf16 (3 MMAs per product) TMA-fed attention kernel, taken from 148 streams per step on, forced
+    for a small ragged batch against the fp32 CUDA-core kernel — log-probs within the EXACT tolerance, greedy ids identical —
+    and on a golden case against the reference's emission, in both geometries."""
+    from asr_streaming_b200 import Engine, PRECISION_EXACT
+    rng = np.random.default_rng(29)
+    n = 21
+    pcm = rng.integers(-4000, 4000, size=(4, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    outs, ids = [], []
+    for force in (False, True):
+        monkeypatch.setenv("ASR_B200_ATTN_STREAM_MIN", "1" if force else "100000")
+        with Engine(model_cfg(PRECISION_EXACT, max_batch=32, max_sessions=32), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n)]
+            got, gi = [], []
+            for t in range(4):
+                if t == 2:
+                    e.reset_sessions(sl[3:11])
+                r = e.step(sl, pcm[t], want_logprobs=True)
+                got.append(r.logprobs)
+                gi.append(r.argmax_ids.copy())
+            outs.append(np.stack(got))
+            ids.append(np.stack(gi))
+    assert np.abs(outs[0] - outs[1]).max() < EXACT_TOL
+    assert np.array_equal(ids[0], ids[1])
+    monkeypatch.setenv("ASR_B200_ATTN_STREAM_MIN", "1")
+    for name, geom, low in (("synth_noise", O.CANONICAL, False), ("lowlat_noise", O.LOW_LATENCY, True)):
+        case, mc = golden(name), meta["cases"][name]
+        with Engine(model_cfg(PRECISION_EXACT, low), packed_weights) as e:
+            em, _, _ = _run_case(e, case, mc, geom)
+        assert np.abs(em - case["emission"]).max() < EXACT_TOL, name
+        assert np.array_equal(em.argmax(-1), case["emission"].argmax(-1)), name
+
+
 def test_streaming_attention_low_latency_geometry(packed_weights, golden, meta, monkeypatch):
     """Low-latency geometry (8 segment rows, 5-block ring) through the streaming attention kernel: 8-row TMA boxes."""
     from asr_streaming_b200 import Engine, PRECISION_FAST

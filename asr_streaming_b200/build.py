@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libasr_b200.so")
 SOURCES = ["engine.cu", "gemm_tcgen05.cu", "gemm_ln.cu", "gemm_simt.cu", "fbank.cu", "layers.cu", "beam.cu", "convmod.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "asr_b200.h")]
+HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "tc_ptx.cuh", "fft_regs.cuh", os.path.join("..", "..", "include", "asr_b200.h")]
 
 
 def _nvcc() -> str:

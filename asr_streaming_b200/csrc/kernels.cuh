@@ -11,6 +11,7 @@ struct FbankParams {
   int pcm_stride;         // samples between consecutive streams
   int n_samples;          // samples staged per stream
   int n_frames, hop, frame_len, frame_off;
+  int blk;                // gcd(hop, frame_len): samples per block sum of the DC-offset pass (filled in by fbank_launch)
   int nc;                 // complex FFT size: 400 (800-pt real) or 256 (512-pt real)
   int kaldi;              // remove-DC + pre-emphasis path
   float in_scale;         // 1/32768 for int16 -> [-1,1) (streaming_server.py:362-363), 1 otherwise

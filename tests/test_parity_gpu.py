@@ -448,6 +448,37 @@ def test_fused_layernorm_large_ragged_batch(packed_weights):
             assert np.array_equal(r, got[t][perm])                       # same kernels, different positions: bit-exact
 
 
+def test_fused_feed_forward_kernel_is_bit_identical(packed_weights, golden, meta, monkeypatch):
+    """The feed-forward block as ONE kernel (FFN1 + GELU -> L2-resident scratch -> FFN2 + residual + LayerNorms; taken from 34
+    256-row tiles per step on) forced for a 200-stream batch (15 full row tiles + a partial one, several tiles per cluster only when
+    clusters are scarce) against the two-kernel path: same MMA shapes and k order, same GELU => bit-identical log-probs and ids over
+    four chained steps; and a golden case against the reference's emission."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(41)
+    n = 200
+    pcm = rng.integers(-4000, 4000, size=(4, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    monkeypatch.setenv("ASR_B200_FUSED_LN_MIN_STREAMS", "1")
+    monkeypatch.setenv("ASR_B200_PAIR_LN_MIN_TILES", "1")
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setenv("ASR_B200_MLP_FUSED", "1" if fused else "0")
+        monkeypatch.setenv("ASR_B200_MLP_MIN_TILES", "1")
+        with Engine(model_cfg(PRECISION_FAST, max_batch=256, max_sessions=256), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n)]
+            got = []
+            for t in range(4):
+                if t == 2:
+                    e.reset_sessions(sl[50:120])
+                got.append(e.step(sl, pcm[t], want_logprobs=True).logprobs)
+            outs.append(np.stack(got))
+    assert np.isfinite(outs[1]).all()
+    assert np.array_equal(outs[0], outs[1])
+    case, mc = golden("synth_noise"), meta["cases"]["synth_noise"]
+    with Engine(model_cfg(PRECISION_FAST, max_batch=16, max_sessions=16), packed_weights) as e:      # one stream: a 20-row partial tile
+        em, _, _ = _run_case(e, case, mc, O.CANONICAL)
+    assert np.abs(em - case["emission"]).max() < FAST_TOL
+
+
 def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch):
     """The persistent double-buffered attention kernel (taken from 148 streams per step on) forced for a small ragged batch:
     same fragments and summation order as the CTA-per-stream kernel => bit-identical log-probs, at every left-context fill."""

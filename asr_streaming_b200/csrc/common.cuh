@@ -195,6 +195,7 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
 // out[row, col] = acc (+bias) (+res)        fp32 out; n_valid masks a ragged N (CTC vocab = 804)
 struct EpiF32 {
+  static constexpr bool kBf16Rows = false;
   float* out;
   const float* bias;   // nullable
   const float* res;    // nullable, same ld as out
@@ -255,6 +256,27 @@ struct EpiOperand {
   __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
+  // Packed-bf16 row path (see epilogue_tile): bias + activation on the 32 values a thread holds of ITS row (columns col0 ..), then
+  // the rows leave as 16-byte pieces.  Same operations in the same order as store() below: bit-identical results.
+  static constexpr bool kBf16Rows = true;
+  __device__ __forceinline__ bool bf16_rows() const { return lo_off == 0; }
+  // v: 8 values of the thread's row at columns col ..
+  __device__ __forceinline__ void apply8(float* v, int col, int) const {
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    if (act == ACT_GELU) {
+      f2_unpack(f2_add(f2_pack(v[0], v[1]), f2_pack(ba.x, ba.y)), v[0], v[1]);
+      f2_unpack(f2_add(f2_pack(v[2], v[3]), f2_pack(ba.z, ba.w)), v[2], v[3]);
+      f2_unpack(f2_add(f2_pack(v[4], v[5]), f2_pack(bb.x, bb.y)), v[4], v[5]);
+      f2_unpack(f2_add(f2_pack(v[6], v[7]), f2_pack(bb.z, bb.w)), v[6], v[7]);
+      gelu_erf2(v[0], v[1]); gelu_erf2(v[2], v[3]); gelu_erf2(v[4], v[5]); gelu_erf2(v[6], v[7]);
+    } else {
+      const float b8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float x = v[k] + b8[k]; v[k] = act == ACT_SILU ? silu(x) : x; }
+    }
+  }
+  __device__ __forceinline__ int section_col0(int) const { return 0; }
+  __device__ __forceinline__ bf16* row_ptr(RowCtx, int row, int col, int) const { return out + (size_t)row * ld + col; }
   __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&)[8], const float4& b4) const {
     const int rsub = lane >> 3;
     if (act == ACT_GELU) {
@@ -330,6 +352,17 @@ struct EpiQKV {
   }
   __device__ __forceinline__ const float* bias_ptr() const { return bias; }
   __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
+  // Packed-bf16 row path (bf16 K/V cache and q only): same arithmetic as store(), (acc + bias) * scale.
+  static constexpr bool kBf16Rows = sizeof(T) == 2;
+  __device__ __forceinline__ bool bf16_rows() const { return true; }
+  __device__ __forceinline__ void apply8(float* v, int col, int tile_col0) const {
+    const float sc = tile_col0 < d ? qscale : 1.0f;          // a tile never straddles the q | k | v sections
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    v[0] = (v[0] + ba.x) * sc; v[1] = (v[1] + ba.y) * sc; v[2] = (v[2] + ba.z) * sc; v[3] = (v[3] + ba.w) * sc;
+    v[4] = (v[4] + bb.x) * sc; v[5] = (v[5] + bb.y) * sc; v[6] = (v[6] + bb.z) * sc; v[7] = (v[7] + bb.w) * sc;
+  }
+  __device__ __forceinline__ int section_col0(int tile_col0) const { return tile_col0 / d * d; }      // first column of the tile's q | k | v section
+  __device__ __forceinline__ bf16* row_ptr(RowCtx ctx, int, int col, int sec_col0) const { return reinterpret_cast<bf16*>(ctx) + (col - sec_col0); }
   __device__ __forceinline__ void store(int row0, int col, int lane, int M, float (&v)[8][4], const RowCtx (&ctx)[8], const float4& b4) const {
     const int rsub = lane >> 3;
     const int sec = col / d;

@@ -44,6 +44,57 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
 #pragma unroll
   for (int i = 0; i < 8; ++i) ctx[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 4 * i + (lane >> 3));
   const float* bias = epi.bias_ptr();
+  if constexpr (Epi::kBf16Rows) {
+    if (epi.bf16_rows() && tile_col0 + BN <= p.N) {
+      // bf16 outputs: bias / activation in the thread = row layout, convert, transpose 16-byte pieces (XOR-swizzled, conflict-free
+      // both ways) and store 8 rows x 64 B per instruction — a third of the instructions of the fp32 transpose path below, which is
+      // what the K = 512 GEMMs (8 k-blocks of MMA per 128 x 256 accumulator) are bound by.
+      typename Epi::RowCtx c4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c4[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 8 * i + (lane >> 2));
+      const int sec_col0 = epi.section_col0(tile_col0);
+      uint32_t* xw = reinterpret_cast<uint32_t*>(xpose);
+      mbar_wait(tfull, tfull_phase);
+      tc_fence_after();
+      auto finish16 = [&](float (&v)[32], int c) {
+        const int col0 = tile_col0 + c * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          epi.apply8(v + 8 * q, col0 + 8 * q, tile_col0);
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+          o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+          *reinterpret_cast<uint4*>(xw + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + (lane >> 2), pc = lane & 3;
+          const uint4 o = *reinterpret_cast<const uint4*>(xw + r * 16 + 4 * (pc ^ ((r >> 1) & 3)));
+          if (row0 + r < p.M) *reinterpret_cast<uint4*>(epi.row_ptr(c4[i], row0 + r, col0 + 8 * pc, sec_col0)) = o;
+        }
+        __syncwarp();
+      };
+      float v[32];
+      if constexpr (kChunks == 2 * kStride) {
+        // two chunks per warp: both TMEM loads in flight before the first chunk's math
+        float w[32];
+        tmem_ld32(taddr + (uint32_t)(half * 32), v);
+        tmem_ld32(taddr + (uint32_t)((half + kStride) * 32), w);
+        tmem_ld_wait();
+        finish16(v, half);
+        finish16(w, half + kStride);
+      } else {
+#pragma unroll 1
+        for (int c = half; c < kChunks; c += kStride) {
+          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          finish16(v, c);
+        }
+      }
+      return;
+    }
+  }
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   if (half >= kChunks) return;

@@ -193,6 +193,18 @@ template <> __device__ __forceinline__ unsigned long long shfl_ctx<unsigned long
 // ------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
+// Diagnostic only (asr_debug_gemm_time epi 3): waits for the accumulator and drops it — the mainloop's own speed.
+struct EpiNull {
+  static constexpr bool kBf16Rows = false;
+  typedef int RowCtx;
+  __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
+  __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
+  __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
+  __device__ __forceinline__ void store(int, int, int, int, float (&)[8][4], const RowCtx (&)[8], const float4&) const {}
+};
+template <class E> struct IsNullEpi { static constexpr bool value = false; };
+template <> struct IsNullEpi<EpiNull> { static constexpr bool value = true; };
+
 // out[row, col] = acc (+bias) (+res)        fp32 out; n_valid masks a ragged N (CTC vocab = 804)
 struct EpiF32 {
   static constexpr bool kBf16Rows = false;
@@ -259,7 +271,7 @@ struct EpiOperand {
   // Packed-bf16 row path (see epilogue_tile): bias + activation on the 32 values a thread holds of ITS row (columns col0 ..), then
   // the rows leave as 16-byte pieces.  Same operations in the same order as store() below: bit-identical results.
   static constexpr bool kBf16Rows = true;
-  __device__ __forceinline__ bool bf16_rows() const { return lo_off == 0; }
+  __host__ __device__ __forceinline__ bool bf16_rows() const { return lo_off == 0; }
   // v: 8 values of the thread's row at columns col ..
   __device__ __forceinline__ void apply8(float* v, int col, int) const {
     const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
@@ -354,7 +366,7 @@ struct EpiQKV {
   __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
   // Packed-bf16 row path (bf16 K/V cache and q only): same arithmetic as store(), (acc + bias) * scale.
   static constexpr bool kBf16Rows = sizeof(T) == 2;
-  __device__ __forceinline__ bool bf16_rows() const { return true; }
+  __host__ __device__ __forceinline__ bool bf16_rows() const { return true; }
   __device__ __forceinline__ void apply8(float* v, int col, int tile_col0) const {
     const float sc = tile_col0 < d ? qscale : 1.0f;          // a tile never straddles the q | k | v sections
     const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));

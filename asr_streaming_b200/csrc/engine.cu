@@ -97,6 +97,8 @@ struct AsrEngine {
   int no_pair = 0;
   int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
   int no_fuse2 = 0;             // ASR_B200_NO_LN_FUSE2=1: second LayerNorm statistics by their own TMEM pass
+  int pair_a = 0;               // ASR_B200_PAIR_A=1: short-K pair GEMMs with the A tile resident in shared memory
+  int pair128 = 0;              // ASR_B200_PAIR128=1: short-K pair GEMMs (QKV, FFN1) with 256 x 128 tiles and four accumulator stages
   int mlp_fused = 0;            // ASR_B200_MLP_FUSED=1: the feed-forward block as ONE kernel at large batches (measured 9.4 vs 8.5 ms per step at
                                 // 4096 streams: both forms are bound by the epilogue warps, not by the 670 MB of hidden-activation traffic the fusion saves)
   int mlp_min_tiles = 34;       // 256-row tiles needed before the feed-forward block runs as the one fused kernel (ASR_B200_MLP_MIN_TILES)
@@ -353,8 +355,12 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
   const int k_eff = w.K * (e->geo.split ? 3 : 1);
   const long pair_tiles = (long)((M + 255) / 256) * (w.N / 256);
   if (bn == 256 && !e->no_pair && w.N % 256 == 0 && ((k_eff >= 1024 && pair_tiles >= e->num_sms / 2) || pair_tiles >= 4 * (e->num_sms / 2)))
-    bn = kPairTile;
-  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 ? 0 : (bn == 128 || bn == kPairTile ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
+    bn = (e->pair128 && k_eff <= 512) ? kPairTile128 : kPairTile;
+  if constexpr (Epi::kBf16Rows) {
+    // short K, bf16 outputs (QKV, FFN1 in FAST precision): keep the A tile resident, stream only B
+    if (bn == kPairTile && e->pair_a && k_eff <= 512 && w.N % 512 == 0 && epi.bf16_rows()) bn = kPairTileA;
+  }
+  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 || bn == kPairTile128 ? 0 : (bn == 128 || bn == kPairTile || bn == kPairTileA ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
 }
 
 int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const LnEpilogue& ep) {
@@ -726,6 +732,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
   if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
   if (const char* mf = getenv("ASR_B200_MLP_FUSED")) e->mlp_fused = mf[0] == '1';
+  if (const char* p8 = getenv("ASR_B200_PAIR128")) e->pair128 = p8[0] == '1';
+  if (const char* pa = getenv("ASR_B200_PAIR_A")) e->pair_a = pa[0] == '1';
   if (const char* mt = getenv("ASR_B200_MLP_MIN_TILES")) e->mlp_min_tiles = atoi(mt);
   if (const char* qt = getenv("ASR_B200_QUAD_LN_MAX_TILES")) e->quad_ln_max_tiles = atoi(qt);
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
@@ -1328,7 +1336,7 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
       if (gemm_simt<EpiF32>(dA.as<bf16>(), ld, dB.as<bf16>(), ld, p, epi, 0)) break;
     } else {
       CUtensorMap ta, tb;
-      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile ? 128 : bn)) break;
+      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile || bn == kPairTileA ? 128 : (bn == kPairTile128 ? 64 : bn))) break;
       if (gemm_tc<EpiF32>(ta, tb, p, epi, bn, prop.multiProcessorCount, 0)) break;
     }
     cudaError_t err = cudaDeviceSynchronize();
@@ -1431,7 +1439,7 @@ int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t 
     cudaMemset(dA.p, 0x3c, dA.bytes); cudaMemset(dB.p, 0x3c, dB.bytes); cudaMemset(dR.p, 0, dR.bytes); cudaMemset(dbias.p, 0, dbias.bytes);
     const GemmProblem p = make_problem(M, N, K, split);
     CUtensorMap ta, tb;
-    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile ? 128 : bn)) break;
+    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile || bn == kPairTileA ? 128 : (bn == kPairTile128 ? 64 : bn))) break;
     EpiF32 e_plain{dC.as<float>(), nullptr, nullptr, N, N};
     EpiF32 e_res{dC.as<float>(), dbias.as<float>(), dR.as<float>(), N, N};
     EpiOperand e_op{dO.as<bf16>(), dbias.as<float>(), N, 0, ACT_GELU};
@@ -1441,6 +1449,7 @@ int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t 
       if (it == 3) cudaEventRecord(e0, 0);
       if (epi_kind == 0) ok = !gemm_tc<EpiF32>(ta, tb, p, e_plain, bn, prop.multiProcessorCount, 0);
       else if (epi_kind == 1) ok = !gemm_tc<EpiF32>(ta, tb, p, e_res, bn, prop.multiProcessorCount, 0);
+      else if (epi_kind == 3) ok = !gemm_tc<EpiNull>(ta, tb, p, EpiNull{}, bn, prop.multiProcessorCount, 0);
       else ok = !gemm_tc<EpiOperand>(ta, tb, p, e_op, bn, prop.multiProcessorCount, 0);
     }
     if (!ok) break;

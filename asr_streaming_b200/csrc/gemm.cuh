@@ -4,6 +4,8 @@
 
 namespace asr {
 
+constexpr int kPairTileA = 514;     // cta_group::2 kernel with the A tile resident in shared memory (K <= 512, bf16-row epilogues; tmB = box-128 map)
+constexpr int kPairTile128 = 513;   // cta_group::2 kernel with a 256 x 128 tile and four accumulator stages (tmB = box-64 map)
 constexpr int kPairTile = 512;   // `bn` value selecting the cta_group::2 kernel (256 x 256 tile per CTA pair; tmB = box-128 map)
 
 // C = A * B^T with fused epilogue.  tmA / tmB: 2D bf16 tensor maps, box {64, 128} and {64, bn}, 128B swizzle.

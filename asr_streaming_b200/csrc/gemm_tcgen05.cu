@@ -33,10 +33,17 @@ constexpr int kStagingBytes = kEpiWarps * kXposeFloats * 4;   // pair kernel
 //   * before the accumulator is complete (overlapping the MMAs): RowCtx of the thread's row, L2 prefetch of its residual rows;
 //   * tcgen05.ld (thread = row) runs one 32-column chunk ahead of the math (two register sets);
 //   * each chunk is transposed through shared memory so that global accesses are full 128-byte lines (see common.cuh).
-template <int BN, int kStride, class Epi>
+#ifdef ASR_EPI_TIMING
+__device__ unsigned long long g_epi_clk[8];                 // [0] tiles, [1] wait tfull, [2] TMEM loads, [3] math + staging + stores
+#define EPI_T(var) const long long var = clock64()
+#else
+#define EPI_T(var)
+#endif
+template <int BN, int kStride, class Epi, bool kBf16Only = false>
 __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem& p, int row0, int tile_col0, int half, int lane,
                                               uint32_t taddr, uint32_t tfull, uint32_t tfull_phase, float* xpose) {
   constexpr int kChunks = BN / 32;
+  if constexpr (IsNullEpi<Epi>::value) { mbar_wait(tfull, tfull_phase); tc_fence_after(); return; }
   const int my_row = row0 + lane;
   const typename Epi::RowCtx my_ctx = epi.row_ctx(my_row < p.M ? my_row : p.M - 1, tile_col0);
   if (my_row < p.M) epi.prefetch_tile(my_row, tile_col0, (p.N - tile_col0) < BN ? (p.N - tile_col0) : BN, my_ctx);
@@ -45,7 +52,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
   for (int i = 0; i < 8; ++i) ctx[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 4 * i + (lane >> 3));
   const float* bias = epi.bias_ptr();
   if constexpr (Epi::kBf16Rows) {
-    if (epi.bf16_rows() && tile_col0 + BN <= p.N) {
+    if (kBf16Only || (epi.bf16_rows() && tile_col0 + BN <= p.N)) {
       // bf16 outputs: bias / activation in the thread = row layout, convert, transpose 16-byte pieces (XOR-swizzled, conflict-free
       // both ways) and store 8 rows x 64 B per instruction — a third of the instructions of the fp32 transpose path below, which is
       // what the K = 512 GEMMs (8 k-blocks of MMA per 128 x 256 accumulator) are bound by.
@@ -54,6 +61,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
       for (int i = 0; i < 4; ++i) c4[i] = shfl_ctx<typename Epi::RowCtx>(my_ctx, 8 * i + (lane >> 2));
       const int sec_col0 = epi.section_col0(tile_col0);
       uint32_t* xw = reinterpret_cast<uint32_t*>(xpose);
+      EPI_T(t0);
       mbar_wait(tfull, tfull_phase);
       tc_fence_after();
       auto finish16 = [&](float (&v)[32], int c) {
@@ -67,6 +75,9 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
           *reinterpret_cast<uint4*>(xw + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) = o;
         }
         __syncwarp();
+#ifdef ASR_EPI_TIMING
+        const long long ta = clock64();
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + (lane >> 2), pc = lane & 3;
@@ -74,16 +85,28 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
           if (row0 + r < p.M) *reinterpret_cast<uint4*>(epi.row_ptr(c4[i], row0 + r, col0 + 8 * pc, sec_col0)) = o;
         }
         __syncwarp();
+#ifdef ASR_EPI_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 64) atomicAdd(&g_epi_clk[4], (unsigned long long)(clock64() - ta));
+#endif
       };
       float v[32];
       if constexpr (kChunks == 2 * kStride) {
         // two chunks per warp: both TMEM loads in flight before the first chunk's math
         float w[32];
+        EPI_T(t1);
         tmem_ld32(taddr + (uint32_t)(half * 32), v);
         tmem_ld32(taddr + (uint32_t)((half + kStride) * 32), w);
         tmem_ld_wait();
+        EPI_T(t2);
         finish16(v, half);
         finish16(w, half + kStride);
+#ifdef ASR_EPI_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 64) {
+          const long long t3 = clock64();
+          atomicAdd(&g_epi_clk[0], 1ull); atomicAdd(&g_epi_clk[1], (unsigned long long)(t1 - t0));
+          atomicAdd(&g_epi_clk[2], (unsigned long long)(t2 - t1)); atomicAdd(&g_epi_clk[3], (unsigned long long)(t3 - t2));
+        }
+#endif
       } else {
 #pragma unroll 1
         for (int c = half; c < kChunks; c += kStride) {
@@ -95,6 +118,7 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
       return;
     }
   }
+  if constexpr (kBf16Only) return;                       // (unreachable: the launcher checks the epilogue type and N)
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   if (half >= kChunks) return;
@@ -279,13 +303,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   tfull[a]  : per CTA, same multicast commit after the last k-block
 //   tempty[a] : leader's barrier only; 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
 // ==========================================================================================================
-constexpr int P_BN = 256;
-constexpr int P_STAGES = 4;
-constexpr int P_STAGE_BYTES = (BM + P_BN / 2) * BK * 2;            // 32 KB per CTA
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + kStagingBytes + 1024 + 256;
-template <class Epi>
+// P_BN = 128 variant (256 x 128 tile per pair): FOUR 128-column accumulator stages instead of two 256-column ones.  A K = 512 tile is
+// only 8 k-blocks of MMA (~2.9 us); with two stages the chain commit -> epilogue -> tempty -> next-but-one tile does not fit under one
+// tile of MMA and costs ~2.2 us per tile (measured); four stages give it three tiles.  The price is 24 instead of 32 KB of
+// operands per k-block for half the flops (1.5 x the L2 ingest per flop).
+template <int P_BN> struct PairCfg {
+  static constexpr int NACC = 512 / P_BN;                           // TMEM accumulator stages
+  static constexpr int STAGES = P_BN == 256 ? 4 : 6;
+  static constexpr int STAGE_BYTES = (BM + P_BN / 2) * BK * 2;      // 32 / 24 KB per CTA
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 1024 + 256;
+};
+template <class Epi, int P_BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi) {
+  constexpr int P_STAGES = PairCfg<P_BN>::STAGES, P_STAGE_BYTES = PairCfg<P_BN>::STAGE_BYTES, NACC = PairCfg<P_BN>::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + P_STAGES * P_STAGE_BYTES;
@@ -293,8 +324,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + 2 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * P_STAGES + 4);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + NACC + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * P_STAGES + 2 * NACC);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,7 +340,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -371,7 +402,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -392,10 +423,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_cta(tempty_bar(acc), 0);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
+#ifdef ASR_EPI_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 64 && g_epi_clk[0]) {
+    printf("epilogue warp 0 of CTA 0: %llu tiles, per tile: wait tfull %llu clk, TMEM loads %llu clk, math + staging + stores %llu clk (of which LDS + STG %llu)\n", g_epi_clk[0],
+           g_epi_clk[1] / g_epi_clk[0], g_epi_clk[2] / g_epi_clk[0], g_epi_clk[3] / g_epi_clk[0], g_epi_clk[4] / g_epi_clk[0]);
+    g_epi_clk[0] = g_epi_clk[1] = g_epi_clk[2] = g_epi_clk[3] = g_epi_clk[4] = 0;
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still signal or read
   if (warp == 1) {
@@ -404,14 +442,186 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <class Epi>
+template <class Epi, int P_BN>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
+  constexpr int P_SMEM_BYTES = PairCfg<P_BN>::SMEM_BYTES;
   static size_t attr_done[kMaxDevices] = {0};
-  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2_kernel<Epi>, (size_t)P_SMEM_BYTES, attr_done));
+  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2_kernel<Epi, P_BN>, (size_t)P_SMEM_BYTES, attr_done));
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P_BN - 1) / P_BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi>, dim3(2 * pairs), dim3(kThreads), P_SMEM_BYTES, st, tmA, tmB128, p, epi));
+  ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi, P_BN>, dim3(2 * pairs), dim3(kThreads), P_SMEM_BYTES, st, tmA, tmB128, p, epi));
   return 0;
+}
+
+// ==========================================================================================================
+// A-RESIDENT CTA-pair variant for short K (K <= 512: QKV, FFN1).  These GEMMs are bound by the L2 -> SM operand ingest, not by the
+// tensor pipe or the epilogue (halving the tile width, i.e. 1.5 x the ingest per flop, costs 30 %; a third of the epilogue instructions
+// changes nothing).  So the A tile (this CTA's 128 rows x K, 128 KB) is loaded ONCE per work unit and stays in shared memory while the
+// unit's N tiles stream only their B operand (16 KB per k-block and CTA instead of 32): a unit = one 256-row block x half of the N
+// tiles (two units per block keep the 74 pairs balanced: 640 units / 74), ingest per tile 128 KB + 128/3 (QKV) or 128/4 (FFN1) KB
+// instead of 256 KB.  It fits because the bf16-row epilogue needs 2 KB of staging per warp instead of 4.6 KB.
+//   a_full[kb] / a_empty[kb] : per k-block of the resident A tile (leader's barrier collects both CTAs' 16 KB; released by the commit
+//                              after the unit's last tile used it, so the next unit's A streams in behind the MMAs)
+//   b_full[s] / b_empty[s]   : the B ring, as in gemm_tc2_kernel
+// ==========================================================================================================
+constexpr int RA_KB = 8;                                            // k-blocks of the resident A tile (K <= 512)
+constexpr int RA_B_STAGES = 4;
+constexpr int RA_B_STAGE_BYTES = (256 / 2) * BK * 2;                // 16 KB: this CTA's half of the 256 weight rows
+constexpr int RA_A_BYTES = RA_KB * BM * BK * 2;                     // 128 KB
+constexpr int RA_XPOSE_FLOATS = 512;                                // 2 KB per epilogue warp (bf16-row path only)
+constexpr int RA_SMEM_BYTES = RA_A_BYTES + RA_B_STAGES * RA_B_STAGE_BYTES + kEpiWarps * RA_XPOSE_FLOATS * 4 + 1024 + 256;
+static_assert(RA_SMEM_BYTES <= 232448, "A-resident pair GEMM: shared memory budget");
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2a_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi, int n_split) {
+  constexpr int P_BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + RA_A_BYTES;
+  const uint32_t staging_base = b_base + RA_B_STAGES * RA_B_STAGE_BYTES;
+  const uint32_t bar_base = staging_base + kEpiWarps * RA_XPOSE_FLOATS * 4;
+  auto a_full = [&](int k) { return bar_base + 8u * k; };
+  auto a_empty = [&](int k) { return bar_base + 8u * (RA_KB + k); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * RA_KB + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * RA_KB + RA_B_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = p.N / P_BN;
+  const int tpu = n_tiles / n_split;                        // N tiles per unit
+  const int num_units = m_pairs * n_split;
+  const int n_kb = p.K / BK;                                // <= RA_KB
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int k = 0; k < RA_KB; ++k) { mbar_init(a_full(k), 1); mbar_init(a_empty(k), 1); }
+    for (int s = 0; s < RA_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += n_clusters, a_phase ^= 1u) {
+        const int m_pair = unit / n_split, part = unit - m_pair * n_split;
+        const int row_a = m_pair * 2 * BM + (int)rank * BM;
+        for (int t = 0; t < tpu; ++t) {
+          const int row_b = (part * tpu + t) * P_BN + (int)rank * (P_BN / 2);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            if (t == 0) {                                   // the unit's A tile, k-block by k-block, interleaved with the first tile's B
+              mbar_wait(a_empty(kb), a_phase ^ 1u);
+              if (rank == 0) mbar_expect_tx(a_full(kb), 2u * (uint32_t)(BM * BK * 2));
+              tma_load_2d_pair(smem_base + (uint32_t)(kb * BM * BK * 2), &tmA, kb * BK, row_a, a_full(kb) & kPeerBitMask);
+            }
+            mbar_wait(b_empty(stage), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(b_full(stage), 2u * (uint32_t)RA_B_STAGE_BYTES);
+            tma_load_2d_pair(b_base + (uint32_t)(stage * RA_B_STAGE_BYTES), &tmB, kb * BK, row_b, b_full(stage) & kPeerBitMask);
+            if (++stage == RA_B_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += n_clusters, a_phase ^= 1u) {
+        for (int t = 0; t < tpu; ++t) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P_BN);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(a_full(kb), a_phase);                 // (already complete for every tile but the unit's first)
+            mbar_wait(b_full(stage), phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t adesc = make_smem_desc(smem_base + (uint32_t)(kb * BM * BK * 2));
+              const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(stage * RA_B_STAGE_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit_pair(b_empty(stage), 3);
+              if (t == tpu - 1) umma_commit_pair(a_empty(kb), 3);     // the resident A k-block may be overwritten by the next unit's
+              if (kb == n_kb - 1) umma_commit_pair(tfull_bar(acc), 3);
+            }
+            __syncwarp();
+            if (++stage == RA_B_STAGES) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (16 warps, both CTAs): bf16-row path only =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * RA_XPOSE_FLOATS;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int unit = cluster_id; unit < num_units; unit += n_clusters) {
+      const int m_pair = unit / n_split, part = unit - m_pair * n_split;
+      const int row0 = m_pair * 2 * BM + (int)rank * BM + quarter * 32;
+      for (int t = 0; t < tpu; ++t) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P_BN);
+        epilogue_tile<P_BN, kEpiWarps / 4, Epi, true>(epi, p, row0, (part * tpu + t) * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cta(tempty_bar(acc), 0);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <class Epi>
+int launch_pair_a(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
+  if constexpr (Epi::kBf16Rows) {
+    const int n_tiles = p.N / 256;
+    if (p.N % 256 != 0 || n_tiles % 2 != 0 || p.passes != 1 || p.K > RA_KB * BK || !epi.bf16_rows()) {
+      set_error("gemm_tc: the A-resident pair kernel needs bf16 row outputs, one pass, K <= %d and N a multiple of 512 (N %d K %d passes %d)", RA_KB * BK, p.N, p.K, p.passes);
+      return -1;
+    }
+    static size_t attr_done[kMaxDevices] = {0};
+    ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2a_kernel<Epi>, (size_t)RA_SMEM_BYTES, attr_done));
+    const int n_split = 2;
+    const int units = ((p.M + 2 * BM - 1) / (2 * BM)) * n_split;
+    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
+    ASR_CUDA_OK(launch_pdl(gemm_tc2a_kernel<Epi>, dim3(2 * pairs), dim3(kThreads), RA_SMEM_BYTES, st, tmA, tmB128, p, epi, n_split));
+    return 0;
+  } else {
+    set_error("gemm_tc: the A-resident pair kernel exists for bf16-row epilogues only");
+    return -1;
+  }
 }
 
 template <int BN, class Epi>
@@ -432,7 +642,9 @@ int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p
   if (p.M <= 0) return 0;
   if (p.K % BK != 0) { set_error("gemm_tc: K=%d not a multiple of %d", p.K, BK); return -1; }
   switch (bn) {
-    case kPairTile: return launch_pair<Epi>(tmA, tmB, p, epi, num_sms, st);   // tmB must be the 128-row-box map
+    case kPairTile: return launch_pair<Epi, 256>(tmA, tmB, p, epi, num_sms, st);      // tmB must be the 128-row-box map
+    case kPairTile128: return launch_pair<Epi, 128>(tmA, tmB, p, epi, num_sms, st);   // tmB must be the 64-row-box map
+    case kPairTileA: return launch_pair_a<Epi>(tmA, tmB, p, epi, num_sms, st);        // tmB must be the 128-row-box map
     case 64: return launch_bn<64, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 128: return launch_bn<128, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 256: return launch_bn<256, Epi>(tmA, tmB, p, epi, num_sms, st);
@@ -442,6 +654,7 @@ int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p
 }
 
 template int gemm_tc<EpiF32>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiF32&, int, int, cudaStream_t);
+template int gemm_tc<EpiNull>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiNull&, int, int, cudaStream_t);
 template int gemm_tc<EpiOperand>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiOperand&, int, int, cudaStream_t);
 template int gemm_tc<EpiQKV<float>>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiQKV<float>&, int, int, cudaStream_t);
 template int gemm_tc<EpiQKV<bf16>>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiQKV<bf16>&, int, int, cudaStream_t);

@@ -39,6 +39,10 @@ CASES = [
     (2432, 512, 2048, 512, 0),       # odd number of 128-row tiles (19): the peer CTA of the last pair is all padding
     (1000, 1536, 512, 512, 1),       # pair kernel, EXACT passes
     (300, 804, 512, 128, 1),
+    (256, 128, 64, 513, 0),          # bn = 513: cta_group::2 kernel with 256 x 128 tiles and four TMEM accumulator stages
+    (5120, 1536, 512, 513, 0),       # 240 pair tiles on 74 pairs: the accumulator ring wraps
+    (5000, 2048, 512, 513, 0),       # ragged M
+    (1000, 1536, 512, 513, 1),       # EXACT passes
 ]
 
 

@@ -479,6 +479,24 @@ def test_fused_feed_forward_kernel_is_bit_identical(packed_weights, golden, meta
     assert np.abs(em - case["emission"]).max() < FAST_TOL
 
 
+def test_a_resident_pair_gemm_is_bit_identical(packed_weights, monkeypatch):
+    """QKV and FFN1 at large batches through the A-resident cta_group::2 kernel (the 128 x 512 A tile stays in shared memory while
+    the unit's N tiles stream only B) against the streaming pair kernel: same MMA shapes and k order => bit-identical log-probs.
+    700 streams = 55 row blocks (the last one ragged), 110 units on 74 pairs: units of different blocks follow each other in a pair."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(43)
+    n = 700
+    pcm = rng.integers(-4000, 4000, size=(3, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    outs = []
+    for resident in (False, True):
+        monkeypatch.setenv("ASR_B200_PAIR_A", "1" if resident else "0")
+        with Engine(model_cfg(PRECISION_FAST, max_batch=n, max_sessions=n), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n)]
+            outs.append(np.stack([e.step(sl, pcm[t], want_logprobs=True).logprobs for t in range(3)]))
+    assert np.isfinite(outs[1]).all()
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch):
     """The persistent double-buffered attention kernel (taken from 148 streams per step on) forced for a small ragged batch:
     same fragments and summation order as the CTA-per-stream kernel => bit-identical log-probs, at every left-context fill."""

@@ -204,6 +204,9 @@ ASR_API int asr_convmod_step(AsrConvModule* m, int32_t n, const int32_t* slots, 
 ASR_API int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res,
                               const float* g1, const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows,
                               int32_t compact_seg, float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int32_t pair, int device);
+/* Diagnostic: mean ms per launch of the tcgen05 GEMM on operands already in HBM.  bn: 64 / 128 / 256 = 1-CTA tile width, 512 = cta_group::2
+ * pair (256 x 256), 513 = pair with 256 x 128 tiles and four accumulator stages, 514 = pair with the A tile resident in shared memory (epi 2
+ * only).  epi_kind: 0 fp32 store, 1 + bias + fp32 residual, 2 bias + GELU -> bf16 operand, 3 none (accumulator dropped: the mainloop alone). */
 ASR_API int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, int32_t epi_kind, int32_t iters, float* ms_out, int device);
 
 #ifdef __cplusplus

@@ -348,8 +348,8 @@ int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M,
   ProfScope ps(e, cat);
   if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
   int bn = pick_bn(e, M, w.N);
-  // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand ingest per SM).  The 1-CTA 128 x 256 tile needs 96 B/clk/SM from L2
-  // at full tensor rate against a chip-wide cap of ~42 B/clk/SM, the pair 64 B/clk/SM.  Measured on B200
+  // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand traffic per SM: 32 instead of 48 KB per k-block through L2 -> shared
+  // memory -> tensor core).  Measured on B200
   // (profiles/r01_gemm_sweep_*.txt): pair wins at K = 2048 (FFN2 127 vs 138 us) and, since the packed-math GELU epilogue stopped
   // being the limiter, also at K = 512 for large M (FFN1 150 vs 157 us, QKV 116 vs 121 us); at small M the coupled epilogues lose.
   const int k_eff = w.K * (e->geo.split ? 3 : 1);

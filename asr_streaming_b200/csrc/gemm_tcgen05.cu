@@ -295,9 +295,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA loads its own
 // 128 rows of A and HALF of the B tile (128 of the 256 weight rows); the leader's single thread issues
 // tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads A/B from both CTAs' shared memory and writes each CTA's 128
-// accumulator rows into that CTA's TMEM.  Per SM and k-block this ingests 32 KB instead of 48 KB from L2 — the 1-CTA
-// kernel sits at ~40 B/clk/SM, the chip-wide L2 cap (profiles/r01_ncu_full_4096streams_gemm_attention.csv) — and the
-// smaller stage allows a 6-deep ring.
+// accumulator rows into that CTA's TMEM.  Per SM and k-block this moves 32 KB instead of 48 KB through L2 -> shared memory -> tensor
+// core (TMA writes + UMMA operand reads of the 1-CTA 128 x 256 tile want 192 B/clk of a 128 B/clk shared-memory pipe at full tensor
+// rate, the pair 128), and the smaller stage allows a deeper ring.  Alone (null epilogue) this mainloop runs at 1.75 PFLOP/s even at
+// K = 512; with an epilogue the K = 512 GEMMs stop at ~1.07 PFLOP/s because the epilogue's own shared-memory round trip queues behind
+// that saturated pipe (profiles/r01_epilogue_clock64_timing.log).
 //   full[s]   : leader's barrier only; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA), leader arms 64 KB
 //   empty[s]  : per CTA, arrived by the leader's tcgen05.commit multicast (mask 0b11)
 //   tfull[a]  : per CTA, same multicast commit after the last k-block
@@ -454,9 +456,10 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmPro
 }
 
 // ==========================================================================================================
-// A-RESIDENT CTA-pair variant for short K (K <= 512: QKV, FFN1).  These GEMMs are bound by the L2 -> SM operand ingest, not by the
-// tensor pipe or the epilogue (halving the tile width, i.e. 1.5 x the ingest per flop, costs 30 %; a third of the epilogue instructions
-// changes nothing).  So the A tile (this CTA's 128 rows x K, 128 KB) is loaded ONCE per work unit and stays in shared memory while the
+// A-RESIDENT CTA-pair variant for short K (K <= 512: QKV, FFN1) — an experiment kept as an opt-in (ASR_B200_PAIR_A=1): bit-identical
+// to gemm_tc2_kernel and 7 % SLOWER (128 vs 119 us on 81,920 x 1536 x 512): the operand traffic it saves is not what bounds these GEMMs
+// (their mainloop alone runs at 1.75 PFLOP/s), and the unit boundary exposes the A reload.
+// The A tile (this CTA's 128 rows x K, 128 KB) is loaded ONCE per work unit and stays in shared memory while the
 // unit's N tiles stream only their B operand (16 KB per k-block and CTA instead of 32): a unit = one 256-row block x half of the N
 // tiles (two units per block keep the 74 pairs balanced: 640 units / 74), ingest per tile 128 KB + 128/3 (QKV) or 128/4 (FFN1) KB
 // instead of 256 KB.  It fits because the bf16-row epilogue needs 2 KB of staging per warp instead of 4.6 KB.

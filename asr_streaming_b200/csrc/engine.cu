@@ -9,6 +9,7 @@
 #include <chrono>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/asr_b200.h"
@@ -97,6 +98,11 @@ struct AsrEngine {
   int no_pair = 0;
   int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
   int no_fuse2 = 0;             // ASR_B200_NO_LN_FUSE2=1: second LayerNorm statistics by their own TMEM pass
+  // CUDA graphs of the per-step kernel chain for small batches (launch-bound: ~290 launches of a few us each).  Key = (streams, staging
+  // buffer, pcm format, log-probs wanted, beam): captured the second time a key is seen, replayed afterwards.  ASR_B200_NO_GRAPHS=1: off.
+  struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int seen = 0; };
+  std::unordered_map<uint64_t, StepGraph> graphs;
+  int use_graphs = 1, graph_max_streams = 128, graph_max_entries = 256;
   int pair_a = 0;               // ASR_B200_PAIR_A=1: short-K pair GEMMs with the A tile resident in shared memory
   int pair128 = 0;              // ASR_B200_PAIR128=1: short-K pair GEMMs (QKV, FFN1) with 256 x 128 tiles and four accumulator stages
   int mlp_fused = 0;            // ASR_B200_MLP_FUSED=1: the feed-forward block as ONE kernel at large batches (measured 9.4 vs 8.5 ms per step at
@@ -506,6 +512,55 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   return 0;
 }
 
+void drop_step_graphs(AsrEngine* e) {
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
+
+// The full per-step chain, replayed from a CUDA graph when the batch is small enough to be launch-bound.
+int run_step_chain(AsrEngine* e, int n, int pcm_format, bool want_logprobs) {
+  const Geo& g = e->geo;
+  if (!e->use_graphs || e->prof_on || n > e->graph_max_streams) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
+  const char* asm_env = getenv("ASR_B200_ATTN_STREAM_MIN");           // read per launch by the attention dispatch: part of what a graph froze
+  const uint64_t key = ((uint64_t)n << 8) | ((uint64_t)(e->act_slots == e->d_slots2.as<int>()) << 0) | ((uint64_t)(pcm_format == ASR_PCM_F32) << 1) |
+                       ((uint64_t)want_logprobs << 2) | ((uint64_t)(e->beam > 0) << 3) | ((uint64_t)((asm_env ? atoi(asm_env) : 148) & 0xffff) << 32);
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    if ((int)e->graphs.size() >= e->graph_max_entries) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
+    it = e->graphs.emplace(key, AsrEngine::StepGraph()).first;
+  }
+  AsrEngine::StepGraph& sg = it->second;
+  if (sg.exec) {
+    ASR_CUDA_OK(cudaGraphLaunch(sg.exec, e->stream));
+    e->launches += sg.launches;
+    return 0;
+  }
+  if (sg.seen++ == 0 || sg.seen < 0) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);   // first sight: direct (also warms every per-device cache)
+  // second sight: capture, instantiate, launch
+  const uint64_t l0 = e->launches;
+  if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); sg.seen = -1000000; return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs); }
+  const int rc = run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+  const uint64_t captured = e->launches - l0;
+  e->launches = l0;
+  if (rc || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    sg.seen = -1000000;                                   // never try this key again
+    if (rc) return -1;
+    return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) { cudaGetLastError(); sg.seen = -1000000; return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs); }
+  sg.exec = exec; sg.launches = captured;
+  ASR_CUDA_OK(cudaGraphLaunch(sg.exec, e->stream));
+  e->launches += sg.launches;
+  return 0;
+}
+
 int check_step_args(AsrEngine* e, int n, const int32_t* slots) {
   if (!e) { set_error("null engine"); return -1; }
   if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch = %d]", n, e->cfg.max_batch); return -1; }
@@ -598,7 +653,7 @@ int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int 
     ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
     ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     use_buffer(e, b);
-    if (run_pipeline(e, n, fmt, e->geo.n_layers, true, want_lp)) return -1;
+    if (run_step_chain(e, n, fmt, want_lp)) return -1;
     if (enqueue_d2h(e, b, n, want_lp)) return -1;
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
@@ -635,7 +690,7 @@ int submit_rings(AsrEngine* e, int n, const int32_t* slots, const int16_t* base,
     ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
     ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     use_buffer(e, b);
-    if (run_pipeline(e, n, ASR_PCM_I16, e->geo.n_layers, true, want_lp)) return -1;
+    if (run_step_chain(e, n, ASR_PCM_I16, want_lp)) return -1;
     if (enqueue_d2h(e, b, n, want_lp)) return -1;
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
@@ -688,6 +743,8 @@ void destroy_engine(AsrEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->h_scratch, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
@@ -734,6 +791,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* mf = getenv("ASR_B200_MLP_FUSED")) e->mlp_fused = mf[0] == '1';
   if (const char* p8 = getenv("ASR_B200_PAIR128")) e->pair128 = p8[0] == '1';
   if (const char* pa = getenv("ASR_B200_PAIR_A")) e->pair_a = pa[0] == '1';
+  if (getenv("ASR_B200_NO_GRAPHS")) e->use_graphs = 0;
+  if (const char* gm = getenv("ASR_B200_GRAPH_MAX_STREAMS")) e->graph_max_streams = atoi(gm);
   if (const char* mt = getenv("ASR_B200_MLP_MIN_TILES")) e->mlp_min_tiles = atoi(mt);
   if (const char* qt = getenv("ASR_B200_QUAD_LN_MAX_TILES")) e->quad_ln_max_tiles = atoi(qt);
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
@@ -1115,7 +1174,7 @@ int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
   if (n <= 0 || n > e->cfg.max_batch) { set_error("n = %d outside (0, max_batch]", n); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   use_buffer(e, 0);
-  if (run_pipeline(e, n, e->staged_fmt, e->geo.n_layers, true, want_logprobs != 0)) return -1;
+  if (run_step_chain(e, n, e->staged_fmt, want_logprobs != 0)) return -1;
   ++e->steps; e->stream_chunks += n;
   return 0;
 }
@@ -1197,6 +1256,7 @@ int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k) {
     set_error("asr_set_beam: beam must be in [0, %d], cand_k in [1, %d]", BEAM_MAX, BEAM_CAND_MAX); return -1;
   }
   ASR_CUDA_OK(cudaSetDevice(e->device));
+  drop_step_graphs(e);                                     // the beam kernel's arguments are part of what the graphs captured
   if (beam > 0 && !e->bm_tokens.p) {
     const size_t S = e->cfg.max_sessions, B = e->cfg.max_batch;
     if (e->bm_n.alloc(4 * S) || e->bm_cur.alloc(4 * S) || e->bm_len.alloc(4 * S * BEAM_MAX) || e->bm_last.alloc(4 * S * BEAM_MAX) ||

@@ -497,6 +497,36 @@ def test_a_resident_pair_gemm_is_bit_identical(packed_weights, monkeypatch):
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_cuda_graph_replay_is_bit_identical(packed_weights, monkeypatch):
+    """Small batches replay the per-step kernel chain from a CUDA graph (captured the second time a (streams, staging buffer,
+    format, outputs) key is seen): six chained steps of a 5-stream batch with a mid-sequence reset and a change of the batch size,
+    against the same engine with ASR_B200_NO_GRAPHS=1 — identical log-probs, ids and incremental tokens; the launch counter keeps
+    counting the kernels of replayed steps."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    rng = np.random.default_rng(47)
+    n = 5
+    pcm = rng.integers(-4000, 4000, size=(6, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    runs = []
+    for graphs in (False, True):
+        if graphs:
+            monkeypatch.delenv("ASR_B200_NO_GRAPHS", raising=False)
+        else:
+            monkeypatch.setenv("ASR_B200_NO_GRAPHS", "1")
+        with Engine(model_cfg(PRECISION_FAST, max_batch=8, max_sessions=8), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n)]
+            out = []
+            for t in range(6):
+                if t == 3:
+                    e.reset_sessions(sl[1:3])
+                k = n if t != 4 else 3                                   # another key in between
+                r = e.step(sl[:k], pcm[t, :k], want_logprobs=True)
+                out.append((r.logprobs.copy(), r.argmax_ids.copy(), [list(x) for x in r.new_tokens]))
+            runs.append((out, e.stats()["kernel_launches"]))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert runs[0][1] == runs[1][1]
+
+
 def test_streaming_attention_kernel_is_bit_identical(packed_weights, monkeypatch):
     """The persistent double-buffered attention kernel (taken from 148 streams per step on) forced for a small ragged batch:
     same fragments and summation order as the CTA-per-stream kernel => bit-identical log-probs, at every left-context fill."""

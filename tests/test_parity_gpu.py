@@ -498,9 +498,9 @@ def test_a_resident_pair_gemm_is_bit_identical(packed_weights, monkeypatch):
 
 
 def test_cuda_graph_replay_is_bit_identical(packed_weights, monkeypatch):
-    """Small batches replay the per-step kernel chain from a CUDA graph (captured the second time a (streams, staging buffer,
+    """Small batches can replay the per-step kernel chain from a CUDA graph (captured the second time a (streams, staging buffer,
     format, outputs) key is seen): six chained steps of a 5-stream batch with a mid-sequence reset and a change of the batch size,
-    against the same engine with ASR_B200_NO_GRAPHS=1 — identical log-probs, ids and incremental tokens; the launch counter keeps
+    (ASR_B200_GRAPHS=1; opt-in) against the plain launches — identical log-probs, ids and incremental tokens; the launch counter keeps
     counting the kernels of replayed steps."""
     from asr_streaming_b200 import Engine, PRECISION_FAST
     rng = np.random.default_rng(47)
@@ -508,10 +508,7 @@ def test_cuda_graph_replay_is_bit_identical(packed_weights, monkeypatch):
     pcm = rng.integers(-4000, 4000, size=(6, n, O.CANONICAL.chunk_length)).astype(np.int16)
     runs = []
     for graphs in (False, True):
-        if graphs:
-            monkeypatch.delenv("ASR_B200_NO_GRAPHS", raising=False)
-        else:
-            monkeypatch.setenv("ASR_B200_NO_GRAPHS", "1")
+        monkeypatch.setenv("ASR_B200_GRAPHS", "1" if graphs else "0")
         with Engine(model_cfg(PRECISION_FAST, max_batch=8, max_sessions=8), packed_weights) as e:
             sl = [e.open_session() for _ in range(n)]
             out = []

@@ -27,6 +27,12 @@ namespace {
 using namespace tc;
 
 constexpr int LN_N = 512;
+#ifdef ASR_EPI_TIMING
+__device__ unsigned long long g_ln_clk[8];                  // [0] tiles, [1] wait tfull, [2] R1, [3] exchange(s), [4] R2
+#define LN_T(var) const long long var = clock64()
+#else
+#define LN_T(var)
+#endif
 constexpr int kMaxHiddenTiles = 8;                         // MLP form: ffn <= 8 * 256
 constexpr int L_STATS4_BYTES = 4 * BM * 16 + 2 * BM * 16;      // float4 payload of the derived second-LN statistics (PAIR shape only)
 // Three shapes of the same kernel (SHAPE):
@@ -514,8 +520,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.global.L2 [%0];" ::"l"(r + wq * 32));
         if (CHUNKS == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (wq + 4) * 32));
       }
+      LN_T(lt0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      LN_T(lt1);
 
       float raw[32];
       // PAIR shape with two LayerNorms: the statistics of y = LN_a(v) are derived from chunk-centred weighted moments of v
@@ -560,6 +568,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         q_a = q_a + q_b + 16.0f * d * d;                     // Chan: n_a n_b / (n_a + n_b) = 16
         s_a += s_b;
       }
+      LN_T(lt2);
       RowStats st = exchange_row_stats<NSPLIT, N_T>(s_a, q_a, X, round++);
       RowStats st2 = st;                                     // statistics of y (two-LN forms)
 
@@ -615,6 +624,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       // ---------------- R2: fp32 row + bf16 LayerNorm(row) with full-line stores
+      LN_T(lt3);
       float mu[8], rs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -672,6 +682,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
+#ifdef ASR_EPI_TIMING
+      if (blockIdx.x == 0 && threadIdx.x == 64) {
+        const long long lt4 = clock64();
+        atomicAdd(&g_ln_clk[0], 1ull); atomicAdd(&g_ln_clk[1], (unsigned long long)(lt1 - lt0)); atomicAdd(&g_ln_clk[2], (unsigned long long)(lt2 - lt1));
+        atomicAdd(&g_ln_clk[3], (unsigned long long)(lt3 - lt2)); atomicAdd(&g_ln_clk[4], (unsigned long long)(lt4 - lt3));
+      }
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -682,6 +699,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+#ifdef ASR_EPI_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 64 && g_ln_clk[0]) {
+    printf("gemm_ln<%d,%d> K %d epilogue warp 0 of CTA 0: %llu tiles, per tile: wait tfull %llu clk, R1 %llu, exchange %llu, R2 %llu\n", SHAPE, (int)MLP, p.K, g_ln_clk[0],
+           g_ln_clk[1] / g_ln_clk[0], g_ln_clk[2] / g_ln_clk[0], g_ln_clk[3] / g_ln_clk[0], g_ln_clk[4] / g_ln_clk[0]);
+    g_ln_clk[0] = g_ln_clk[1] = g_ln_clk[2] = g_ln_clk[3] = g_ln_clk[4] = 0;
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();                                       // the peer may still read this CTA's statistics through DSMEM
   if (warp == 1) {

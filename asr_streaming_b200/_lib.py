@@ -80,6 +80,7 @@ SIGNATURES = {
     "asr_convmod_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "asr_debug_gemm_ln": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.POINTER(C.c_float), C.c_int32, C.c_int]),
+    "asr_pipeline_gpu_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int32]),
     "asr_debug_gemm_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int]),
 }
 

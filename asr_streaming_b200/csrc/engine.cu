@@ -157,6 +157,8 @@ struct AsrEngine {
   int* act_slots = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0[2] = {nullptr, nullptr}, ev_t1[2] = {nullptr, nullptr};     // timing: kernel chain + D2H of a pipelined step on the engine stream
+  double pipe_gpu_ms = 0.0; uint64_t pipe_gpu_n = 0;
   // asr_session_reset_many: ring of pinned slot lists (+ the event of each list's H2D) so that back-to-back calls never wait
   static constexpr int kResetRing = 4;
   cudaEvent_t ev_reset[kResetRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -655,8 +657,10 @@ int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int 
     ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
     ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     use_buffer(e, b);
+    if (e->ev_t0[b]) cudaEventRecord(e->ev_t0[b], e->stream);
     if (run_step_chain(e, n, fmt, want_lp)) return -1;
     if (enqueue_d2h(e, b, n, want_lp)) return -1;
+    if (e->ev_t1[b]) cudaEventRecord(e->ev_t1[b], e->stream);
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
   e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
@@ -692,8 +696,10 @@ int submit_rings(AsrEngine* e, int n, const int32_t* slots, const int16_t* base,
     ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
     ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     use_buffer(e, b);
+    if (e->ev_t0[b]) cudaEventRecord(e->ev_t0[b], e->stream);
     if (run_step_chain(e, n, ASR_PCM_I16, want_lp)) return -1;
     if (enqueue_d2h(e, b, n, want_lp)) return -1;
+    if (e->ev_t1[b]) cudaEventRecord(e->ev_t1[b], e->stream);
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
   e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
@@ -708,6 +714,10 @@ int collect_step(AsrEngine* e, int ticket, const AsrStepOut* out) {
   if (pd.n) {
     ASR_CUDA_OK(cudaSetDevice(e->device));
     ASR_CUDA_OK(cudaEventSynchronize(e->ev_done[ticket]));
+    if (e->ev_t0[ticket] && e->ev_t1[ticket]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e->ev_t0[ticket], e->ev_t1[ticket]) == cudaSuccess) { e->pipe_gpu_ms += ms; ++e->pipe_gpu_n; } else cudaGetLastError();
+    }
     deliver(e, ticket, pd.n, pd.want_lp, out);
   }
   pd.active = 0;
@@ -757,7 +767,8 @@ void destroy_engine(AsrEngine* e) {
   }
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
+  for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+                                if (e->ev_t0[i]) cudaEventDestroy(e->ev_t0[i]); if (e->ev_t1[i]) cudaEventDestroy(e->ev_t1[i]); }
   if (e->h_reset) cudaFreeHost(e->h_reset);
   for (auto ev : e->ev_reset) if (ev) cudaEventDestroy(ev);
   e->d_reset.free();
@@ -922,7 +933,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     bool ev_ok = true;
     for (int i = 0; i < 2; ++i)
       ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreate(&e->ev_t0[i]) == cudaSuccess && cudaEventCreate(&e->ev_t1[i]) == cudaSuccess;
     for (int i = 0; i < AsrEngine::kResetRing; ++i) ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_reset[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok) { set_error("cudaEventCreate failed"); break; }
     if (cudaMallocHost((void**)&e->h_reset, 4 * (size_t)cfg->max_sessions * AsrEngine::kResetRing) != cudaSuccess ||
@@ -1178,6 +1190,14 @@ int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
   use_buffer(e, 0);
   if (run_step_chain(e, n, e->staged_fmt, want_logprobs != 0)) return -1;
   ++e->steps; e->stream_chunks += n;
+  return 0;
+}
+
+int asr_pipeline_gpu_time(AsrEngine* e, double* total_ms, uint64_t* n_steps, int32_t reset) {
+  if (!e || !total_ms || !n_steps) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  *total_ms = e->pipe_gpu_ms; *n_steps = e->pipe_gpu_n;
+  if (reset) { e->pipe_gpu_ms = 0.0; e->pipe_gpu_n = 0; }
   return 0;
 }
 

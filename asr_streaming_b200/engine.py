@@ -302,6 +302,12 @@ class Engine:
         _lib.check(self.lib, self.lib.asr_get_stats(self._h, C.byref(s)), "asr_get_stats")
         return {k: getattr(s, k) for k, _ in _lib.AsrStatsC._fields_}
 
+    def pipeline_gpu_time(self, reset: bool = True):
+        """(total device ms, steps) of the pipelined steps collected so far (kernel chain + result D2H on the engine stream)."""
+        ms, n = C.c_double(), C.c_uint64()
+        _lib.check(self.lib, self.lib.asr_pipeline_gpu_time(self._h, C.byref(ms), C.byref(n), int(reset)), "asr_pipeline_gpu_time")
+        return ms.value, int(n.value)
+
     PROF_NAMES = ("fbank", "gemm_input_linear", "layernorm", "gemm_qkv", "attention", "gemm_out_proj", "gemm_ffn1", "gemm_ffn2",
                   "gemm_ctc1", "gemm_ctc2", "ctc_greedy", "beam")
 

@@ -489,24 +489,31 @@ def run_ours(args):
         for _ in range(lat_passes):
             dt, n_run = wl.run_sync()
             lat_ms.append(1e3 * dt)
-        wl.run_pipelined(2, streams // 2)
+        # two ticks per pass (<= streams / 2 rows each, two in flight): the GPU is busy 97 % of the wall time (asr_pipeline_gpu_time: 15.8 of
+        # 16.3 ms per pass).  One tick per pass needs 7 % less GPU time (14.7 ms) but exposes the host side of the loop (feed + gather +
+        # bookkeeping of 3,275 sessions in one Python thread): 20.2 ms per pass, measured.  ASR_BENCH_E2E_ROWS overrides.
+        e2e_rows = int(os.environ.get("ASR_BENCH_E2E_ROWS", streams // 2))
+        wl.run_pipelined(2, e2e_rows)
         barrier()
         c0 = (wl.run_chunks, wl.skipped_chunks, wl.endpoints)
         h0 = (wl.t_submit, wl.t_collect, wl.t_after, wl.n_ticks)
+        eng.pipeline_gpu_time(reset=True)
         t0 = time.perf_counter()
-        wl.run_pipelined(e2e_steps, streams // 2)
+        wl.run_pipelined(e2e_steps, e2e_rows)
         barrier()
+        gpu_busy_ms, gpu_busy_n = eng.pipeline_gpu_time(reset=True)
         e2e_s = max_over_ranks(time.perf_counter() - t0) * (args.steps / e2e_steps)      # normalised to K steps (e2e_steps of them were run)
         run_c, skip_c, end_c = wl.run_chunks - c0[0], wl.skipped_chunks - c0[1], wl.endpoints - c0[2]
         per_chunk_in = cfg.chunk_length * 2 + 4
         per_chunk_out = cfg.seg_rows * 4 * 2 + 3 * 4 + 4 * 256 + 8
         h2d, d2h = run_c * per_chunk_in // e2e_steps, run_c * per_chunk_out // e2e_steps
-        extra["ragged"] = {"sessions": streams, "batch_assembly": "device gather from pinned rings" if dev_gather else "host gather + DMA", "ticks_in_flight": 2, "max_rows_per_tick": streams // 2, "e2e_steps_run": e2e_steps,
+        extra["ragged"] = {"sessions": streams, "batch_assembly": "device gather from pinned rings" if dev_gather else "host gather + DMA", "ticks_in_flight": 2, "max_rows_per_tick": e2e_rows, "e2e_steps_run": e2e_steps,
                            "decoded_chunks_per_pass": run_c / e2e_steps, "vad_skipped_chunks_per_pass": skip_c / e2e_steps,
                            "endpoints_per_pass": end_c / e2e_steps,
                            "host_ms_per_tick": {"submit_tick (ready + gate + gather + enqueue)": 1e3 * (wl.t_submit - h0[0]) / max(1, wl.n_ticks - h0[3]),
                                                 "collect_tick (wait + bookkeeping + rules)": 1e3 * (wl.t_collect - h0[1]) / max(1, wl.n_ticks - h0[3]),
                                                 "scripted endpoints": 1e3 * (wl.t_after - h0[2]) / max(1, wl.n_ticks - h0[3])},
+                           "gpu_busy_ms_per_pass": gpu_busy_ms / e2e_steps, "gpu_steps_per_pass": gpu_busy_n / e2e_steps,
                            "e2e_counts": "audio-seconds of the chunks actually decoded (VAD-skipped chunks are excluded from e2e.value)"}
         e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / e2e_steps
     else:

@@ -200,6 +200,10 @@ ASR_API int asr_convmod_destroy(AsrConvModule* m);
 ASR_API int asr_convmod_reset(AsrConvModule* m, int32_t n, const int32_t* slots);
 ASR_API int asr_convmod_step(AsrConvModule* m, int32_t n, const int32_t* slots, const float* x, float* y);
 
+/* Device time (CUDA events on the engine stream: kernel chain + result D2H) of the pipelined steps collected so far: with the wall time of
+ * the same ticks it says how much of a tick the GPU was busy.  reset != 0 clears the counters. */
+ASR_API int asr_pipeline_gpu_time(AsrEngine* e, double* total_ms, uint64_t* n_steps, int32_t reset);
+
 /* Diagnostic: the GEMM (N = 512) with residual add + LayerNorm(s) fused into the epilogue (csrc/gemm_ln.cu) on host operands. */
 ASR_API int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* A, const float* W, const float* bias, const float* res,
                               const float* g1, const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows,

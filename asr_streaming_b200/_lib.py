@@ -8,7 +8,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class AsrLibraryError(RuntimeError):
@@ -25,7 +25,33 @@ class AsrConfigC(C.Structure):
 class AsrStepOutC(C.Structure):
     _fields_ = [("argmax_ids", C.c_void_p), ("new_tokens", C.c_void_p), ("n_new", C.c_void_p), ("blank_frames", C.c_void_p),
                 ("has_token", C.c_void_p), ("logprobs", C.c_void_p), ("beam_tokens", C.c_void_p), ("beam_len", C.c_void_p),
-                ("beam_score", C.c_void_p)]
+                ("beam_score", C.c_void_p), ("has_text", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class AsrSchedConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("capacity", "chunk_length", "segment_length", "buffer_length", "seg_rows", "sample_rate", "max_batch",
+                                         "backlog_chunks", "max_tokens", "device_gather")] + [("relative_cost", C.c_double)]
+
+
+class AsrSchedArraysC(C.Structure):
+    _fields_ = [("audio", C.c_void_p), ("audio_row_samples", C.c_int64), ("rd", C.c_void_p), ("wr", C.c_void_p), ("active", C.c_void_p),
+                ("inflight", C.c_void_p), ("slot", C.c_void_p), ("tok", C.c_void_p), ("ntok", C.c_void_p), ("n_frames", C.c_void_p),
+                ("chunk_processed", C.c_void_p), ("chunk_processed_total", C.c_void_p), ("trailing", C.c_void_p), ("contain_token", C.c_void_p),
+                ("segment", C.c_void_p), ("last_served", C.c_void_p), ("relative_cost", C.c_void_p), ("overflow", C.c_void_p)]
+
+
+class AsrSchedPlanC(C.Structure):
+    _fields_ = [("tick", C.c_int32), ("n", C.c_int32), ("rows", C.c_void_p), ("slots", C.c_void_p), ("offsets", C.c_void_p),
+                ("n_skipped", C.c_int32), ("skipped", C.c_void_p)]
+
+
+class AsrSchedResultC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("rows", C.c_void_p), ("n_new", C.c_void_p), ("new_tokens", C.c_void_p), ("final_flags", C.c_void_p),
+                ("final_rule", C.c_void_p), ("overflow", C.c_void_p), ("n_skipped", C.c_int32), ("skipped", C.c_void_p), ("n_final", C.c_int32),
+                ("final_rows", C.c_void_p), ("final_rule_of", C.c_void_p), ("final_ntok", C.c_void_p), ("final_tok_off", C.c_void_p),
+                ("final_utt", C.c_void_p), ("final_tok", C.c_void_p), ("argmax_ids", C.c_void_p), ("blank_frames", C.c_void_p),
+                ("has_token", C.c_void_p), ("has_text", C.c_void_p), ("flags", C.c_void_p), ("beam_tokens", C.c_void_p), ("beam_len", C.c_void_p),
+                ("beam_score", C.c_void_p), ("logprobs", C.c_void_p)]
 
 
 class AsrStatsC(C.Structure):
@@ -46,6 +72,7 @@ SIGNATURES = {
     "asr_session_reset": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_session_close": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_session_reset_many": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "asr_set_silent_ids": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "asr_gather_pcm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "asr_pcm_peaks": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "asr_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
@@ -73,6 +100,7 @@ SIGNATURES = {
     "asr_debug_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "asr_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int]),
+    "asr_debug_gemm_operand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "asr_convmod_weights_count": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "asr_convmod_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]),
     "asr_convmod_destroy": (C.c_int, [C.c_void_p]),
@@ -81,6 +109,22 @@ SIGNATURES = {
     "asr_debug_gemm_ln": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.POINTER(C.c_float), C.c_int32, C.c_int]),
     "asr_pipeline_gpu_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int32]),
+    "asr_sched_create": (C.c_int, [C.POINTER(AsrSchedConfigC), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "asr_sched_destroy": (C.c_int, [C.c_void_p]),
+    "asr_sched_arrays": (C.c_int, [C.c_void_p, C.POINTER(AsrSchedArraysC)]),
+    "asr_sched_set_rules": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "asr_sched_open": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "asr_sched_close": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_sched_reset_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "asr_sched_accept": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "asr_sched_ready": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "asr_sched_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(AsrSchedPlanC)]),
+    "asr_sched_commit": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrSchedResultC)]),
+    "asr_sched_update": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrStepOutC)]),
+    "asr_sched_endpoints": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrSchedResultC)]),
+    "asr_sched_abort": (C.c_int, [C.c_void_p, C.c_int32]),
+    "asr_sched_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(AsrSchedResultC), C.POINTER(C.c_int32)]),
+    "asr_sched_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AsrSchedResultC)]),
     "asr_debug_gemm_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int]),
 }
 

@@ -7,7 +7,7 @@
 //   ext(i, k)             : p_nb' = (tok_k == last(i) ? p_b(i) : p_tot(i)) + lp[tok_k]
 //   next beam             = the `beam` best by logaddexp(p_b', p_nb'), ties to the lower enumeration index.
 // Prefix identity is a 64-bit rolling hash + length; token strings live in a per-session double buffer in HBM
-// ([2][16][256] int16) and are copied warp-parallel when a beam entry is (re)built.
+// ([2][16][1024] int16) and are copied warp-parallel, 16 bytes per lane, when a beam entry is (re)built.
 #include "kernels.cuh"
 
 namespace asr {
@@ -166,7 +166,12 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
         pnbn = ((S.len[src] > 0 && S.last[src] == app) ? S.pb[src] : S.ptot[src]) + S.cand_lp[k];
       }
       const int L = S.len[src];
-      for (int i = lane; i < L; i += 32) dst_buf[t * BEAM_MAX_LEN + i] = src_buf[src * BEAM_MAX_LEN + i];
+      {                                                            // rows are BEAM_MAX_LEN * 2 bytes apart and 16-byte aligned: whole uint4 pieces
+        const uint4* s4 = reinterpret_cast<const uint4*>(src_buf + src * BEAM_MAX_LEN);
+        uint4* d4 = reinterpret_cast<uint4*>(dst_buf + t * BEAM_MAX_LEN);
+        for (int i = lane; i * 8 < L; i += 32) d4[i] = s4[i];
+      }
+      __syncwarp();
       if (lane == 0) {
         if (app >= 0) dst_buf[t * BEAM_MAX_LEN + L] = (int16_t)app;
         S.o_len[t] = L + (app >= 0); S.o_last[t] = app >= 0 ? app : S.last[src];
@@ -187,9 +192,15 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
   }
   if (lane == 0) { P.n_beam[slot] = nb; P.cur[slot] = cur; }
   const int L0 = S.len[0];
-  const int16_t* best_tok = tok_base + (size_t)cur * BEAM_MAX * BEAM_MAX_LEN;
-  for (int i = lane; i < L0; i += 32) P.out_tokens[(size_t)w * BEAM_MAX_LEN + i] = best_tok[i];
-  if (lane == 0) { P.out_len[w] = L0; P.out_score[w] = lae(S.pb[0], S.pnb[0]); }
+  {
+    const uint4* s4 = reinterpret_cast<const uint4*>(tok_base + (size_t)cur * BEAM_MAX * BEAM_MAX_LEN);
+    uint4* d4 = reinterpret_cast<uint4*>(P.out_tokens + (size_t)w * BEAM_MAX_LEN);
+    for (int i = lane; i * 8 < L0; i += 32) d4[i] = s4[i];
+  }
+  int full = 0;                                                   // a hypothesis that can no longer be extended: the caller must know
+  if (lane < nb) full = S.len[lane] >= P.max_len;
+  full = __any_sync(0xffffffffu, full);
+  if (lane == 0) { P.out_len[w] = L0; P.out_score[w] = lae(S.pb[0], S.pnb[0]); if (full) P.out_flags[w] |= 1; }
 }
 
 __global__ void beam_reset_kernel(BeamParams P, int slot) {

@@ -196,6 +196,7 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 // Diagnostic only (asr_debug_gemm_time epi 3): waits for the accumulator and drops it — the mainloop's own speed.
 struct EpiNull {
   static constexpr bool kBf16Rows = false;
+  static constexpr bool kStreamTiles = false;
   typedef int RowCtx;
   __device__ __forceinline__ RowCtx row_ctx(int, int) const { return 0; }
   __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
@@ -208,6 +209,7 @@ template <> struct IsNullEpi<EpiNull> { static constexpr bool value = true; };
 // out[row, col] = acc (+bias) (+res)        fp32 out; n_valid masks a ragged N (CTC vocab = 804)
 struct EpiF32 {
   static constexpr bool kBf16Rows = false;
+  static constexpr bool kStreamTiles = false;
   float* out;
   const float* bias;   // nullable
   const float* res;    // nullable, same ld as out
@@ -271,10 +273,10 @@ struct EpiOperand {
   // Packed-bf16 row path (see epilogue_tile): bias + activation on the 32 values a thread holds of ITS row (columns col0 ..), then
   // the rows leave as 16-byte pieces.  Same operations in the same order as store() below: bit-identical results.
   static constexpr bool kBf16Rows = true;
+  static constexpr bool kStreamTiles = false;
   __host__ __device__ __forceinline__ bool bf16_rows() const { return lo_off == 0; }
-  // v: 8 values of the thread's row at columns col ..
-  __device__ __forceinline__ void apply8(float* v, int col, int) const {
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+  // v: 8 values of the thread's row; ba / bb: the bias of their columns
+  __device__ __forceinline__ void apply8(float* v, const float4& ba, const float4& bb, int) const {
     if (act == ACT_GELU) {
       f2_unpack(f2_add(f2_pack(v[0], v[1]), f2_pack(ba.x, ba.y)), v[0], v[1]);
       f2_unpack(f2_add(f2_pack(v[2], v[3]), f2_pack(ba.z, ba.w)), v[2], v[3]);
@@ -349,6 +351,8 @@ struct EpiQKV {
   const int* past_len;   // [n_slots]
   int rows, seg_rows, rc_rows, ring, d;
   float qscale;
+  long long kv_row0 = 0;     // stream tiling: first row of this layer's slab in the [rows, d] view of the whole cache
+  int slot_rows = 0;         //                rows per session inside the slab (2 * ring)
   typedef unsigned long long RowCtx;          // T* of column 0 of this tile's section (q | k | v) in the destination row
   __device__ __forceinline__ RowCtx row_ctx(int row, int tile_col0) const {
     const int sec = tile_col0 / d;            // 0: q, 1: k, 2: v
@@ -366,10 +370,10 @@ struct EpiQKV {
   __device__ __forceinline__ void prefetch_tile(int, int, int, RowCtx) const {}
   // Packed-bf16 row path (bf16 K/V cache and q only): same arithmetic as store(), (acc + bias) * scale.
   static constexpr bool kBf16Rows = sizeof(T) == 2;
+  static constexpr bool kStreamTiles = sizeof(T) == 2;       // gemm.cuh kPairTileQKV: M tiles cut along streams, every destination a TMA box
   __host__ __device__ __forceinline__ bool bf16_rows() const { return true; }
-  __device__ __forceinline__ void apply8(float* v, int col, int tile_col0) const {
+  __device__ __forceinline__ void apply8(float* v, const float4& ba, const float4& bb, int tile_col0) const {
     const float sc = tile_col0 < d ? qscale : 1.0f;          // a tile never straddles the q | k | v sections
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col)), bb = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
     v[0] = (v[0] + ba.x) * sc; v[1] = (v[1] + ba.y) * sc; v[2] = (v[2] + ba.z) * sc; v[3] = (v[3] + ba.w) * sc;
     v[4] = (v[4] + bb.x) * sc; v[5] = (v[5] + bb.y) * sc; v[6] = (v[6] + bb.z) * sc; v[7] = (v[7] + bb.w) * sc;
   }

@@ -15,6 +15,7 @@
 #include "../../include/asr_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "sched_hooks.h"
 
 namespace asr {
 
@@ -70,6 +71,7 @@ struct WeightMat {            // one nn.Linear weight as a tcgen05 B operand
 
 struct LayerW {
   WeightMat qkv, o, w1, w2;
+  TsMaps ts_qkv, ts_ffn1;                 // tensor maps + bias (kernel-parameter copy) of the TMA-store epilogues
   const float *bqkv, *bo, *ln_in_g, *ln_in_b, *ln_ff_g, *ln_ff_b, *b1, *b2, *ln_out_g, *ln_out_b;
   const float* ln_out_consts = nullptr;   // LnEpilogue::y_consts of layer_norm_output (device), see gemm.cuh
 };
@@ -79,10 +81,11 @@ struct FbankPlan {
   DevBuf window, tw, w2, mel_start, mel_cnt, mel_off, mel_w;
 };
 
-struct Operand {              // a GEMM A operand buffer + its tensor map
+struct Operand {              // a GEMM A operand buffer + its tensor maps
   DevBuf buf;
   int rows = 0, K = 0, ld = 0, lo_off = 0;
-  CUtensorMap tm;
+  CUtensorMap tm;             // load map: box {64, 128}
+  CUtensorMap tm_st;          // store map of the GEMM that produces it (TMA-store epilogue): box {64, 32}
 };
 
 }  // namespace
@@ -94,8 +97,11 @@ struct AsrEngine {
   AsrConfig cfg;
   Geo geo;
   int device = 0, num_sms = 148;
-  int simt_gemm = 0;
   int no_pair = 0;
+  int tma_store = 1;            // TMA-store epilogues of the bf16-output pair GEMMs (ASR_B200_NO_TMA_STORE=1: LSU epilogue, for A/B)
+  TsMaps ts_ctc1;               // CTC1 (Linear + SiLU): store map of a_ctc + bias
+  CUtensorMap tm_a_ln_seg;      // a_ln as [stream][row][K], segment-row box (stream-tiled Q | K | V projection)
+  bool qkv_ts_ready = false;
   int no_pair_ln = 0;           // ASR_B200_NO_PAIR_LN=1: gemm_ln always in the 2-CTA shape
   int no_fuse2 = 0;             // ASR_B200_NO_LN_FUSE2=1: second LayerNorm statistics by their own TMEM pass
   // CUDA graphs of the per-step kernel chain for small batches (launch-bound: ~290 launches of a few us each).  Key = (streams, staging
@@ -105,8 +111,6 @@ struct AsrEngine {
   struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int seen = 0; };
   std::unordered_map<uint64_t, StepGraph> graphs;
   int use_graphs = 0, graph_max_streams = 128, graph_max_entries = 256;
-  int pair_a = 0;               // ASR_B200_PAIR_A=1: short-K pair GEMMs with the A tile resident in shared memory
-  int pair128 = 0;              // ASR_B200_PAIR128=1: short-K pair GEMMs (QKV, FFN1) with 256 x 128 tiles and four accumulator stages
   int mlp_fused = 0;            // ASR_B200_MLP_FUSED=1: the feed-forward block as ONE kernel at large batches (measured 9.4 vs 8.5 ms per step at
                                 // 4096 streams: both forms are bound by the epilogue warps, not by the 670 MB of hidden-activation traffic the fusion saves)
   int mlp_min_tiles = 34;       // 256-row tiles needed before the feed-forward block runs as the one fused kernel (ASR_B200_MLP_MIN_TILES)
@@ -133,15 +137,18 @@ struct AsrEngine {
   DevBuf h_scratch;             // fused feed-forward: [clusters * 256, ffn] bf16 hidden activations, L2-resident
   CUtensorMap tm_h;
   bool mlp_ready = false;
-  DevBuf kv_cache, past_len, prev_id, n_frames, last_tok;
+  DevBuf kv_cache, past_len, prev_id, n_frames, last_tok, seg_has_text, silent_mask;
   CUtensorMap tm_kv, tm_rc;      // head-major 3D views of the K/V cache / right-context scratch for the streaming attention kernel (bf16 only)
   bool attn_tma = false;
   size_t slot_stride = 0;        // elements between two sessions' rings inside one layer's slab
   size_t layer_stride = 0;       // elements between two layers' slabs: K/V cache layout is [layer][slot][K|V][ring][d]
   std::vector<int> free_slots;
   std::vector<uint8_t> slot_open;
+  std::vector<uint8_t> slot_inflight;     // submitted, uncollected steps that carry the slot (0..2)
+  std::vector<uint32_t> slot_stamp;       // duplicate detection inside one step: epoch of the last step that listed the slot
+  uint32_t stamp_epoch = 0;
   // outputs
-  DevBuf d_argmax, d_newtok, d_nnew, d_blank, d_hastok, d_logprobs;
+  DevBuf d_argmax, d_newtok, d_nnew, d_blank, d_hastok, d_hastext, d_flags, d_logprobs;
   // prefix beam search (optional)
   int beam = 0, cand_k = 0;
   DevBuf bm_n, bm_cur, bm_len, bm_last, bm_pb, bm_pnb, bm_hash, bm_tokens, d_beam_tok, d_beam_len, d_beam_score;
@@ -165,7 +172,7 @@ struct AsrEngine {
   int32_t* h_reset = nullptr;
   DevBuf d_reset;
   int reset_pos = 0;
-  struct Pending { int n = 0; int want_lp = 0; int active = 0; std::chrono::steady_clock::time_point t0; } pend[2];
+  struct Pending { int n = 0; int want_lp = 0; int active = 0; std::chrono::steady_clock::time_point t0; std::vector<int32_t> slots; } pend[2];
   int cur_buf = 0;
 
   // per-kernel-family CUDA-event profiling (bench.py roofline): pairs recorded on the launching stream
@@ -315,7 +322,8 @@ int make_operand(AsrEngine* e, Operand* a, int rows, int K) {
   a->rows = (int)round_up(rows, 128); a->K = K; a->ld = split ? 2 * K : K; a->lo_off = split ? K : 0;
   if (a->buf.alloc((size_t)a->rows * a->ld * sizeof(bf16))) return -1;
   ASR_CUDA_OK(cudaMemset(a->buf.p, 0, a->buf.bytes));
-  return make_tmap_bf16_2d(&a->tm, a->buf.p, (uint64_t)a->ld, (uint64_t)a->rows, (uint64_t)a->ld, 128);
+  return make_tmap_bf16_2d(&a->tm, a->buf.p, (uint64_t)a->ld, (uint64_t)a->rows, (uint64_t)a->ld, 128) ||
+         make_tmap_bf16_2d(&a->tm_st, a->buf.p, (uint64_t)a->ld, (uint64_t)a->rows, (uint64_t)a->ld, 32);
 }
 
 int pick_bn(const AsrEngine* e, int M, int N) {
@@ -352,25 +360,30 @@ struct ProfScope {       // brackets one kernel launch with events when profilin
   }
 };
 
+// ts: tensor maps + bias of the TMA-store epilogue of the pair kernel, when this GEMM has one (bf16 operand outputs)
 template <class Epi>
-int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const Epi& epi) {
+int run_gemm(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const Epi& epi, const TsMaps* ts = nullptr, int n_streams = 0) {
   const GemmProblem p = make_problem(M, w.N, w.K, e->geo.split);
   ProfScope ps(e, cat);
-  if (e->simt_gemm) return gemm_simt<Epi>(a.buf.as<bf16>(), a.ld, w.w, w.ld, p, epi, e->stream);
   int bn = pick_bn(e, M, w.N);
   // CTA pairs (cta_group::2, 256 x 256 tile, half the B-operand traffic per SM: 32 instead of 48 KB per k-block through L2 -> shared
-  // memory -> tensor core).  Measured on B200
-  // (profiles/r01_gemm_sweep_*.txt): pair wins at K = 2048 (FFN2 127 vs 138 us) and, since the packed-math GELU epilogue stopped
-  // being the limiter, also at K = 512 for large M (FFN1 150 vs 157 us, QKV 116 vs 121 us); at small M the coupled epilogues lose.
+  // memory -> tensor core).  Measured on B200 (profiles/r01_gemm_sweep_*.txt): pair wins at K = 2048 (FFN2 127 vs 138 us) and also
+  // at K = 512 for large M (FFN1 150 vs 157 us, QKV 116 vs 121 us); at small M the coupled epilogues lose.
   const int k_eff = w.K * (e->geo.split ? 3 : 1);
   const long pair_tiles = (long)((M + 255) / 256) * (w.N / 256);
-  if (bn == 256 && !e->no_pair && w.N % 256 == 0 && ((k_eff >= 1024 && pair_tiles >= e->num_sms / 2) || pair_tiles >= 4 * (e->num_sms / 2)))
-    bn = (e->pair128 && k_eff <= 512) ? kPairTile128 : kPairTile;
-  if constexpr (Epi::kBf16Rows) {
-    // short K, bf16 outputs (QKV, FFN1 in FAST precision): keep the A tile resident, stream only B
-    if (bn == kPairTile && e->pair_a && k_eff <= 512 && w.N % 512 == 0 && epi.bf16_rows()) bn = kPairTileA;
+  if (bn == 256 && !e->no_pair && w.N % 256 == 0 && ((k_eff >= 1024 && pair_tiles >= e->num_sms / 2) || pair_tiles >= 4 * (e->num_sms / 2))) bn = kPairTile;
+  const CUtensorMap& tmB = w.tm[bn == 64 ? 0 : (bn == 128 || bn == kPairTile ? 1 : 2)];
+  if (bn == kPairTile && e->tma_store && ts && w.N <= kTsBiasMax) {
+    if constexpr (Epi::kStreamTiles) {
+      if (e->qkv_ts_ready && n_streams > 0 && &a == &e->a_ln) {
+        const StreamTiling stl = make_stream_tiling(n_streams, e->geo.seg_rows, e->geo.rc_rows);
+        return gemm_tc<Epi>(e->tm_a_ln_seg, tmB, p, epi, kPairTileQKV, e->num_sms, e->stream, ts, &stl);
+      }
+    } else if constexpr (Epi::kBf16Rows) {
+      if (epi.bf16_rows()) return gemm_tc<Epi>(a.tm, tmB, p, epi, kPairTileTS, e->num_sms, e->stream, ts);
+    }
   }
-  return gemm_tc<Epi>(a.tm, w.tm[bn == 64 || bn == kPairTile128 ? 0 : (bn == 128 || bn == kPairTile || bn == kPairTileA ? 1 : 2)], p, epi, bn, e->num_sms, e->stream);
+  return gemm_tc<Epi>(a.tm, tmB, p, epi, bn, e->num_sms, e->stream);
 }
 
 int run_gemm_ln(AsrEngine* e, int cat, const Operand& a, const WeightMat& w, int M, const LnEpilogue& ep) {
@@ -397,7 +410,8 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     eq.bias = L.bqkv; eq.slots = slots; eq.past_len = e->past_len.as<int>();
     eq.rows = g.rows; eq.seg_rows = g.seg_rows; eq.rc_rows = g.rc_rows; eq.ring = g.ring; eq.d = d;
     eq.qscale = 1.0f / sqrtf((float)(d / g.n_heads));                                   // TA:emformer.py:108
-    if (run_gemm(e, ASR_PROF_GEMM_QKV, e->a_ln, L.qkv, M, eq)) return -1;
+    eq.kv_row0 = (long long)l * (long long)(e->layer_stride / d); eq.slot_rows = (int)(e->slot_stride / d);
+    if (run_gemm(e, ASR_PROF_GEMM_QKV, e->a_ln, L.qkv, M, eq, &L.ts_qkv, n)) return -1;
 
     AttnParams<T> ap;
     ap.q = e->q.as<T>(); ap.cache_layer = cache_layer; ap.slot_stride = e->slot_stride; ap.rc = e->rc_kv.as<T>();
@@ -414,7 +428,7 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
       const bool mlp = e->mlp_ready && e->mlp_fused && (M + 255) / 256 >= e->mlp_min_tiles;
       if (!mlp) {
         EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
-        if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1)) return -1;
+        if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1, &L.ts_ffn1)) return -1;
       }
       // FFN2 + residual + LN_out -> x (fp32) and LN_in of the next layer -> QKV operand (last layer: segment rows -> CTC operand)
       LnEpilogue e2{L.b2, e->x1.as<float>(), L.ln_out_g, L.ln_out_b, nullptr, nullptr, e->x.as<float>(), nullptr, 0, 0, 0, 0, 0};
@@ -443,7 +457,7 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
     if (run_gemm(e, ASR_PROF_GEMM_OUT, e->a_attn, L.o, M, eo)) return -1;
     { ProfScope ps(e, ASR_PROF_LN); if (ln_to_operand(e->x1.as<float>(), L.ln_ff_g, L.ln_ff_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, d, e->stream)) return -1; }
     EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
-    if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1)) return -1;
+    if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1, &L.ts_ffn1)) return -1;
     EpiF32 e2{e->x2.as<float>(), L.b2, e->x1.as<float>(), d, d};
     if (run_gemm(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
     ProfScope ps_ln(e, ASR_PROF_LN);
@@ -482,7 +496,7 @@ BeamParams beam_params(AsrEngine* e, int n) {
   P.n = n; P.seg_rows = e->geo.seg_rows; P.vocab = e->geo.vocab; P.beam = e->beam; P.cand_k = e->cand_k; P.max_len = BEAM_MAX_LEN - 1;
   P.n_beam = e->bm_n.as<int>(); P.cur = e->bm_cur.as<int>(); P.len = e->bm_len.as<int>(); P.last = e->bm_last.as<int>();
   P.pb = e->bm_pb.as<float>(); P.pnb = e->bm_pnb.as<float>(); P.hash = e->bm_hash.as<unsigned long long>(); P.tokens = e->bm_tokens.as<int16_t>();
-  P.out_tokens = e->d_beam_tok.as<int>(); P.out_len = e->d_beam_len.as<int>(); P.out_score = e->d_beam_score.as<float>();
+  P.out_tokens = e->d_beam_tok.as<int16_t>(); P.out_len = e->d_beam_len.as<int>(); P.out_score = e->d_beam_score.as<float>(); P.out_flags = e->d_flags.as<int>();
   return P;
 }
 
@@ -502,14 +516,15 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   if (!with_ctc) return 0;
   const int Mc = n * g.seg_rows;
   EpiOperand ec1{e->a_ctc.buf.as<bf16>(), e->ctc_b1, e->a_ctc.ld, e->a_ctc.lo_off, ACT_SILU};    // decoder.py:67
-  if (run_gemm(e, ASR_PROF_GEMM_CTC1, e->a_enc, e->ctc1, Mc, ec1)) return -1;
+  if (run_gemm(e, ASR_PROF_GEMM_CTC1, e->a_enc, e->ctc1, Mc, ec1, &e->ts_ctc1)) return -1;
   EpiF32 ec2{e->logits.as<float>(), e->ctc_b2, nullptr, g.vocab, g.vocab};                        // decoder.py:68
   if (run_gemm(e, ASR_PROF_GEMM_CTC2, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
   CtcParams cp;
   cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->act_slots;
   cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
+  cp.seg_has_text = e->seg_has_text.as<int>(); cp.silent_mask = e->silent_mask.as<uint32_t>();
   cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
-  cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>();
+  cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>(); cp.has_text = e->d_hastext.as<int>(); cp.flags = e->d_flags.as<int>();
   cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
   { ProfScope ps(e, ASR_PROF_CTC); if (ctc_greedy_launch(cp, n, e->stream)) return -1; }
   if (e->beam > 0) { ProfScope ps(e, ASR_PROF_BEAM); if (beam_launch(beam_params(e, n), e->stream)) return -1; }
@@ -569,10 +584,25 @@ int check_step_args(AsrEngine* e, int n, const int32_t* slots) {
   if (!e) { set_error("null engine"); return -1; }
   if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch = %d]", n, e->cfg.max_batch); return -1; }
   if (n && !slots) { set_error("null slots"); return -1; }
-  for (int i = 0; i < n; ++i)
+  if (++e->stamp_epoch == 0) { std::fill(e->slot_stamp.begin(), e->slot_stamp.end(), 0u); e->stamp_epoch = 1; }
+  for (int i = 0; i < n; ++i) {
     if (slots[i] < 0 || slots[i] >= e->cfg.max_sessions || !e->slot_open[slots[i]]) { set_error("slot %d (index %d) is not an open session", slots[i], i); return -1; }
+    // a session may appear at most once per step: two rows of one slot would race on its K/V ring rows and greedy carry
+    if (e->slot_stamp[slots[i]] == e->stamp_epoch) { set_error("slot %d appears twice in one step (index %d)", slots[i], i); return -1; }
+    e->slot_stamp[slots[i]] = e->stamp_epoch;
+  }
   return 0;
 }
+
+void mark_inflight(AsrEngine* e, int b, int n, const int32_t* slots) {
+  e->pend[b].slots.assign(slots, slots + n);
+  for (int i = 0; i < n; ++i) ++e->slot_inflight[slots[i]];
+}
+void clear_inflight(AsrEngine* e, int b) {
+  for (int32_t s : e->pend[b].slots) if (e->slot_inflight[s]) --e->slot_inflight[s];
+  e->pend[b].slots.clear();
+}
+bool ticket_pending(const AsrEngine* e) { return e->pend[0].active || e->pend[1].active; }
 
 size_t pcm_bytes(const AsrEngine* e, int n, int fmt) { return (size_t)n * e->geo.chunk_len * (fmt == ASR_PCM_F32 ? 4 : 2); }
 
@@ -616,7 +646,9 @@ std::vector<OutItem> out_layout(AsrEngine* e, int n, bool want_lp) {
   add(e->d_nnew, 4 * (size_t)n, 4 * B, 2, true);
   add(e->d_blank, 4 * (size_t)n, 4 * B, 3, true);
   add(e->d_hastok, 4 * (size_t)n, 4 * B, 4, true);
-  add(e->d_beam_tok, 4 * (size_t)n * BEAM_MAX_LEN, 4 * B * BEAM_MAX_LEN, 6, e->beam > 0);
+  add(e->d_hastext, 4 * (size_t)n, 4 * B, 9, true);
+  add(e->d_flags, 4 * (size_t)n, 4 * B, 10, true);
+  add(e->d_beam_tok, 2 * (size_t)n * BEAM_MAX_LEN, 2 * B * BEAM_MAX_LEN, 6, e->beam > 0);
   add(e->d_beam_len, 4 * (size_t)n, 4 * B, 7, e->beam > 0);
   add(e->d_beam_score, 4 * (size_t)n, 4 * B, 8, e->beam > 0);
   add(e->d_logprobs, 4 * nS * g.vocab, 4 * BS * g.vocab, 5, want_lp);
@@ -627,6 +659,7 @@ void* out_field(const AsrStepOut* o, int f) {
   switch (f) {
     case 0: return o->argmax_ids; case 1: return o->new_tokens; case 2: return o->n_new; case 3: return o->blank_frames;
     case 4: return o->has_token; case 5: return o->logprobs; case 6: return o->beam_tokens; case 7: return o->beam_len; case 8: return o->beam_score;
+    case 9: return o->has_text; case 10: return o->flags;
   }
   return nullptr;
 }
@@ -641,9 +674,19 @@ int enqueue_d2h(AsrEngine* e, int b, int n, bool want_lp) {
 void deliver(AsrEngine* e, int b, int n, bool want_lp, const AsrStepOut* out) {
   if (!out) return;
   const uint8_t* ho = reinterpret_cast<const uint8_t*>(e->h_buf[b]) + e->h_out_off;
-  for (auto& it : out_layout(e, n, want_lp)) {
+  const auto items = out_layout(e, n, want_lp);
+  const int32_t* beam_len = nullptr;
+  for (auto& it : items) if (it.field == 7) beam_len = reinterpret_cast<const int32_t*>(ho + it.hoff);
+  for (auto& it : items) {
     void* dst = out_field(out, it.field);
-    if (dst) memcpy(dst, ho + it.hoff, it.bytes);
+    if (!dst) continue;
+    if (it.field == 6 && beam_len) {                        // hypotheses: only the valid prefix of every row (2 KB rows, mostly short)
+      const int16_t* src = reinterpret_cast<const int16_t*>(ho + it.hoff);
+      int16_t* d = reinterpret_cast<int16_t*>(dst);
+      for (int i = 0; i < n; ++i) memcpy(d + (size_t)i * BEAM_MAX_LEN, src + (size_t)i * BEAM_MAX_LEN, 2 * (size_t)std::min(beam_len[i], (int32_t)BEAM_MAX_LEN));
+    } else {
+      memcpy(dst, ho + it.hoff, it.bytes);
+    }
   }
 }
 
@@ -664,6 +707,7 @@ int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int 
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
   e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
+  mark_inflight(e, b, n, slots);
   e->cur_buf ^= 1;
   if (ticket) *ticket = b;
   return 0;
@@ -703,6 +747,7 @@ int submit_rings(AsrEngine* e, int n, const int32_t* slots, const int16_t* base,
     ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
   }
   e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
+  mark_inflight(e, b, n, slots);
   e->cur_buf ^= 1;
   if (ticket) *ticket = b;
   return 0;
@@ -712,8 +757,12 @@ int collect_step(AsrEngine* e, int ticket, const AsrStepOut* out) {
   if (ticket < 0 || ticket > 1 || !e->pend[ticket].active) { set_error("asr_collect: ticket %d is not in flight", ticket); return -1; }
   auto& pd = e->pend[ticket];
   if (pd.n) {
-    ASR_CUDA_OK(cudaSetDevice(e->device));
-    ASR_CUDA_OK(cudaEventSynchronize(e->ev_done[ticket]));
+    const cudaError_t ce = cudaSetDevice(e->device) == cudaSuccess ? cudaEventSynchronize(e->ev_done[ticket]) : cudaErrorInvalidDevice;
+    if (ce != cudaSuccess) {                                // the ticket is gone either way: its sessions must not stay locked
+      pd.active = 0; clear_inflight(e, ticket);
+      set_error("asr_collect: step failed on the device: %s", cudaGetErrorString(ce));
+      return -1;
+    }
     if (e->ev_t0[ticket] && e->ev_t1[ticket]) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, e->ev_t0[ticket], e->ev_t1[ticket]) == cudaSuccess) { e->pipe_gpu_ms += ms; ++e->pipe_gpu_n; } else cudaGetLastError();
@@ -721,6 +770,7 @@ int collect_step(AsrEngine* e, int ticket, const AsrStepOut* out) {
     deliver(e, ticket, pd.n, pd.want_lp, out);
   }
   pd.active = 0;
+  clear_inflight(e, ticket);
   return 0;
 }
 
@@ -740,14 +790,20 @@ void record_step(AsrEngine* e, int n, double ms) {
   else { e->step_ms[e->step_ms_pos] = (float)ms; e->step_ms_pos = (e->step_ms_pos + 1) % 4096; }
 }
 
-int reset_slot(AsrEngine* e, int slot) {
-  const int zero = 0, neg = -1;
-  ASR_CUDA_OK(cudaMemcpyAsync(e->past_len.as<int>() + slot, &zero, 4, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaMemcpyAsync(e->n_frames.as<int>() + slot, &zero, 4, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaMemcpyAsync(e->prev_id.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaMemcpyAsync(e->last_tok.as<int>() + slot, &neg, 4, cudaMemcpyHostToDevice, e->stream));
-  if (e->beam > 0 && beam_reset_launch(beam_params(e, 0), slot, e->cfg.max_sessions, e->stream)) return -1;
-  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));     // the 4-byte host sources are stack variables
+// Stream-ordered, asynchronous reset of the listed sessions (endpoint / open): takes effect after every step already enqueued and
+// never waits for the device — the pinned slot list is one of kResetRing, so only that list's previous H2D copy is waited for.
+int reset_slots_async(AsrEngine* e, int n, const int32_t* slots) {
+  if (n <= 0) return 0;
+  const int r = e->reset_pos;
+  e->reset_pos = (r + 1) % AsrEngine::kResetRing;
+  int32_t* hs = e->h_reset + (size_t)r * e->cfg.max_sessions;
+  int* ds = e->d_reset.as<int>() + (size_t)r * e->cfg.max_sessions;
+  ASR_CUDA_OK(cudaEventSynchronize(e->ev_reset[r]));
+  memcpy(hs, slots, 4 * (size_t)n);
+  ASR_CUDA_OK(cudaMemcpyAsync(ds, hs, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaEventRecord(e->ev_reset[r], e->stream));
+  if (reset_slots_launch(ds, n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->seg_has_text.as<int>(), e->stream)) return -1;
+  if (e->beam > 0 && beam_reset_many_launch(beam_params(e, 0), ds, n, e->stream)) return -1;
   return 0;
 }
 
@@ -759,7 +815,7 @@ void destroy_engine(AsrEngine* e) {
   e->graphs.clear();
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->h_scratch, &e->past_len,
-                    &e->prev_id, &e->n_frames, &e->last_tok, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_logprobs,
+                    &e->prev_id, &e->n_frames, &e->last_tok, &e->seg_has_text, &e->silent_mask, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_hastext, &e->d_flags, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
   for (DevBuf* b : bufs) b->free();
   for (FbankPlan* pl : {&e->mel128, &e->kaldi80}) {
@@ -792,18 +848,15 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
 
   AsrEngine* e = new AsrEngine();
   e->cfg = *cfg; e->geo = g; e->device = device; e->num_sms = prop.multiProcessorCount;
-  const char* dbg = getenv("ASR_B200_DEBUG_SIMT_GEMM");
-  e->simt_gemm = dbg && dbg[0] == '1';
   const char* np_ = getenv("ASR_B200_NO_PAIR_GEMM");
   e->no_pair = np_ && np_[0] == '1';
   if (const char* nf = getenv("ASR_B200_NO_FUSED_LN")) e->fused_ln = !(nf[0] == '1');
-  if (e->simt_gemm || cfg->d_model != 512) e->fused_ln = 0;
+  if (cfg->d_model != 512) e->fused_ln = 0;
   if (const char* pl = getenv("ASR_B200_NO_PAIR_LN")) e->no_pair_ln = pl[0] == '1';
   if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
   if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
   if (const char* mf = getenv("ASR_B200_MLP_FUSED")) e->mlp_fused = mf[0] == '1';
-  if (const char* p8 = getenv("ASR_B200_PAIR128")) e->pair128 = p8[0] == '1';
-  if (const char* pa = getenv("ASR_B200_PAIR_A")) e->pair_a = pa[0] == '1';
+  if (const char* nt = getenv("ASR_B200_NO_TMA_STORE")) e->tma_store = !(nt[0] == '1');
   if (const char* ug = getenv("ASR_B200_GRAPHS")) e->use_graphs = ug[0] == '1';
   if (const char* gm = getenv("ASR_B200_GRAPH_MAX_STREAMS")) e->graph_max_streams = atoi(gm);
   if (const char* mt = getenv("ASR_B200_MLP_MIN_TILES")) e->mlp_min_tiles = atoi(mt);
@@ -880,7 +933,8 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->d_src_off[0].alloc(8 * (size_t)B) || e->d_src_off[1].alloc(8 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
         e->x2.alloc(4 * (size_t)M * d) || e->q.alloc(4 * (size_t)M * d) || e->rc_kv.alloc(esz * (size_t)B * 2 * g.rc_rows * d) ||
         e->logits.alloc(4 * (size_t)Mc * g.vocab) || e->d_logprobs.alloc(4 * (size_t)Mc * g.vocab) || e->d_argmax.alloc(4 * (size_t)Mc) ||
-        e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B)) break;
+        e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B) ||
+        e->d_hastext.alloc(4 * (size_t)B) || e->d_flags.alloc(4 * (size_t)B)) break;
     if (make_operand(e, &e->a_fb, B * g.frames, g.n_mels) || make_operand(e, &e->a_ln, M, d) || make_operand(e, &e->a_attn, M, d) ||
         make_operand(e, &e->a_h, M, f) || make_operand(e, &e->a_enc, Mc, d) || make_operand(e, &e->a_ctc, Mc, g.ctc_hidden)) break;
     // ---- sessions
@@ -889,11 +943,12 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     const size_t S = cfg->max_sessions;
     e->slot_stride = (size_t)2 * g.ring * d;
     e->layer_stride = S * e->slot_stride;
-    if (const char* sm = getenv("ASR_B200_KV_SLOT_MAJOR")) if (sm[0] == '1') {     // A/B switch: [slot][layer][K|V][ring][d]
-      e->layer_stride = (size_t)2 * g.ring * d;
-      e->slot_stride = (size_t)g.n_layers * e->layer_stride;
+    if (e->kv_cache.alloc(esz * S * g.n_layers * 2 * g.ring * d) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S) || e->seg_has_text.alloc(4 * S)) break;
+    {
+      std::vector<uint32_t> mask((g.vocab + 31) / 32, 0u);
+      mask[0] = 3u;                                       // ids 0 ('-', blank) and 1 ('|', silence) render to "" (recognition.py:47-52)
+      if (upload(&e->silent_mask, mask.data(), 4 * mask.size())) break;
     }
-    if (e->kv_cache.alloc(esz * S * g.n_layers * 2 * g.ring * d) || e->past_len.alloc(4 * S) || e->prev_id.alloc(4 * S) || e->n_frames.alloc(4 * S) || e->last_tok.alloc(4 * S)) break;
     if (cudaMemsetAsync(e->kv_cache.p, 0, e->kv_cache.bytes, e->stream) != cudaSuccess) { set_error("memset failed"); break; }
     if (g.split && d == 512 && g.n_heads == 8 && (g.seg_rows == 16 || g.seg_rows == 8) && g.rc_rows == 4) {
       // EXACT: ring rows pre-split [hi 512 | lo 512] bf16 = 16 head-sized pieces per row (attention_exact_kernel)
@@ -907,6 +962,38 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
                     !make_tmap_bf16_heads(&e->tm_rc, e->rc_kv.p, (uint64_t)B * 2 * g.rc_rows, 8, (uint32_t)g.rc_rows);
       if (!e->attn_tma) fprintf(stderr, "asr_b200: streaming attention disabled: %s\n", asr_last_error());
     }
+    {
+      // TMA-store epilogues (gemm.cuh): per GEMM the tensor maps of its destinations + a kernel-parameter copy of its bias
+      auto host_bias = [&](const float* dev, int n, TsMaps* ts) { if (n <= kTsBiasMax) memcpy(ts->bias, weights + (dev - e->w_f32.as<float>()), 4 * (size_t)n); };
+      memset(&e->ts_ctc1, 0, sizeof(TsMaps));
+      e->ts_ctc1.c0 = e->a_ctc.tm_st;
+      host_bias(e->ctc_b1, g.ctc_hidden, &e->ts_ctc1);
+      TsMaps qkv;
+      memset(&qkv, 0, sizeof(qkv));
+      if (!g.split && d % 256 == 0 && 32 % g.seg_rows == 0 && 32 % g.rc_rows == 0) {
+        // stream-tiled Q | K | V projection (kPairTileQKV): every destination is a TMA box
+        const uint64_t Bm = (uint64_t)B, rowb = (uint64_t)d * 2;
+        const uint64_t dims3[3] = {(uint64_t)d, (uint64_t)g.rows, Bm}, str3[2] = {rowb, rowb * g.rows};
+        const uint32_t a_seg[3] = {64, (uint32_t)g.seg_rows, (uint32_t)(128 / g.seg_rows)}, a_rc[3] = {64, (uint32_t)g.rc_rows, (uint32_t)(128 / g.rc_rows)};
+        const uint32_t q_seg[3] = {64, (uint32_t)g.seg_rows, (uint32_t)(32 / g.seg_rows)}, q_rc[3] = {64, (uint32_t)g.rc_rows, (uint32_t)(32 / g.rc_rows)};
+        const uint64_t dims4[4] = {(uint64_t)d, (uint64_t)g.rc_rows, 2, Bm}, str4[3] = {rowb, rowb * g.rc_rows, rowb * g.rc_rows * 2};
+        const uint32_t rc4[4] = {64, (uint32_t)g.rc_rows, 1, (uint32_t)(32 / g.rc_rows)};
+        e->qkv_ts_ready = !make_tmap_bf16_nd(&e->tm_a_ln_seg, e->a_ln.buf.p, 3, dims3, str3, a_seg) &&
+                          !make_tmap_bf16_nd(&qkv.a_rc, e->a_ln.buf.p, 3, dims3, str3, a_rc) &&
+                          !make_tmap_bf16_nd(&qkv.c0, e->q.p, 3, dims3, str3, q_seg) && !make_tmap_bf16_nd(&qkv.c1, e->q.p, 3, dims3, str3, q_rc) &&
+                          !make_tmap_bf16_2d(&qkv.c2, e->kv_cache.p, (uint64_t)d, (uint64_t)S * g.n_layers * 2 * g.ring, (uint64_t)d, (uint32_t)g.seg_rows) &&
+                          !make_tmap_bf16_nd(&qkv.c3, e->rc_kv.p, 4, dims4, str4, rc4);
+        if (!e->qkv_ts_ready) fprintf(stderr, "asr_b200: stream-tiled QKV projection disabled: %s\n", asr_last_error());
+      }
+      for (int l = 0; l < g.n_layers; ++l) {
+        LayerW& L = e->layers[l];
+        L.ts_qkv = qkv;
+        host_bias(L.bqkv, 3 * d, &L.ts_qkv);
+        memset(&L.ts_ffn1, 0, sizeof(TsMaps));
+        L.ts_ffn1.c0 = e->a_h.tm_st;
+        host_bias(L.b1, f, &L.ts_ffn1);
+      }
+    }
     if (e->mlp_fused && !g.split && d == 512 && g.ffn % 512 == 0 && g.ffn <= 2048 && (size_t)B * g.rows >= (size_t)256 * e->mlp_min_tiles) {
       // fused feed-forward block for large batches: one 256-row slab of hidden activations per resident cluster (37 MB at most)
       const int clusters = mlp_ln_clusters(e->num_sms);
@@ -916,14 +1003,16 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
       else fprintf(stderr, "asr_b200: fused feed-forward kernel disabled: %s\n", asr_last_error());
     }
     if (fill_i32(e->past_len.as<int>(), 0, S, e->stream) || fill_i32(e->n_frames.as<int>(), 0, S, e->stream) ||
-        fill_i32(e->prev_id.as<int>(), -1, S, e->stream) || fill_i32(e->last_tok.as<int>(), -1, S, e->stream)) break;
+        fill_i32(e->prev_id.as<int>(), -1, S, e->stream) || fill_i32(e->last_tok.as<int>(), -1, S, e->stream) || fill_i32(e->seg_has_text.as<int>(), 0, S, e->stream)) break;
     e->slot_open.assign(S, 0);
+    e->slot_inflight.assign(S, 0);
+    e->slot_stamp.assign(S, 0u);
     e->free_slots.resize(S);
     for (size_t i = 0; i < S; ++i) e->free_slots[i] = (int)(S - 1 - i);
     // ---- pinned staging: [pcm (f32 worst case) | slots | outputs]
     const size_t in_bytes = round_up(pcm_bytes(e, B, ASR_PCM_F32), 256) + round_up(4 * (size_t)B, 256);
-    const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 5 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256) +
-                             round_up(4 * (size_t)B * BEAM_MAX_LEN, 256) + 4096;
+    const size_t out_bytes = 2 * round_up(4 * (size_t)Mc, 256) + 7 * round_up(4 * (size_t)B, 256) + round_up(4 * (size_t)Mc * g.vocab, 256) +
+                             round_up(2 * (size_t)B * BEAM_MAX_LEN, 256) + 4096;
     e->h_out_off = in_bytes; e->h_stage_bytes = in_bytes + out_bytes;
     if (cudaMallocHost(&e->h_buf[0], e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_buf[1], e->h_stage_bytes) != cudaSuccess) {
       set_error("cudaMallocHost(2 x %zu) failed", e->h_stage_bytes); break;
@@ -983,6 +1072,58 @@ int run_fbank_kind(AsrEngine* e, int kind, int n, int fmt, int n_samples, int su
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------ hooks of the native scheduler (sched.cu)
+namespace asr {
+
+int engine_submit_gather(AsrEngine* e, int n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
+                         bool device_gather, bool want_lp, int* ticket) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (device_gather) return submit_rings(e, n, slots, base, row_stride, rows, offsets, want_lp, ticket);
+  if (n < 0 || n > e->cfg.max_batch) { set_error("n = %d outside [0, max_batch]", n); return -1; }
+  if (e->pend[e->cur_buf].active) { set_error("two steps are already in flight: collect the oldest ticket first"); return -1; }
+  int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[e->cur_buf]);
+  const size_t L = e->geo.chunk_len;
+  parallel_rows(n, 8, [&](int a, int b) {
+    for (int i = a; i < b; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
+  });
+  return submit_step(e, n, slots, dst, ASR_PCM_I16, want_lp, ticket);
+}
+
+int engine_collect_view(AsrEngine* e, int ticket, StepView* v) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int n = (ticket == 0 || ticket == 1) ? e->pend[ticket].n : 0;
+  const bool want_lp = (ticket == 0 || ticket == 1) && e->pend[ticket].want_lp;
+  const auto t0 = (ticket == 0 || ticket == 1) ? e->pend[ticket].t0 : std::chrono::steady_clock::now();
+  if (collect_step(e, ticket, nullptr)) return -1;
+  *v = StepView();
+  v->n = n;
+  const uint8_t* ho = reinterpret_cast<const uint8_t*>(e->h_buf[ticket]) + e->h_out_off;
+  for (auto& it : out_layout(e, n, want_lp)) {
+    const void* p = ho + it.hoff;
+    switch (it.field) {
+      case 0: v->argmax_ids = (const int32_t*)p; break; case 1: v->new_tokens = (const int32_t*)p; break; case 2: v->n_new = (const int32_t*)p; break;
+      case 3: v->blank_frames = (const int32_t*)p; break; case 4: v->has_token = (const int32_t*)p; break; case 5: v->logprobs = (const float*)p; break;
+      case 6: v->beam_tokens = (const int16_t*)p; break; case 7: v->beam_len = (const int32_t*)p; break; case 8: v->beam_score = (const float*)p; break;
+      case 9: v->has_text = (const int32_t*)p; break; case 10: v->flags = (const int32_t*)p; break;
+    }
+  }
+  if (n) record_step(e, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
+}
+
+int engine_reset_async(AsrEngine* e, int n, const int32_t* slots) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n <= 0) return 0;
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  return reset_slots_async(e, n, slots);
+}
+
+int engine_open_slot(AsrEngine* e, int32_t* slot) { return asr_session_open(e, slot); }
+int engine_close_slot(AsrEngine* e, int32_t slot) { return asr_session_close(e, slot); }
+int engine_wait_inputs(AsrEngine* e) { return asr_wait_inputs(e); }
+
+}  // namespace asr
+
 // ================================================================================================ C ABI
 extern "C" {
 
@@ -1035,8 +1176,8 @@ int asr_session_open(AsrEngine* e, int32_t* slot_out) {
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->free_slots.empty()) { set_error("no free session slot (max_sessions = %d)", e->cfg.max_sessions); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  const int s = e->free_slots.back();
-  if (reset_slot(e, s)) return -1;
+  const int32_t s = e->free_slots.back();
+  if (reset_slots_async(e, 1, &s)) return -1;
   e->free_slots.pop_back();
   e->slot_open[s] = 1;
   *slot_out = s;
@@ -1048,7 +1189,7 @@ int asr_session_reset(AsrEngine* e, int32_t slot) {
   std::lock_guard<std::mutex> lk(e->mu);
   if (slot < 0 || slot >= e->cfg.max_sessions || !e->slot_open[slot]) { set_error("slot %d is not an open session", slot); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  return reset_slot(e, slot);
+  return reset_slots_async(e, 1, &slot);
 }
 
 int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
@@ -1059,19 +1200,7 @@ int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots) {
   for (int i = 0; i < n; ++i)
     if (slots[i] < 0 || slots[i] >= e->cfg.max_sessions || !e->slot_open[slots[i]]) { set_error("slot %d is not an open session", slots[i]); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  // Stream-ordered and asynchronous: the resets take effect after every step already enqueued (a step in flight must not be
-  // waited for here, the scheduler pipelines ticks).  The pinned slot list is reused, so wait for the previous list's H2D only.
-  const int r = e->reset_pos;
-  e->reset_pos = (r + 1) % AsrEngine::kResetRing;
-  int32_t* hs = e->h_reset + (size_t)r * e->cfg.max_sessions;
-  int* ds = e->d_reset.as<int>() + (size_t)r * e->cfg.max_sessions;
-  ASR_CUDA_OK(cudaEventSynchronize(e->ev_reset[r]));
-  memcpy(hs, slots, 4 * (size_t)n);
-  ASR_CUDA_OK(cudaMemcpyAsync(ds, hs, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-  ASR_CUDA_OK(cudaEventRecord(e->ev_reset[r], e->stream));
-  if (reset_slots_launch(ds, n, e->past_len.as<int>(), e->n_frames.as<int>(), e->prev_id.as<int>(), e->last_tok.as<int>(), e->stream)) return -1;
-  if (e->beam > 0 && beam_reset_many_launch(beam_params(e, 0), ds, n, e->stream)) return -1;
-  return 0;
+  return reset_slots_async(e, n, slots);
 }
 
 /* Batch assembly in native code: copies, for i < n, chunk_length samples starting at base[rows[i] * row_stride + offsets[i]] into
@@ -1110,6 +1239,7 @@ int asr_session_close(AsrEngine* e, int32_t slot) {
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (slot < 0 || slot >= e->cfg.max_sessions || !e->slot_open[slot]) { set_error("slot %d is not an open session", slot); return -1; }
+  if (e->slot_inflight[slot]) { set_error("slot %d rides a submitted step: asr_collect its ticket before closing the session", slot); return -1; }
   e->slot_open[slot] = 0;
   e->free_slots.push_back(slot);
   return 0;
@@ -1177,6 +1307,7 @@ int asr_collect(AsrEngine* e, int32_t ticket, const AsrStepOut* out) {
 int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t fmt) {
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
+  if (ticket_pending(e)) { set_error("asr_stage while an asr_submit ticket is in flight (staging buffer 0 may still be read)"); return -1; }
   e->staged_fmt = fmt;
   use_buffer(e, 0);
   return stage_inputs(e, 0, n, slots, pcm, fmt, e->stream);
@@ -1186,6 +1317,7 @@ int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs) {
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (n <= 0 || n > e->cfg.max_batch) { set_error("n = %d outside (0, max_batch]", n); return -1; }
+  if (ticket_pending(e)) { set_error("asr_run_staged while an asr_submit ticket is in flight"); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   use_buffer(e, 0);
   if (run_step_chain(e, n, e->staged_fmt, want_logprobs != 0)) return -1;
@@ -1226,6 +1358,7 @@ void* asr_pinned_pcm(AsrEngine* e, uint64_t* capacity_bytes) {
 int asr_stage_raw(AsrEngine* e, const void* pcm, uint64_t bytes) {
   if (!e || !pcm) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
+  if (ticket_pending(e)) { set_error("asr_stage_raw while an asr_submit ticket is in flight"); return -1; }
   if (bytes > e->d_pcm.bytes) { set_error("asr_stage_raw: %llu bytes > staging capacity %zu", (unsigned long long)bytes, e->d_pcm.bytes); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   memcpy(e->h_buf[0], pcm, bytes);
@@ -1255,6 +1388,7 @@ int asr_fbank(AsrEngine* e, int32_t kind, int32_t n, const void* pcm, int32_t fm
   if (!e || !pcm || !out) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (n <= 0) return 0;
+  if (ticket_pending(e)) { set_error("asr_fbank while an asr_submit ticket is in flight"); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   const size_t in_bytes = (size_t)n * n_samples * (fmt == ASR_PCM_F32 ? 4 : 2);
   if (in_bytes > e->d_pcm.bytes) { set_error("asr_fbank: input of %zu bytes exceeds staging capacity %zu (raise max_batch)", in_bytes, e->d_pcm.bytes); return -1; }
@@ -1283,7 +1417,7 @@ int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k) {
     const size_t S = e->cfg.max_sessions, B = e->cfg.max_batch;
     if (e->bm_n.alloc(4 * S) || e->bm_cur.alloc(4 * S) || e->bm_len.alloc(4 * S * BEAM_MAX) || e->bm_last.alloc(4 * S * BEAM_MAX) ||
         e->bm_pb.alloc(4 * S * BEAM_MAX) || e->bm_pnb.alloc(4 * S * BEAM_MAX) || e->bm_hash.alloc(8 * S * BEAM_MAX) ||
-        e->bm_tokens.alloc(2 * S * 2 * BEAM_MAX * BEAM_MAX_LEN) || e->d_beam_tok.alloc(4 * B * BEAM_MAX_LEN) || e->d_beam_len.alloc(4 * B) ||
+        e->bm_tokens.alloc(2 * S * 2 * BEAM_MAX * BEAM_MAX_LEN) || e->d_beam_tok.alloc(2 * B * BEAM_MAX_LEN) || e->d_beam_len.alloc(4 * B) ||
         e->d_beam_score.alloc(4 * B)) return -1;
   }
   e->beam = beam; e->cand_k = cand_k;
@@ -1291,6 +1425,20 @@ int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k) {
     if (beam_reset_launch(beam_params(e, 0), -1, e->cfg.max_sessions, e->stream)) return -1;
     ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
   }
+  return 0;
+}
+
+int asr_set_silent_ids(AsrEngine* e, int32_t n, const int32_t* ids) {
+  if (!e || (n > 0 && !ids)) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  std::vector<uint32_t> mask((e->geo.vocab + 31) / 32, 0u);
+  for (int i = 0; i < n; ++i) {
+    if (ids[i] < 0 || ids[i] >= e->geo.vocab) { set_error("asr_set_silent_ids: id %d outside the vocabulary of %d", ids[i], e->geo.vocab); return -1; }
+    mask[ids[i] >> 5] |= 1u << (ids[i] & 31);
+  }
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));            // configuration call: not on the serving path
+  ASR_CUDA_OK(cudaMemcpy(e->silent_mask.p, mask.data(), 4 * mask.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -1341,6 +1489,7 @@ int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const 
   if (!e) { set_error("null engine"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
   if (n_layers < 0 || n_layers > e->geo.n_layers) { set_error("n_layers out of range"); return -1; }
+  if (ticket_pending(e)) { set_error("asr_debug_step_partial while an asr_submit ticket is in flight"); return -1; }
   use_buffer(e, 0);
   if (stage_inputs(e, 0, n, slots, pcm, fmt, e->stream)) return -1;
   if (n == 0) return 0;
@@ -1414,11 +1563,10 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
     if (convert_weight(dA32.as<float>(), dA.as<bf16>(), M, K, ld, lo, 0) || convert_weight(dB32.as<float>(), dB.as<bf16>(), N, K, ld, lo, 0)) break;
     const GemmProblem p = make_problem(M, N, K, split);
     EpiF32 epi{dC.as<float>(), bias ? dbias.as<float>() : nullptr, nullptr, N, N};
-    if (impl == 1) {
-      if (gemm_simt<EpiF32>(dA.as<bf16>(), ld, dB.as<bf16>(), ld, p, epi, 0)) break;
-    } else {
+    if (impl != 0) { set_error("asr_debug_gemm: impl %d does not exist (0 = tcgen05)", impl); break; }
+    {
       CUtensorMap ta, tb;
-      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile || bn == kPairTileA ? 128 : (bn == kPairTile128 ? 64 : bn))) break;
+      if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile ? 128 : bn)) break;
       if (gemm_tc<EpiF32>(ta, tb, p, epi, bn, prop.multiProcessorCount, 0)) break;
     }
     cudaError_t err = cudaDeviceSynchronize();
@@ -1427,6 +1575,44 @@ int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split,
     rc = 0;
   } while (0);
   dA32.free(); dB32.free(); dA.free(); dB.free(); dC.free(); dbias.free();
+  return rc;
+}
+
+/* Diagnostic: act(A B^T + bias) written as a bf16 operand through the EpiOperand epilogue (act: 0 none, 1 GELU, 2 SiLU), returned as fp32.
+ * bn = 512: pair kernel, LSU epilogue; 515: pair kernel, TMA-store epilogue; 64 / 128 / 256: one-CTA kernels. */
+int asr_debug_gemm_operand(int32_t M, int32_t N, int32_t K, int32_t bn, int32_t act, const float* A, const float* B, const float* bias, float* out, int device) {
+  if (!A || !B || !bias || !out || M <= 0 || N <= 0 || K <= 0 || K % 64) { set_error("asr_debug_gemm_operand: bad arguments"); return -1; }
+  ASR_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ASR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int Mp = (int)round_up(M, 256);
+  DevBuf dA32, dB32, dA, dB, dO, dbias;
+  std::vector<bf16> ho;
+  int rc = -1;
+  do {
+    if (dA32.alloc(4 * (size_t)M * K) || dB32.alloc(4 * (size_t)N * K) || dA.alloc(2 * (size_t)Mp * K) || dB.alloc(2 * (size_t)N * K) || dO.alloc(2 * (size_t)Mp * N) ||
+        dbias.alloc(4 * (size_t)N)) break;
+    if (cudaMemcpy(dA32.p, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dB32.p, B, 4 * (size_t)N * K, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dbias.p, bias, 4 * (size_t)N, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); break; }
+    cudaMemset(dA.p, 0, dA.bytes); cudaMemset(dO.p, 0xff, dO.bytes);
+    if (convert_weight(dA32.as<float>(), dA.as<bf16>(), M, K, K, 0, 0) || convert_weight(dB32.as<float>(), dB.as<bf16>(), N, K, K, 0, 0)) break;
+    const GemmProblem p = make_problem(M, N, K, 0);
+    const bool pair = bn == kPairTile || bn == kPairTileTS;
+    CUtensorMap ta, tb;
+    TsMaps ts = {};
+    if (make_tmap_bf16_2d(&ta, dA.p, K, Mp, K, 128) || make_tmap_bf16_2d(&tb, dB.p, K, N, K, pair ? 128 : bn)) break;
+    if (bn == kPairTileTS && (N > kTsBiasMax || make_tmap_bf16_2d(&ts.c0, dO.p, N, Mp, N, 32))) { if (N > kTsBiasMax) set_error("N > %d", kTsBiasMax); break; }
+    if (N <= kTsBiasMax) memcpy(ts.bias, bias, 4 * (size_t)N);
+    EpiOperand epi{dO.as<bf16>(), dbias.as<float>(), N, 0, act};
+    if (gemm_tc<EpiOperand>(ta, tb, p, epi, bn, prop.multiProcessorCount, 0, bn == kPairTileTS ? &ts : nullptr)) break;
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { set_error("asr_debug_gemm_operand: kernel failed: %s", cudaGetErrorString(err)); break; }
+    ho.resize((size_t)M * N);
+    if (cudaMemcpy(ho.data(), dO.p, 2 * ho.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); break; }
+    for (size_t i = 0; i < ho.size(); ++i) out[i] = __bfloat162float(ho[i]);
+    rc = 0;
+  } while (0);
+  dA32.free(); dB32.free(); dA.free(); dB.free(); dO.free(); dbias.free();
   return rc;
 }
 
@@ -1521,7 +1707,10 @@ int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t 
     cudaMemset(dA.p, 0x3c, dA.bytes); cudaMemset(dB.p, 0x3c, dB.bytes); cudaMemset(dR.p, 0, dR.bytes); cudaMemset(dbias.p, 0, dbias.bytes);
     const GemmProblem p = make_problem(M, N, K, split);
     CUtensorMap ta, tb;
-    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, bn == kPairTile || bn == kPairTileA ? 128 : (bn == kPairTile128 ? 64 : bn))) break;
+    const bool pair = bn == kPairTile || bn == kPairTileTS;
+    if (make_tmap_bf16_2d(&ta, dA.p, ld, Mp, ld, 128) || make_tmap_bf16_2d(&tb, dB.p, ld, N, ld, pair ? 128 : bn)) break;
+    TsMaps ts = {};                                        // (bias zero, like dbias)
+    if (bn == kPairTileTS && make_tmap_bf16_2d(&ts.c0, dO.p, N, M, N, 32)) break;
     EpiF32 e_plain{dC.as<float>(), nullptr, nullptr, N, N};
     EpiF32 e_res{dC.as<float>(), dbias.as<float>(), dR.as<float>(), N, N};
     EpiOperand e_op{dO.as<bf16>(), dbias.as<float>(), N, 0, ACT_GELU};
@@ -1532,7 +1721,7 @@ int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t 
       if (epi_kind == 0) ok = !gemm_tc<EpiF32>(ta, tb, p, e_plain, bn, prop.multiProcessorCount, 0);
       else if (epi_kind == 1) ok = !gemm_tc<EpiF32>(ta, tb, p, e_res, bn, prop.multiProcessorCount, 0);
       else if (epi_kind == 3) ok = !gemm_tc<EpiNull>(ta, tb, p, EpiNull{}, bn, prop.multiProcessorCount, 0);
-      else ok = !gemm_tc<EpiOperand>(ta, tb, p, e_op, bn, prop.multiProcessorCount, 0);
+      else ok = !gemm_tc<EpiOperand>(ta, tb, p, e_op, bn, prop.multiProcessorCount, 0, bn == kPairTileTS ? &ts : nullptr);
     }
     if (!ok) break;
     cudaEventRecord(e1, 0);

@@ -68,7 +68,10 @@ __device__ __forceinline__ void epilogue_tile(const Epi& epi, const GemmProblem&
         const int col0 = tile_col0 + c * 32;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          epi.apply8(v + 8 * q, col0 + 8 * q, tile_col0);
+          {
+            const float* bp = epi.bias_ptr() + col0 + 8 * q;
+            epi.apply8(v + 8 * q, __ldg(reinterpret_cast<const float4*>(bp)), __ldg(reinterpret_cast<const float4*>(bp + 4)), tile_col0);
+          }
           uint4 o;
           o.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
           o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
@@ -298,31 +301,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // accumulator rows into that CTA's TMEM.  Per SM and k-block this moves 32 KB instead of 48 KB through L2 -> shared memory -> tensor
 // core (TMA writes + UMMA operand reads of the 1-CTA 128 x 256 tile want 192 B/clk of a 128 B/clk shared-memory pipe at full tensor
 // rate, the pair 128), and the smaller stage allows a deeper ring.  Alone (null epilogue) this mainloop runs at 1.75 PFLOP/s even at
-// K = 512; with an epilogue the K = 512 GEMMs stop at ~1.07 PFLOP/s because the epilogue's own shared-memory round trip queues behind
-// that saturated pipe (profiles/r01_epilogue_clock64_timing.log).
+// K = 512.
 //   full[s]   : leader's barrier only; both CTAs' TMA loads complete_tx on it (cta_group::2 TMA), leader arms 64 KB
 //   empty[s]  : per CTA, arrived by the leader's tcgen05.commit multicast (mask 0b11)
 //   tfull[a]  : per CTA, same multicast commit after the last k-block
-//   tempty[a] : leader's barrier only; 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
+//   tempty[a] : leader's barrier only; 2 x 16 epilogue warps arrive (the peer's through mapa / shared::cluster)
+//
+// Three epilogue modes (MODE):
+//   0  generic: tcgen05.ld -> registers -> shared-memory transpose -> LSU stores (any functor; fp32 outputs, EXACT precision)
+//   1  TMA-store, row tiling: bf16 outputs of the thread = row layout are staged ONCE in shared memory in the 128B-swizzled box layout
+//      (32 rows x 64 columns per warp, conflict-free 16-byte stores) and leave with one cp.async.bulk.tensor store per warp and tile
+//      — no LDS, no STG, no address arithmetic per row; the TMA engine writes whole 128-byte lines.  (FFN1, CTC1)
+//   2  TMA-store, stream tiling (QKV, FAST precision): the M tiles are cut along STREAMS instead of rows through 3D maps of the A
+//      operand viewed as [stream][row in chunk][k] — "segment tiles" (128 / seg_rows streams x the seg_rows segment rows) and
+//      "right-context tiles" (128 / rc_rows streams x the rc_rows look-ahead rows).  A warp's 32 accumulator rows are then whole
+//      streams, and every destination of the fused Q | K | V projection is a TMA box: q rows through a 3D map of q, the K / V rows of a
+//      stream's segment are one seg_rows x 64 box in that session's ring (the ring advances by seg_rows, so the block never wraps), the
+//      right-context K / V rows one 4D box of the scratch.  Replaces the per-row pointer table + 64-byte LSU scatter.
 // ==========================================================================================================
-// P_BN = 128 variant (256 x 128 tile per pair): FOUR 128-column accumulator stages instead of two 256-column ones.  A K = 512 tile is
-// only 8 k-blocks of MMA (~2.9 us); with two stages the chain commit -> epilogue -> tempty -> next-but-one tile does not fit under one
-// tile of MMA and costs ~2.2 us per tile (measured); four stages give it three tiles.  The price is 24 instead of 32 KB of
-// operands per k-block for half the flops (1.5 x the L2 ingest per flop).
-template <int P_BN> struct PairCfg {
-  static constexpr int NACC = 512 / P_BN;                           // TMEM accumulator stages
-  static constexpr int STAGES = P_BN == 256 ? 4 : 6;
-  static constexpr int STAGE_BYTES = (BM + P_BN / 2) * BK * 2;      // 32 / 24 KB per CTA
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + 1024 + 256;
+constexpr int P_BN = 256;
+constexpr int P_STAGES = 4;
+constexpr int P_STAGE_BYTES = (BM + P_BN / 2) * BK * 2;             // 32 KB per CTA
+constexpr int TS_WARP_BYTES = 32 * 128;                             // one 32-row x 64-column bf16 box per epilogue warp
+template <int MODE> struct PairSmem {
+  static constexpr int STAGING = MODE == 0 ? kStagingBytes : kEpiWarps * TS_WARP_BYTES;
+  static constexpr int BYTES = P_STAGES * P_STAGE_BYTES + STAGING + 1024 + 256;
 };
-template <class Epi, int P_BN>
+
+// MODE 1 / 2: one accumulator tile of this warp (32 rows x 64 columns: chunks 2 * half, 2 * half + 1) -> bias / activation in the
+// thread = row layout -> packed bf16 -> the warp's staging box (row r at r * 128 B, 16-byte piece j at (j ^ (r & 7)) * 16: the
+// CU_TENSOR_MAP_SWIZZLE_128B pattern, bank-conflict-free for the 8 lanes of a store phase) -> fence.proxy.async.  The caller issues
+// the TMA store(s) after the __syncwarp() that ends this function.
+template <class Epi>
+__device__ __forceinline__ void ts_fill_box(const Epi& epi, const TsMaps& ts, int tile_col0, int half, int lane, uint32_t taddr, uint32_t tfull,
+                                            uint32_t tfull_phase, uint32_t stg) {
+  // the previous tile's store(s) of this warp must have finished READING the staging box (they had a whole tile's time)
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  float v[32], w[32];
+  {
+    tmem_ld32(taddr + (uint32_t)(half * 64), v);
+    tmem_ld32(taddr + (uint32_t)(half * 64 + 32), w);
+    tmem_ld_wait();
+  }
+  const int col0 = tile_col0 + half * 64;
+  const uint32_t row_addr = stg + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    {
+      const float* cb = ts.bias + col0 + 8 * q;              // kernel parameter: constant-bank loads, warp-uniform address
+      epi.apply8(v + 8 * q, make_float4(cb[0], cb[1], cb[2], cb[3]), make_float4(cb[4], cb[5], cb[6], cb[7]), tile_col0);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((uint32_t)q ^ sw) << 4)), "r"(pack_bf16x2(v[8 * q], v[8 * q + 1])),
+                 "r"(pack_bf16x2(v[8 * q + 2], v[8 * q + 3])), "r"(pack_bf16x2(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16x2(v[8 * q + 6], v[8 * q + 7])) : "memory");
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    {
+      const float* cb = ts.bias + col0 + 32 + 8 * q;
+      epi.apply8(w + 8 * q, make_float4(cb[0], cb[1], cb[2], cb[3]), make_float4(cb[4], cb[5], cb[6], cb[7]), tile_col0);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((uint32_t)(4 + q) ^ sw) << 4)), "r"(pack_bf16x2(w[8 * q], w[8 * q + 1])),
+                 "r"(pack_bf16x2(w[8 * q + 2], w[8 * q + 3])), "r"(pack_bf16x2(w[8 * q + 4], w[8 * q + 5])), "r"(pack_bf16x2(w[8 * q + 6], w[8 * q + 7])) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // my generic-proxy writes before the async-proxy (TMA) read of the box
+  __syncwarp();
+}
+
+template <class Epi, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi) {
-  constexpr int P_STAGES = PairCfg<P_BN>::STAGES, P_STAGE_BYTES = PairCfg<P_BN>::STAGE_BYTES, NACC = PairCfg<P_BN>::NACC;
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TsMaps ts, GemmProblem p, Epi epi,
+                StreamTiling stl) {
+  constexpr int NACC = 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + P_STAGES * P_STAGE_BYTES;
-  const uint32_t bar_base = staging_base + kStagingBytes;
+  const uint32_t bar_base = staging_base + PairSmem<MODE>::STAGING;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + s); };
@@ -331,21 +388,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Warp roles: TMA producer = warp 0, MMA issuer = warp 1, epilogue = warps 2 .. 17 (TMEM lane quarter = warp % 4).  Placing the two
+  // single-thread roles at the highest warp ids instead changes nothing (profiles/r02_gemm_warp_roles.log).
+  constexpr int kProducerWarp = 0, kMmaWarp = 1, kEpiWarp0 = 2;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + P_BN - 1) / P_BN;
+  const int n_tiles = (p.N + P_BN - 1) / P_BN;
+  // MODE 2: pair tiles [0, seg_pairs) are segment tiles, the rest right-context tiles
+  const int m_pairs = MODE == 2 ? stl.seg_pairs + stl.rc_pairs : (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = m_pairs * n_tiles;
   const int kb_per_pass = p.K / BK;
   const int total_kb = kb_per_pass * p.passes;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (MODE >= 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&ts.c0) : "memory");
+    if (MODE == 2) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&ts.a_rc) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&ts.c1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&ts.c2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&ts.c3) : "memory");
+    }
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -356,7 +425,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -364,6 +433,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
         const int row_a = m_pair * 2 * BM + (int)rank * BM;
         const int row_b = n_blk * P_BN + (int)rank * (P_BN / 2);
+        const bool seg_tile = m_pair < stl.seg_pairs;
+        const int stream0 = seg_tile ? (2 * m_pair + (int)rank) * stl.spt_seg : (2 * (m_pair - stl.seg_pairs) + (int)rank) * stl.spt_rc;
         for (int ps = 0; ps < p.passes; ++ps) {
           for (int kb = 0; kb < kb_per_pass; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);       // own slot free: the leader's MMAs that read it (in both CTAs) retired
@@ -371,14 +442,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t sb = sa + BM * BK * 2;
             const uint32_t lbar = full_bar(stage) & kPeerBitMask;
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)P_STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, p.a_koff[ps] + kb * BK, row_a, lbar);
+            if constexpr (MODE == 2) {
+              if (seg_tile) tma_load_3d_pair(sa, &tmA, p.a_koff[ps] + kb * BK, 0, stream0, lbar);
+              else tma_load_3d_pair(sa, &ts.a_rc, p.a_koff[ps] + kb * BK, stl.seg_rows, stream0, lbar);
+            } else {
+              tma_load_2d_pair(sa, &tmA, p.a_koff[ps] + kb * BK, row_a, lbar);
+            }
             tma_load_2d_pair(sb, &tmB, p.b_koff[ps] + kb * BK, row_b, lbar);
             if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
@@ -408,17 +484,54 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9, both CTAs) =====================
-    const int ew = warp - 2;
+    // ===================== epilogue (16 warps, both CTAs) =====================
+    const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * kXposeFloats;
+    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * kXposeFloats;     // MODE 0
+    const uint32_t stg = staging_base + (uint32_t)(ew * TS_WARP_BYTES);                                               // MODE 1 / 2
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
       const int row0 = m_pair * 2 * BM + (int)rank * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P_BN);
-      epilogue_tile<P_BN, kEpiWarps / 4, Epi>(epi, p, row0, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+      if constexpr (MODE == 0) {
+        epilogue_tile<P_BN, kEpiWarps / 4, Epi>(epi, p, row0, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
+      } else if constexpr (MODE == 1) {
+        ts_fill_box(epi, ts, n_blk * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, stg);
+        if (lane == 0 && row0 < p.M) {
+          tma_store_2d(&ts.c0, stg, n_blk * P_BN + half * 64, row0);
+          tma_store_commit();
+        }
+      } else {
+        // ---- MODE 2: Q | K | V with stream tiling
+        const bool seg_tile = m_pair < stl.seg_pairs;
+        const int spw = seg_tile ? stl.spw_seg : stl.spw_rc;                      // streams per warp (32 rows)
+        const int stream_w = (seg_tile ? (2 * m_pair + (int)rank) * stl.spt_seg : (2 * (m_pair - stl.seg_pairs) + (int)rank) * stl.spt_rc) + quarter * spw;
+        const int tile_col0 = n_blk * P_BN;
+        const int sec = tile_col0 / epi.d;                                        // 0: q, 1: k, 2: v (a tile never straddles the sections)
+        const int col_sec = tile_col0 - sec * epi.d + half * 64;
+        int kv_row = -1;                                                          // lane i < spw: cache row of stream (stream_w + i)'s segment block
+        if (sec > 0 && seg_tile && lane < spw && stream_w + lane < stl.n_streams) {
+          const int slot = __ldg(epi.slots + stream_w + lane);
+          kv_row = (int)(epi.kv_row0 + (long long)slot * epi.slot_rows + (long long)(sec - 1) * epi.ring + __ldg(epi.past_len + slot) % epi.ring);
+        }
+        ts_fill_box(epi, ts, tile_col0, half, lane, taddr, tfull_bar(acc), acc_phase, stg);
+        if (sec == 0) {
+          if (lane == 0 && stream_w < stl.n_streams) {
+            if (seg_tile) tma_store_3d(&ts.c0, stg, col_sec, 0, stream_w); else tma_store_3d(&ts.c1, stg, col_sec, stl.seg_rows, stream_w);
+            tma_store_commit();
+          }
+        } else if (seg_tile) {
+          if (kv_row >= 0) {
+            tma_store_2d(&ts.c2, stg + (uint32_t)(lane * stl.seg_rows * 128), col_sec, kv_row);
+            tma_store_commit();
+          }
+        } else if (lane == 0 && stream_w < stl.n_streams) {
+          tma_store_4d(&ts.c3, stg, col_sec, 0, sec - 1, stream_w);
+          tma_store_commit();
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -427,10 +540,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
+    if (MODE >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the staging box outlives this CTA's last store
   }
 
 #ifdef ASR_EPI_TIMING
-  if (blockIdx.x == 0 && threadIdx.x == 64 && g_epi_clk[0]) {
+  if (blockIdx.x == 0 && threadIdx.x == 32 * kEpiWarp0 && g_epi_clk[0]) {
     printf("epilogue warp 0 of CTA 0: %llu tiles, per tile: wait tfull %llu clk, TMEM loads %llu clk, math + staging + stores %llu clk (of which LDS + STG %llu)\n", g_epi_clk[0],
            g_epi_clk[1] / g_epi_clk[0], g_epi_clk[2] / g_epi_clk[0], g_epi_clk[3] / g_epi_clk[0], g_epi_clk[4] / g_epi_clk[0]);
     g_epi_clk[0] = g_epi_clk[1] = g_epi_clk[2] = g_epi_clk[3] = g_epi_clk[4] = 0;
@@ -438,193 +552,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
   tc_fence_before();
   cluster_sync_all();                                      // nobody frees TMEM / exits while the peer may still signal or read
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-template <class Epi, int P_BN>
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
-  constexpr int P_SMEM_BYTES = PairCfg<P_BN>::SMEM_BYTES;
+template <class Epi, int MODE>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB128, const TsMaps& ts, const GemmProblem& p, const Epi& epi, const StreamTiling& stl,
+                int num_sms, cudaStream_t st) {
+  constexpr int SMEM = PairSmem<MODE>::BYTES;
   static size_t attr_done[kMaxDevices] = {0};
-  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2_kernel<Epi, P_BN>, (size_t)P_SMEM_BYTES, attr_done));
-  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P_BN - 1) / P_BN);
+  ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2_kernel<Epi, MODE>, (size_t)SMEM, attr_done));
+  const int m_pairs = MODE == 2 ? stl.seg_pairs + stl.rc_pairs : (p.M + 2 * BM - 1) / (2 * BM);
+  const int tiles = m_pairs * ((p.N + P_BN - 1) / P_BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi, P_BN>, dim3(2 * pairs), dim3(kThreads), P_SMEM_BYTES, st, tmA, tmB128, p, epi));
+  ASR_CUDA_OK(launch_pdl(gemm_tc2_kernel<Epi, MODE>, dim3(2 * pairs), dim3(kThreads), SMEM, st, tmA, tmB128, ts, p, epi, stl));
   return 0;
-}
-
-// ==========================================================================================================
-// A-RESIDENT CTA-pair variant for short K (K <= 512: QKV, FFN1) — an experiment kept as an opt-in (ASR_B200_PAIR_A=1): bit-identical
-// to gemm_tc2_kernel and 7 % SLOWER (128 vs 119 us on 81,920 x 1536 x 512): the operand traffic it saves is not what bounds these GEMMs
-// (their mainloop alone runs at 1.75 PFLOP/s), and the unit boundary exposes the A reload.
-// The A tile (this CTA's 128 rows x K, 128 KB) is loaded ONCE per work unit and stays in shared memory while the
-// unit's N tiles stream only their B operand (16 KB per k-block and CTA instead of 32): a unit = one 256-row block x half of the N
-// tiles (two units per block keep the 74 pairs balanced: 640 units / 74), ingest per tile 128 KB + 128/3 (QKV) or 128/4 (FFN1) KB
-// instead of 256 KB.  It fits because the bf16-row epilogue needs 2 KB of staging per warp instead of 4.6 KB.
-//   a_full[kb] / a_empty[kb] : per k-block of the resident A tile (leader's barrier collects both CTAs' 16 KB; released by the commit
-//                              after the unit's last tile used it, so the next unit's A streams in behind the MMAs)
-//   b_full[s] / b_empty[s]   : the B ring, as in gemm_tc2_kernel
-// ==========================================================================================================
-constexpr int RA_KB = 8;                                            // k-blocks of the resident A tile (K <= 512)
-constexpr int RA_B_STAGES = 4;
-constexpr int RA_B_STAGE_BYTES = (256 / 2) * BK * 2;                // 16 KB: this CTA's half of the 256 weight rows
-constexpr int RA_A_BYTES = RA_KB * BM * BK * 2;                     // 128 KB
-constexpr int RA_XPOSE_FLOATS = 512;                                // 2 KB per epilogue warp (bf16-row path only)
-constexpr int RA_SMEM_BYTES = RA_A_BYTES + RA_B_STAGES * RA_B_STAGE_BYTES + kEpiWarps * RA_XPOSE_FLOATS * 4 + 1024 + 256;
-static_assert(RA_SMEM_BYTES <= 232448, "A-resident pair GEMM: shared memory budget");
-template <class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tc2a_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, Epi epi, int n_split) {
-  constexpr int P_BN = 256;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_base = smem_base + RA_A_BYTES;
-  const uint32_t staging_base = b_base + RA_B_STAGES * RA_B_STAGE_BYTES;
-  const uint32_t bar_base = staging_base + kEpiWarps * RA_XPOSE_FLOATS * 4;
-  auto a_full = [&](int k) { return bar_base + 8u * k; };
-  auto a_empty = [&](int k) { return bar_base + 8u * (RA_KB + k); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * RA_KB + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * RA_KB + RA_B_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + 2 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * RA_KB + 2 * RA_B_STAGES + 4);
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = p.N / P_BN;
-  const int tpu = n_tiles / n_split;                        // N tiles per unit
-  const int num_units = m_pairs * n_split;
-  const int n_kb = p.K / BK;                                // <= RA_KB
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int k = 0; k < RA_KB; ++k) { mbar_init(a_full(k), 1); mbar_init(a_empty(k), 1); }
-    for (int s = 0; s < RA_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, a_phase = 0;
-      for (int unit = cluster_id; unit < num_units; unit += n_clusters, a_phase ^= 1u) {
-        const int m_pair = unit / n_split, part = unit - m_pair * n_split;
-        const int row_a = m_pair * 2 * BM + (int)rank * BM;
-        for (int t = 0; t < tpu; ++t) {
-          const int row_b = (part * tpu + t) * P_BN + (int)rank * (P_BN / 2);
-          for (int kb = 0; kb < n_kb; ++kb) {
-            if (t == 0) {                                   // the unit's A tile, k-block by k-block, interleaved with the first tile's B
-              mbar_wait(a_empty(kb), a_phase ^ 1u);
-              if (rank == 0) mbar_expect_tx(a_full(kb), 2u * (uint32_t)(BM * BK * 2));
-              tma_load_2d_pair(smem_base + (uint32_t)(kb * BM * BK * 2), &tmA, kb * BK, row_a, a_full(kb) & kPeerBitMask);
-            }
-            mbar_wait(b_empty(stage), phase ^ 1u);
-            if (rank == 0) mbar_expect_tx(b_full(stage), 2u * (uint32_t)RA_B_STAGE_BYTES);
-            tma_load_2d_pair(b_base + (uint32_t)(stage * RA_B_STAGE_BYTES), &tmB, kb * BK, row_b, b_full(stage) & kPeerBitMask);
-            if (++stage == RA_B_STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-      int stage = 0; uint32_t phase = 0, a_phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int unit = cluster_id; unit < num_units; unit += n_clusters, a_phase ^= 1u) {
-        for (int t = 0; t < tpu; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P_BN);
-          for (int kb = 0; kb < n_kb; ++kb) {
-            mbar_wait(a_full(kb), a_phase);                 // (already complete for every tile but the unit's first)
-            mbar_wait(b_full(stage), phase);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint64_t adesc = make_smem_desc(smem_base + (uint32_t)(kb * BM * BK * 2));
-              const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(stage * RA_B_STAGE_BYTES));
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_commit_pair(b_empty(stage), 3);
-              if (t == tpu - 1) umma_commit_pair(a_empty(kb), 3);     // the resident A k-block may be overwritten by the next unit's
-              if (kb == n_kb - 1) umma_commit_pair(tfull_bar(acc), 3);
-            }
-            __syncwarp();
-            if (++stage == RA_B_STAGES) { stage = 0; phase ^= 1u; }
-          }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue (16 warps, both CTAs): bf16-row path only =====================
-    const int ew = warp - 2;
-    const int quarter = warp & 3;
-    const int half = ew >> 2;
-    float* xpose = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) + ew * RA_XPOSE_FLOATS;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int unit = cluster_id; unit < num_units; unit += n_clusters) {
-      const int m_pair = unit / n_split, part = unit - m_pair * n_split;
-      const int row0 = m_pair * 2 * BM + (int)rank * BM + quarter * 32;
-      for (int t = 0; t < tpu; ++t) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P_BN);
-        epilogue_tile<P_BN, kEpiWarps / 4, Epi, true>(epi, p, row0, (part * tpu + t) * P_BN, half, lane, taddr, tfull_bar(acc), acc_phase, xpose);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (rank == 0) mbar_arrive(tempty_bar(acc));
-          else mbar_arrive_cta(tempty_bar(acc), 0);
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-template <class Epi>
-int launch_pair_a(const CUtensorMap& tmA, const CUtensorMap& tmB128, const GemmProblem& p, const Epi& epi, int num_sms, cudaStream_t st) {
-  if constexpr (Epi::kBf16Rows) {
-    const int n_tiles = p.N / 256;
-    if (p.N % 256 != 0 || n_tiles % 2 != 0 || p.passes != 1 || p.K > RA_KB * BK || !epi.bf16_rows()) {
-      set_error("gemm_tc: the A-resident pair kernel needs bf16 row outputs, one pass, K <= %d and N a multiple of 512 (N %d K %d passes %d)", RA_KB * BK, p.N, p.K, p.passes);
-      return -1;
-    }
-    static size_t attr_done[kMaxDevices] = {0};
-    ASR_CUDA_OK(ensure_dyn_smem(gemm_tc2a_kernel<Epi>, (size_t)RA_SMEM_BYTES, attr_done));
-    const int n_split = 2;
-    const int units = ((p.M + 2 * BM - 1) / (2 * BM)) * n_split;
-    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
-    ASR_CUDA_OK(launch_pdl(gemm_tc2a_kernel<Epi>, dim3(2 * pairs), dim3(kThreads), RA_SMEM_BYTES, st, tmA, tmB128, p, epi, n_split));
-    return 0;
-  } else {
-    set_error("gemm_tc: the A-resident pair kernel exists for bf16-row epilogues only");
-    return -1;
-  }
 }
 
 template <int BN, class Epi>
@@ -641,26 +585,40 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem&
 }  // namespace
 
 template <class Epi>
-int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const Epi& epi, int bn, int num_sms, cudaStream_t st) {
+int gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const Epi& epi, int bn, int num_sms, cudaStream_t st,
+            const TsMaps* ts, const StreamTiling* stl) {
   if (p.M <= 0) return 0;
   if (p.K % BK != 0) { set_error("gemm_tc: K=%d not a multiple of %d", p.K, BK); return -1; }
+  static const TsMaps no_maps = {};
   switch (bn) {
-    case kPairTile: return launch_pair<Epi, 256>(tmA, tmB, p, epi, num_sms, st);      // tmB must be the 128-row-box map
-    case kPairTile128: return launch_pair<Epi, 128>(tmA, tmB, p, epi, num_sms, st);   // tmB must be the 64-row-box map
-    case kPairTileA: return launch_pair_a<Epi>(tmA, tmB, p, epi, num_sms, st);        // tmB must be the 128-row-box map
+    case kPairTile: return launch_pair<Epi, 0>(tmA, tmB, no_maps, p, epi, StreamTiling{}, num_sms, st);      // tmB must be the 128-row-box map
+    case kPairTileTS:
+      if constexpr (Epi::kBf16Rows && !Epi::kStreamTiles) {
+        if (!ts || !epi.bf16_rows() || p.N % P_BN != 0 || p.N > kTsBiasMax) { set_error("gemm_tc: the TMA-store epilogue needs bf16 row outputs, their tensor map and N %% 256 == 0 (N %d)", p.N); return -1; }
+        return launch_pair<Epi, 1>(tmA, tmB, *ts, p, epi, StreamTiling{}, num_sms, st);
+      } else break;
+    case kPairTileQKV:
+      if constexpr (Epi::kStreamTiles) {
+        if (!ts || !stl || p.N != 3 * epi.d || p.N > kTsBiasMax || epi.d % P_BN != 0 || 128 % stl->seg_rows || 32 % stl->seg_rows || 32 % stl->rc_rows || stl->seg_rows + stl->rc_rows != epi.rows) {
+          set_error("gemm_tc: stream tiling needs the tensor maps, N = 3 d, d %% 256 == 0 and row counts that divide 32"); return -1;
+        }
+        return launch_pair<Epi, 2>(tmA, tmB, *ts, p, epi, *stl, num_sms, st);
+      } else break;
     case 64: return launch_bn<64, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 128: return launch_bn<128, Epi>(tmA, tmB, p, epi, num_sms, st);
     case 256: return launch_bn<256, Epi>(tmA, tmB, p, epi, num_sms, st);
   }
-  set_error("gemm_tc: unsupported BN=%d", bn);
+  set_error("gemm_tc: unsupported BN=%d for this epilogue", bn);
   return -1;
 }
 
-template int gemm_tc<EpiF32>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiF32&, int, int, cudaStream_t);
-template int gemm_tc<EpiNull>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiNull&, int, int, cudaStream_t);
-template int gemm_tc<EpiOperand>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiOperand&, int, int, cudaStream_t);
-template int gemm_tc<EpiQKV<float>>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiQKV<float>&, int, int, cudaStream_t);
-template int gemm_tc<EpiQKV<bf16>>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const EpiQKV<bf16>&, int, int, cudaStream_t);
+#define ASR_INST_GEMM(E) template int gemm_tc<E>(const CUtensorMap&, const CUtensorMap&, const GemmProblem&, const E&, int, int, cudaStream_t, const TsMaps*, const StreamTiling*)
+ASR_INST_GEMM(EpiF32);
+ASR_INST_GEMM(EpiNull);
+ASR_INST_GEMM(EpiOperand);
+ASR_INST_GEMM(EpiQKV<float>);
+ASR_INST_GEMM(EpiQKV<bf16>);
+#undef ASR_INST_GEMM
 
 // ------------------------------------------------------------------------------------------
 // Host: TMA descriptors.  cuTensorMapEncodeTiled is fetched through the runtime so the library has no
@@ -715,6 +673,25 @@ int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t rows, uint
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3D) failed: CUresult %d (rows %llu heads %u box_rows %u)", (int)r, (unsigned long long)rows, n_heads, box_rows); return -1; }
+  return 0;
+}
+
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) { set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e)); return -1; }
+    fn = (EncodeTiledFn)p;
+  }
+  if (rank < 2 || rank > 4) { set_error("make_tmap_bf16_nd: rank %d", rank); return -1; }
+  cuuint64_t gdim[4]; cuuint64_t gstr[3]; cuuint32_t bx[4]; cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed: CUresult %d", rank, (int)r); return -1; }
   return 0;
 }
 

@@ -69,13 +69,17 @@ struct CtcParams {
   int* prev_id;            // last argmax id of the segment so far (-1: none)
   int* n_frames;           // frames accumulated in the current utterance segment
   int* last_tok_frame;     // index of last frame with id > 1 (-1: none)
+  int* seg_has_text;       // the segment so far holds an id whose vocabulary string survives greedy_search's stripping (recognition.py:47-52)
+  const uint32_t* silent_mask;   // [ceil(vocab / 32)] bit = id renders to the empty string ('-', '|', '<<', '>>' in the reference vocabulary)
   int* past_len;           // advanced by seg_rows here (end of step)
   // outputs per stream
   int* argmax_ids;         // [B*seg_rows]
   int* new_tokens;         // [B*seg_rows] collapsed, blank-dropped ids appended this chunk
   int* n_new;              // [B]
   int* blank_frames;       // [B]  frames since last token (or all frames if none)
-  int* has_token;          // [B]
+  int* has_token;          // [B]  an id > 1 exists in the segment (the `tokens_idx` test of recognition.py:40)
+  int* has_text;           // [B]  the rendered text of the segment is non-empty (the `if text:` test of stream.py:121)
+  int* flags;              // [B]  cleared here (ASR_FLAG_* bits are OR-ed in by later kernels of the step)
   float* logprobs;         // nullable [B*seg_rows, vocab]
 };
 int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st);
@@ -83,7 +87,8 @@ int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st);
 // ---------------------------------------------------------------- CTC prefix beam search (warp per stream)
 constexpr int BEAM_MAX = 16;         // beam width limit
 constexpr int BEAM_CAND_MAX = 8;     // extension candidates per frame limit
-constexpr int BEAM_MAX_LEN = 256;    // tokens per hypothesis (an utterance is force-ended at 40 s = 1000 frames, asr-online.yaml:103-107)
+constexpr int BEAM_MAX_LEN = 1024;   // tokens per hypothesis: an utterance is force-ended at 40 s = 1000 frames (asr-online.yaml:103-107) and CTC emits
+                                     // at most one token per frame, so the cap is never reached under the reference's rules; if it is, the step says so
 struct BeamParams {
   const float* logprobs;   // [n*seg_rows, vocab] of the current step
   const int* slots;        // [n]
@@ -95,9 +100,10 @@ struct BeamParams {
   unsigned long long* hash;            // [slots*BEAM_MAX]
   int16_t* tokens;                     // [slots][2][BEAM_MAX][BEAM_MAX_LEN]
   // outputs of the step: best hypothesis so far per stream
-  int* out_tokens;         // [n*BEAM_MAX_LEN]
+  int16_t* out_tokens;     // [n*BEAM_MAX_LEN]
   int* out_len;            // [n]
   float* out_score;        // [n]
+  int* out_flags;          // [n] |= ASR_FLAG_BEAM_TRUNCATED when a hypothesis could not be extended because it is BEAM_MAX_LEN - 1 tokens long
 };
 int beam_launch(const BeamParams& P, cudaStream_t st);
 int beam_reset_many_launch(const BeamParams& P, const int* d_slots, int n, cudaStream_t st);
@@ -108,8 +114,8 @@ int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int 
 int fill_i32(int* p, int v, size_t n, cudaStream_t st);
 // device-side batch assembly from pinned host rings (zero-copy reads): dst[i] = base[src_off[i] .. + chunk_len)
 int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st);
-// endpoint on many sessions at once: past_len = n_frames = 0, prev_id = last_tok = -1 for the listed slots
-int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, cudaStream_t st);
+// endpoint on many sessions at once: past_len = n_frames = has_text = 0, prev_id = last_tok = -1 for the listed slots
+int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, int* has_text, cudaStream_t st);
 // per-utterance CMVN over the frames of one call (TA:compliance/kaldi.py:603-606, subtract_mean)
 int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cudaStream_t st);
 

@@ -997,16 +997,19 @@ __global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const int slot = P.slots[b];
-    int prev = P.prev_id[slot], nf = P.n_frames[slot], lt = P.last_tok_frame[slot], n_new = 0;
+    int prev = P.prev_id[slot], nf = P.n_frames[slot], lt = P.last_tok_frame[slot], ht = P.seg_has_text[slot], n_new = 0;
     for (int r = 0; r < P.seg_rows; ++r) {
       const int id = s_ids[r];
       if (id != prev && id != 0) P.new_tokens[(size_t)b * P.seg_rows + n_new++] = id;   // unique_consecutive, then drop blank
       if (id > 1) lt = nf;                                                              // tokens_idx = indices > 1
+      ht |= !((P.silent_mask[id >> 5] >> (id & 31)) & 1u);                              // `if text:` (stream.py:121): an id that renders to something
       prev = id; ++nf;
     }
-    P.prev_id[slot] = prev; P.n_frames[slot] = nf; P.last_tok_frame[slot] = lt;
+    P.prev_id[slot] = prev; P.n_frames[slot] = nf; P.last_tok_frame[slot] = lt; P.seg_has_text[slot] = ht;
     P.n_new[b] = n_new;
     P.has_token[b] = lt >= 0;
+    P.has_text[b] = ht;
+    P.flags[b] = 0;
     P.blank_frames[b] = lt >= 0 ? nf - 1 - lt : nf;
     P.past_len[slot] += P.seg_rows;                                                     // TA:emformer.py:413 (state[3] + update_length)
   }
@@ -1034,10 +1037,10 @@ __global__ void subtract_mean_kernel(float* __restrict__ x, int n_frames, int n_
   }
 }
 
-__global__ void reset_slots_kernel(const int* __restrict__ slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok) {
+__global__ void reset_slots_kernel(const int* __restrict__ slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, int* has_text) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = slots[i];
-    past_len[s] = 0; n_frames[s] = 0; prev_id[s] = -1; last_tok[s] = -1;
+    past_len[s] = 0; n_frames[s] = 0; prev_id[s] = -1; last_tok[s] = -1; has_text[s] = 0;
   }
 }
 
@@ -1139,9 +1142,9 @@ int subtract_mean_launch(float* x, int n_streams, int n_frames, int n_mels, cuda
   return 0;
 }
 
-int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, cudaStream_t st) {
+int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, int* has_text, cudaStream_t st) {
   if (n <= 0) return 0;
-  reset_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(slots, n, past_len, n_frames, prev_id, last_tok);
+  reset_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(slots, n, past_len, n_frames, prev_id, last_tok, has_text);
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

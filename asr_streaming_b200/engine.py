@@ -12,7 +12,8 @@ from .config import ModelConfig
 FRAMERATE = 0.04            # recognition.py:30
 PCM_I16, PCM_F32 = 0, 1
 FBANK_MELSPEC128, FBANK_KALDI80 = 0, 1
-BEAM_MAX_LEN = 256
+BEAM_MAX_LEN = 1024          # ASR_BEAM_MAX_LEN
+FLAG_BEAM_TRUNCATED = 1      # ASR_FLAG_BEAM_TRUNCATED
 
 
 class StepResult:
@@ -20,17 +21,19 @@ class StepResult:
     first access from the padded arrays the device returned: a tick over thousands of sessions never pays for them unless asked."""
 
     def __init__(self, argmax_ids, new_tokens, blank_frames, has_token, logprobs, beam_tokens=None, beam_score=None, n_new=None,
-                 new_tokens_padded=None, beam_tokens_padded=None, beam_len=None):
+                 new_tokens_padded=None, beam_tokens_padded=None, beam_len=None, has_text=None, flags=None):
         self.argmax_ids = argmax_ids                 # [n, S] int32
         self._new_tokens = new_tokens                # n arrays of the ids appended this chunk (collapsed, blank-free) or None (lazy)
         self.blank_frames = blank_frames             # [n] int32
-        self.has_token = has_token                   # [n] bool
+        self.has_token = has_token                   # [n] bool: an id > 1 exists in the segment (recognition.py:40-41)
+        self.has_text = has_token if has_text is None else has_text   # [n] bool: the rendered text of the segment is non-empty (stream.py:121)
+        self.flags = flags                           # [n] int32 FLAG_* bits (None from engines that have none)
         self.logprobs = logprobs                     # [n, S, V] float32 or None
         self._beam_tokens = beam_tokens              # n arrays: best prefix-beam hypothesis of the utterance so far, or None (lazy / no beam)
         self.beam_score = beam_score                 # [n] log-probability of that hypothesis
         self.n_new = n_new                           # [n] int32: len(new_tokens[i])
         self.new_tokens_padded = new_tokens_padded   # [n, S] int32, row i valid in [:n_new[i]] (struct-of-arrays form)
-        self.beam_tokens_padded = beam_tokens_padded  # [n, BEAM_MAX_LEN] int32, row i valid in [:beam_len[i]]
+        self.beam_tokens_padded = beam_tokens_padded  # [n, BEAM_MAX_LEN] int16, row i valid in [:beam_len[i]] (the rest is not written)
         self.beam_len = beam_len
 
     @property
@@ -42,7 +45,7 @@ class StepResult:
     @property
     def beam_tokens(self) -> Optional[List[np.ndarray]]:
         if self._beam_tokens is None and self.beam_tokens_padded is not None:
-            self._beam_tokens = [self.beam_tokens_padded[i, :self.beam_len[i]].copy() for i in range(len(self.beam_len))]
+            self._beam_tokens = [self.beam_tokens_padded[i, :self.beam_len[i]].astype(np.int32) for i in range(len(self.beam_len))]
         return self._beam_tokens
 
     def last_blank(self, i: int) -> float:
@@ -114,6 +117,11 @@ class Engine:
         _lib.check(self.lib, self.lib.asr_session_open(self._h, C.byref(s)), "asr_session_open")
         return s.value
 
+    def set_silent_ids(self, ids: Sequence[int]) -> None:
+        """Vocabulary ids that render to "" in greedy_search (see ``recognition.silent_ids``): they never make ``has_text`` true."""
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        _lib.check(self.lib, self.lib.asr_set_silent_ids(self._h, int(a.size), a.ctypes.data), "asr_set_silent_ids")
+
     def reset_session(self, slot: int) -> None:
         _lib.check(self.lib, self.lib.asr_session_reset(self._h, slot), "asr_session_reset")
 
@@ -166,12 +174,13 @@ class Engine:
     def _alloc_out(self, n: int, want_logprobs: bool):
         S, V = self.S, self.cfg.vocab
         bufs = dict(argmax=np.empty((n, S), np.int32), newtok=np.empty((n, S), np.int32), nnew=np.empty(n, np.int32),
-                    blank=np.empty(n, np.int32), hastok=np.empty(n, np.int32),
+                    blank=np.empty(n, np.int32), hastok=np.empty(n, np.int32), hastext=np.empty(n, np.int32), flags=np.empty(n, np.int32),
                     logprobs=np.empty((n, S, V), np.float32) if want_logprobs else None)
         o = _lib.AsrStepOutC(bufs["argmax"].ctypes.data, bufs["newtok"].ctypes.data, bufs["nnew"].ctypes.data, bufs["blank"].ctypes.data,
                              bufs["hastok"].ctypes.data, bufs["logprobs"].ctypes.data if want_logprobs else None)
+        o.has_text, o.flags = bufs["hastext"].ctypes.data, bufs["flags"].ctypes.data
         if self.beam:
-            bufs["btok"] = np.empty((n, BEAM_MAX_LEN), np.int32)
+            bufs["btok"] = np.empty((n, BEAM_MAX_LEN), np.int16)
             bufs["blen"] = np.empty(n, np.int32)
             bufs["bscore"] = np.empty(n, np.float32)
             o.beam_tokens, o.beam_len, o.beam_score = bufs["btok"].ctypes.data, bufs["blen"].ctypes.data, bufs["bscore"].ctypes.data
@@ -180,7 +189,7 @@ class Engine:
     @staticmethod
     def _result(bufs, n) -> StepResult:
         r = StepResult(bufs["argmax"], None, bufs["blank"], bufs["hastok"].astype(bool), bufs["logprobs"],
-                       n_new=bufs["nnew"], new_tokens_padded=bufs["newtok"])
+                       n_new=bufs["nnew"], new_tokens_padded=bufs["newtok"], has_text=bufs["hastext"].astype(bool), flags=bufs["flags"])
         if "btok" in bufs:
             r.beam_tokens_padded, r.beam_len, r.beam_score = bufs["btok"], bufs["blen"], bufs["bscore"]
         return r
@@ -341,7 +350,7 @@ class Engine:
 
 def debug_gemm(A: np.ndarray, B: np.ndarray, bias: Optional[np.ndarray] = None, impl: int = 0, split: int = 0, bn: int = 128,
                device: int = 0) -> np.ndarray:
-    """C = A @ B.T (+bias) through the tcgen05 (impl 0) or CUDA-core (impl 1) GEMM."""
+    """C = A @ B.T (+bias) through the tcgen05 GEMM."""
     lib = _lib.load_library()
     A = np.ascontiguousarray(A, np.float32)
     B = np.ascontiguousarray(B, np.float32)
@@ -352,6 +361,20 @@ def debug_gemm(A: np.ndarray, B: np.ndarray, bias: Optional[np.ndarray] = None, 
     _lib.check(lib, lib.asr_debug_gemm(impl, M, N, K, split, bn, A.ctypes.data, B.ctypes.data, b.ctypes.data if b is not None else None,
                                        Cm.ctypes.data, device), "asr_debug_gemm")
     return Cm
+
+
+def debug_gemm_operand(A: np.ndarray, B: np.ndarray, bias: np.ndarray, act: int = 1, bn: int = 515, device: int = 0) -> np.ndarray:
+    """bf16(act(A @ B.T + bias)) as fp32 through the EpiOperand epilogue (bn 512: LSU stores, 515: TMA stores; act 0 none, 1 GELU, 2 SiLU)."""
+    lib = _lib.load_library()
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    M, K = A.shape
+    N = B.shape[0]
+    out = np.empty((M, N), np.float32)
+    _lib.check(lib, lib.asr_debug_gemm_operand(M, N, K, bn, act, A.ctypes.data, B.ctypes.data, bias.ctypes.data, out.ctypes.data, device),
+               "asr_debug_gemm_operand")
+    return out
 
 
 def debug_gemm_ln(A: np.ndarray, W: np.ndarray, bias: np.ndarray, res: np.ndarray, g1: np.ndarray, b1: np.ndarray,

@@ -64,6 +64,22 @@ def ids_to_text(ids: Sequence[int], vocab: Optional[Sequence[str]] = None) -> st
     return re.sub(r"\s+", " ", text).strip()
 
 
+def silent_ids(vocab: Optional[Sequence[str]] = None) -> List[int]:
+    """Ids whose vocabulary string renders to "" under recognition.py:47-52 ('-', '|', '<<', '>>' in the reference's
+    corpus/vocab.txt: ids 0, 1, 792, 793).  A segment whose tokens are all silent has empty text: ``Stream.update_stream`` then takes
+    the ``else`` branch (stream.py:121-125).  Every other entry must keep a character that the stripping cannot remove (otherwise
+    emptiness would depend on neighbouring tokens and could not be decided per id): checked here."""
+    v = list(vocab) if vocab is not None else get_vocab()
+    out = []
+    for i, t in enumerate(v):
+        if ids_to_text([i], v) == "" or i == 0:
+            out.append(i)
+        elif not any(c not in "<>-| \t\r\n" for c in t):
+            raise ValueError(f"vocabulary entry {i} ({t!r}) consists of strippable characters only: whether a segment's text is empty "
+                             "would depend on token order; this table is not supported by the per-id silent mask")
+    return out
+
+
 class SessionState:
     """Opaque replacement of the reference's 20x4 state tensor list."""
 
@@ -73,6 +89,7 @@ class SessionState:
         self.n_frames = 0
         self.blank_frames = 0
         self.has_token = False
+        self.has_text = False
         if engine is not None and slot is not None:
             self._fin = weakref.finalize(self, _release, weakref.ref(engine), slot)
 
@@ -155,6 +172,7 @@ class LightningASR:
             weights = weights_from_checkpoint(os.path.join(model_dir or "", filepath), cfg)
         self.cfg = cfg
         self.engine = Engine(cfg, weights, index)
+        self.engine.set_silent_ids(silent_ids(self.vocab))
 
     def init_state(self) -> SessionState:
         """recognition.py:207-217."""
@@ -180,6 +198,7 @@ class LightningASR:
             st.n_frames += self.cfg.seg_rows
             st.blank_frames = int(res.blank_frames[i])
             st.has_token = bool(res.has_token[i])
+            st.has_text = bool(res.has_text[i])
         em = torch.from_numpy(res.logprobs).as_subclass(Emission)
         em._asr_states = out_states
         lengths = torch.full((n,), self.cfg.seg_rows, dtype=torch.long)

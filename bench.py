@@ -214,7 +214,7 @@ class RaggedWorkload:
 
     def _after(self, res):
         """Scripted endpoints: a session whose just-decoded chunk was the last speech chunk of an utterance is reset."""
-        self.skipped_chunks += len(res.skipped)
+        self.skipped_chunks += int(res.skipped_rows.size)
         rows = res.rows
         if rows.size == 0:
             return
@@ -234,7 +234,7 @@ class RaggedWorkload:
                 t0 = time.perf_counter()
                 p = self.sch.submit_tick(gate=self.gate, max_rows=max_rows)
                 self.t_submit += time.perf_counter() - t0
-                if p.rows.size == 0 and not p.res.skipped:
+                if p.rows.size == 0 and p.res.skipped_rows.size == 0:
                     break                                           # nothing left to launch in this pass; `prev` stays in flight
                 self.n_ticks += 1
                 if prev is not None:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ASR_B200_ABI_VERSION 1
+#define ASR_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ASR_API __attribute__((visibility("default")))
@@ -64,20 +64,25 @@ typedef struct AsrConfig {
   int32_t max_batch;       /* max stream-chunks per step */
 } AsrConfig;
 
+#define ASR_BEAM_MAX_LEN 1024        /* tokens per beam hypothesis: rule4 force-ends an utterance at 40 s = 1000 frames (asr-online.yaml:103-107) */
+enum { ASR_FLAG_BEAM_TRUNCATED = 1 };  /* AsrStepOut.flags: a beam hypothesis reached ASR_BEAM_MAX_LEN - 1 tokens and could not be extended */
+
 typedef struct AsrStepOut {     /* all pointers nullable, host memory, n = streams in the step, S = segment rows (16) */
   int32_t* argmax_ids;          /* [n*S]  per-frame argmax of the log-probs (recognition.py:36)                       */
   int32_t* new_tokens;          /* [n*S]  ids appended this chunk after unique_consecutive + blank drop (:44-45)     */
   int32_t* n_new;               /* [n]                                                                                */
   int32_t* blank_frames;        /* [n]    frames since the last id > 1, or all frames of the segment if none (:38-43) */
-  int32_t* has_token;           /* [n]                                                                                */
+  int32_t* has_token;           /* [n]    an id > 1 exists in the segment: `len(tokens_idx)` (recognition.py:40-41)    */
   float* logprobs;              /* [n*S*vocab]  the reference's `emission` (recognition.py:203-204)                   */
   /* CTC prefix beam search (only when asr_set_beam enabled it): best hypothesis of the utterance so far               */
-  int32_t* beam_tokens;         /* [n*ASR_BEAM_MAX_LEN]                                                               */
+  int16_t* beam_tokens;         /* [n*ASR_BEAM_MAX_LEN]  row i valid in [0, beam_len[i])                              */
   int32_t* beam_len;            /* [n]                                                                                */
   float* beam_score;            /* [n]  log P(best prefix)                                                            */
+  int32_t* has_text;            /* [n]    greedy_search's rendered text of the segment is non-empty: the `if text:` of
+                                          Stream.update_stream (stream.py:121); differs from has_token for ids that render to ""
+                                          (asr_set_silent_ids)                                                        */
+  int32_t* flags;               /* [n]    ASR_FLAG_* bits                                                             */
 } AsrStepOut;
-
-#define ASR_BEAM_MAX_LEN 256
 
 typedef struct AsrStats {
   uint64_t steps;               /* asr_step calls                                  */
@@ -103,11 +108,18 @@ ASR_API int asr_engine_destroy(AsrEngine* e);
 
 /* Replaces LightningASR.init_state (recognition.py:207-217) and `stream.state = state_init`
  * (streaming_server.py:324-326, :530): a session owns one K/V ring slot + greedy carry. */
+/* open / reset never wait for the device: the state is cleared by a stream-ordered kernel, i.e. after every step already submitted
+ * (a reset of a session that rides a step in flight applies to the steps submitted afterwards).  close fails while a submitted,
+ * uncollected step carries the session. */
 ASR_API int asr_session_open(AsrEngine* e, int32_t* slot_out);
 ASR_API int asr_session_reset(AsrEngine* e, int32_t slot);           /* endpoint: state := init, emission := []  (:514-515, :530) */
 ASR_API int asr_session_close(AsrEngine* e, int32_t slot);
 /* Endpoints of one tick in one launch.  Asynchronous and stream-ordered: takes effect after every step already submitted. */
 ASR_API int asr_session_reset_many(AsrEngine* e, int32_t n, const int32_t* slots);
+/* Vocabulary ids whose string renders to "" in greedy_search (recognition.py:47-52 strips '<<', '>>', '-' and turns '|' into a space that
+ * strip() removes): they do not make a segment's text non-empty (AsrStepOut.has_text).  Default {0, 1}; the reference vocabulary
+ * (lightspeech/corpus/vocab.txt) also has 792 '<<' and 793 '>>'. */
+ASR_API int asr_set_silent_ids(AsrEngine* e, int32_t n, const int32_t* ids);
 
 /* Native batch assembly for the scheduler: for i < n copy chunk_length int16 samples from base[rows[i]*row_stride + offsets[i]]
  * into row i of the pinned staging buffer of the NEXT step (multi-threaded); *pinned_out = that buffer (pass it as `pcm`). */
@@ -120,7 +132,7 @@ ASR_API int asr_pcm_peaks(int32_t n, const int16_t* base, int64_t row_stride, co
 
 /* Replaces LightningASR.stream (recognition.py:191-204) + greedy_search (recognition.py:33-57) for n sessions with
  * arbitrary, different progress.  pcm: packed [n, chunk_length] int16 (as received from the websocket,
- * streaming_server.py:362) or float32 in [-1,1).  A session may appear at most once per step. */
+ * streaming_server.py:362) or float32 in [-1,1).  A session may appear at most once per step (duplicates are rejected). */
 ASR_API int asr_step(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, const AsrStepOut* out);
 
 /* Pipelined form: asr_submit enqueues a step (H2D on a copy stream, kernels + D2H of the results on the compute stream) and
@@ -139,7 +151,8 @@ ASR_API void* asr_host_alloc(uint64_t bytes);
 ASR_API int asr_host_free(void* p);
 
 /* Same, split for pipelining / device-resident timing: stage = H2D of inputs; run = kernels only (async on the
- * engine stream); fetch = D2H of results + synchronise. */
+ * engine stream); fetch = D2H of results + synchronise.  These (and asr_fbank, asr_stage_raw) use staging buffer 0 and fail while an
+ * asr_submit ticket is in flight. */
 ASR_API int asr_stage(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format);
 ASR_API int asr_run_staged(AsrEngine* e, int32_t n, int32_t want_logprobs);
 ASR_API int asr_fetch(AsrEngine* e, int32_t n, const AsrStepOut* out);
@@ -174,6 +187,80 @@ enum { ASR_PROF_FBANK = 0, ASR_PROF_GEMM_IN, ASR_PROF_LN, ASR_PROF_GEMM_QKV, ASR
 ASR_API int asr_profile_enable(AsrEngine* e, int32_t on);
 ASR_API int asr_profile_read(AsrEngine* e, double* ms, uint64_t* launches);
 
+/* ---- Native session scheduler (csrc/sched.cu): the per-connection loop of the reference server for thousands of sessions at once.
+ * Replaces, per session, Stream (streaming_decoder/stream.py: :23-26 initial zero buffer, :78-87 accept_waveform, :110-125
+ * update_stream, :127-163 endpoint_detected, :159-160 advance by segment_length, :166-189 VAD skip), the chunk loop of
+ * handle_connection_impl (streaming_server.py:367-546), the rule evaluation of online_endpoint.py:42-94 and the v1 batcher
+ * StreamingE2E.process (streaming_decoder_v1/streaming_asr.py:41-119).  Session state is struct-of-arrays owned by the library
+ * (asr_sched_arrays hands out the pointers; Python wraps them as numpy views).  A tick with the engine attached is two calls,
+ * asr_sched_submit / asr_sched_collect, with up to two ticks in flight; plan / commit / update / endpoints are the same bookkeeping
+ * without an engine (CPU tests, or a caller that interposes its own VAD or language-model cost between them). */
+typedef struct AsrScheduler AsrScheduler;
+typedef struct AsrSchedConfig {
+  int32_t capacity;          /* session rows */
+  int32_t chunk_length;      /* samples per chunk            (AudioConfig.chunk_length, utils.py:22) */
+  int32_t segment_length;    /* samples consumed per chunk   (utils.py:18, stream.py:159-160)        */
+  int32_t buffer_length;     /* leading zeros / overlap      (utils.py:20, stream.py:23)             */
+  int32_t seg_rows;          /* output frames per chunk */
+  int32_t sample_rate;
+  int32_t max_batch;         /* sessions per tick at most */
+  int32_t backlog_chunks;    /* ring capacity per session = chunk_length + backlog_chunks * segment_length samples */
+  int32_t max_tokens;        /* greedy tokens kept per utterance segment (overflow is reported, never silent) */
+  int32_t device_gather;     /* != 0: rings in pinned, device-mapped memory, the GPU gathers each tick's chunks itself */
+  double relative_cost;      /* default LM relative cost fed to the endpoint rules (utils.py:126-139; the ARPA LM is absent) */
+} AsrSchedConfig;
+typedef struct AsrSchedArrays {     /* one entry (row) per session; valid for the scheduler's lifetime */
+  int16_t* audio; int64_t audio_row_samples;
+  int64_t *rd, *wr;                 /* read / write positions inside the session's ring */
+  uint8_t *active, *inflight;
+  int32_t* slot;
+  int32_t* tok; int32_t* ntok;      /* [capacity][max_tokens] greedy tokens of the current segment */
+  int64_t *n_frames, *chunk_processed, *chunk_processed_total;
+  double* trailing;                 /* trailing_blank_duration (stream.py:122-125) */
+  uint8_t* contain_token;           /* is_contain_token (stream.py:123) */
+  int64_t *segment, *last_served;
+  double* relative_cost;            /* per session; a language model writes here before the endpoint rules run */
+  uint8_t* overflow;                /* the segment lost tokens (max_tokens) or its beam hypotheses were truncated */
+} AsrSchedArrays;
+typedef struct AsrSchedPlan {       /* the sessions of the tick being assembled (valid until the tick is collected) */
+  int32_t tick, n;
+  const int32_t *rows, *slots; const int64_t* offsets;     /* chunk i = audio[rows[i]][offsets[i] : + chunk_length] */
+  int32_t n_skipped; const int32_t* skipped;               /* VAD-gated sessions: consumed, not run */
+} AsrSchedPlan;
+typedef struct AsrSchedResult {     /* outcome of a tick; pointers valid until two more ticks were submitted */
+  int32_t n; const int32_t* rows;                          /* sessions run through the model, batch order */
+  const int32_t *n_new, *new_tokens;                       /* [n], [n * seg_rows] */
+  const uint8_t* final_flags; const int32_t* final_rule;   /* [n] an endpoint fired after this chunk / index of the rule, -1 */
+  const uint8_t* overflow;                                 /* [n] */
+  int32_t n_skipped; const int32_t* skipped;
+  int32_t n_final;                                         /* endpoints of the tick (served and skipped sessions) */
+  const int32_t *final_rows, *final_rule_of, *final_ntok, *final_tok_off; const double* final_utt; const int32_t* final_tok;
+  /* the engine's step outputs (asr_sched_collect only; pinned memory) */
+  const int32_t *argmax_ids, *blank_frames, *has_token, *has_text, *flags;
+  const int16_t* beam_tokens; const int32_t* beam_len; const float* beam_score; const float* logprobs;
+} AsrSchedResult;
+ASR_API int asr_sched_create(const AsrSchedConfig* cfg, AsrEngine* engine /* nullable */, AsrScheduler** out);
+ASR_API int asr_sched_destroy(AsrScheduler* s);
+ASR_API int asr_sched_arrays(AsrScheduler* s, AsrSchedArrays* out);
+/* Rule table in evaluation order (online_endpoint.py:4-21, asr-online.yaml:31-104); n = 0 disables endpointing. */
+ASR_API int asr_sched_set_rules(AsrScheduler* s, int32_t n, const uint8_t* must_contain_nonsilence, const double* min_trailing_silence,
+                                const double* min_utterance_length, const double* max_relative_cost);
+ASR_API int asr_sched_open(AsrScheduler* s, int32_t row, int32_t slot /* < 0: open an engine session */);
+ASR_API int asr_sched_close(AsrScheduler* s, int32_t row);
+ASR_API int asr_sched_reset_rows(AsrScheduler* s, int32_t n, const int32_t* rows);
+ASR_API int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n);      /* returns 1 when the backlog does not fit */
+ASR_API int asr_sched_ready(AsrScheduler* s, int32_t max_rows, const int32_t** rows, int32_t* n);
+/* gate_threshold >= 0: energy gate (peak of the chunk's new samples) for sessions without text in their segment; keep != NULL: the
+ * caller's own decision for the rows asr_sched_ready returned. */
+ASR_API int asr_sched_plan(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, const uint8_t* keep, AsrSchedPlan* plan);
+ASR_API int asr_sched_commit(AsrScheduler* s, int32_t tick, AsrSchedResult* res);
+ASR_API int asr_sched_update(AsrScheduler* s, int32_t tick, const AsrStepOut* out);
+ASR_API int asr_sched_endpoints(AsrScheduler* s, int32_t tick, AsrSchedResult* res);
+ASR_API int asr_sched_abort(AsrScheduler* s, int32_t tick);
+ASR_API int asr_sched_submit(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, const uint8_t* keep, int32_t want_logprobs, AsrSchedResult* res,
+                             int32_t* tick);
+ASR_API int asr_sched_collect(AsrScheduler* s, int32_t tick, int32_t run_endpoints, AsrSchedResult* res);
+
 /* ---- diagnostics used by tests (not part of the serving path) ---- */
 /* Runs the step but stops after `n_layers` encoder layers (no CTC, no state advance); buffers readable below. */
 ASR_API int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t n_layers);
@@ -182,12 +269,15 @@ ASR_API int asr_debug_read(AsrEngine* e, int32_t which, float* out, uint64_t n_f
 /* Reads the K (which=0) / V (which=1) left context of `layer` of a session in the reference's layout
  * [left_context, d] (oldest row first, zero rows where past_length < left_context) and past_length. */
 ASR_API int asr_debug_read_state(AsrEngine* e, int32_t slot, int32_t layer, int32_t which, float* out, int32_t* past_length);
-/* Stand-alone GEMM C[M,N] = A[M,K] * B[N,K]^T (+bias): impl 0 = tcgen05 kernel, 1 = CUDA-core cross-check. */
+/* Stand-alone GEMM C[M,N] = A[M,K] * B[N,K]^T (+bias) through the tcgen05 kernel (impl must be 0). */
 ASR_API int asr_debug_gemm(int32_t impl, int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, const float* A, const float* B, const float* bias,
                    float* C, int device);
 
-/* Mean milliseconds per launch of the tcgen05 GEMM on operands resident in HBM (microbenchmark; bn = 512 selects the CTA-pair
- * kernel).  epi_kind: 0 plain fp32 store, 1 bias + fp32 residual, 2 bias + GELU -> bf16. */
+/* Stand-alone act(A B^T + bias) -> bf16 operand (returned as fp32).  bn: 64 / 128 / 256 one-CTA tiles, 512 = cta_group::2 pair with the
+ * LSU epilogue, 515 = pair with the TMA-store epilogue.  act: 0 none, 1 GELU, 2 SiLU. */
+ASR_API int asr_debug_gemm_operand(int32_t M, int32_t N, int32_t K, int32_t bn, int32_t act, const float* A, const float* B, const float* bias,
+                                   float* out, int device);
+
 /* ---- Streaming convolution module with per-session cache (csrc/convmod.cu): streaming form of ConvolutionBlock
  * (lightspeech/layers/block.py:129-171: pre_norm -> pointwise_conv1 -> SiLU -> depthwise_conv(k) -> BatchNorm1d(eval) -> SiLU ->
  * pointwise_conv2).  Output = the reference block's output on the whole sequence, delayed by (kernel-1)/2 frames.  Sessions are
@@ -209,8 +299,8 @@ ASR_API int asr_debug_gemm_ln(int32_t M, int32_t K, int32_t split, const float* 
                               const float* g1, const float* b1, const float* g2, const float* b2, int32_t f32_normed, int32_t compact_rows,
                               int32_t compact_seg, float* out_f32, float* out_op_f32, int32_t iters, float* ms_out, int32_t pair, int device);
 /* Diagnostic: mean ms per launch of the tcgen05 GEMM on operands already in HBM.  bn: 64 / 128 / 256 = 1-CTA tile width, 512 = cta_group::2
- * pair (256 x 256), 513 = pair with 256 x 128 tiles and four accumulator stages, 514 = pair with the A tile resident in shared memory (epi 2
- * only).  epi_kind: 0 fp32 store, 1 + bias + fp32 residual, 2 bias + GELU -> bf16 operand, 3 none (accumulator dropped: the mainloop alone). */
+ * pair (256 x 256), 515 = pair with the TMA-store epilogue (epi 2 only).  epi_kind: 0 fp32 store, 1 + bias + fp32 residual, 2 bias + GELU ->
+ * bf16 operand, 3 none (accumulator dropped: the mainloop alone). */
 ASR_API int asr_debug_gemm_time(int32_t M, int32_t N, int32_t K, int32_t split, int32_t bn, int32_t epi_kind, int32_t iters, float* ms_out, int device);
 
 #ifdef __cplusplus

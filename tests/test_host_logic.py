@@ -105,10 +105,12 @@ def test_ids_to_text_matches_reference_rules():
 
 # ------------------------------------------------------------------------------------------------ scheduler (fake engine)
 class FakeEngine:
-    """Stands in for Engine on the CPU: records every step's (slots, pcm) and emits one deterministic token per chunk."""
+    """Stands in for Engine on the CPU with the interface the scheduler drives (open / close / reset_sessions / set_silent_ids / submit /
+    collect): records every step's (slots, pcm) and emits one deterministic token per chunk."""
 
     def __init__(self, cfg):
         self.cfg, self.calls, self._next, self.open_slots, self.resets = cfg, [], 0, set(), []
+        self.tickets, self.busy, self.silent = {}, set(), None
 
     def open_session(self):
         s = self._next
@@ -119,8 +121,11 @@ class FakeEngine:
     def close_session(self, s):
         self.open_slots.remove(s)
 
-    def reset_session(self, s):
-        self.resets.append(s)
+    def reset_sessions(self, slots):
+        self.resets.extend(int(s) for s in slots)
+
+    def set_silent_ids(self, ids):
+        self.silent = set(int(i) for i in ids)
 
     def step(self, slots, pcm, want_logprobs=False):
         slots = list(slots)
@@ -130,6 +135,21 @@ class FakeEngine:
         n, S = len(slots), self.cfg.seg_rows
         new = [np.array([2 + (int(pcm[i, -1]) % 7)], np.int32) for i in range(n)]
         return A.StepResult(np.zeros((n, S), np.int32), new, np.full(n, 3, np.int32), np.ones(n, bool), None)
+
+    # pipelined form (results computed at submit, delivered at collect), at most two tickets in flight
+    def submit(self, slots, pcm, want_logprobs=False):
+        slots = [int(x) for x in slots]
+        assert len(self.tickets) < 2, "more than two steps in flight"
+        assert not (self.busy & set(slots)), "a session was submitted again before its previous chunk was collected"
+        self.busy |= set(slots)
+        t = len(self.calls)
+        self.tickets[t] = (slots, self.step(slots, pcm, want_logprobs))
+        return t
+
+    def collect(self, t):
+        slots, out = self.tickets.pop(t)
+        self.busy -= set(slots)
+        return out
 
 
 def test_scheduler_ragged_batching_and_buffer_semantics():
@@ -245,13 +265,6 @@ def test_endpoint_rules_match_live_reference():
 class TokenEngine(FakeEngine):
     """Fake engine whose chunk decodes to a token iff the chunk's last sample is positive; blank frames = 16 - (sample % 17)."""
 
-    def reset_sessions(self, slots):
-        self.resets.extend(int(s) for s in slots)
-
-    def gather_pcm(self, audio, rows, offsets):
-        L = self.cfg.chunk_length
-        return np.stack([audio[r, o:o + L] for r, o in zip(rows, offsets)]) if len(rows) else np.zeros((0, L), np.int16)
-
     def __init__(self, cfg):
         super().__init__(cfg)
         self.frames = {}
@@ -354,28 +367,6 @@ def test_scheduler_vectorised_gate_and_backlog_compaction():
             b.accept_waveform(quiet)
 
 
-class PipelinedTokenEngine(TokenEngine):
-    """TokenEngine + submit/collect (results computed at submit, delivered at collect), at most two tickets in flight."""
-
-    def __init__(self, cfg):
-        super().__init__(cfg)
-        self.tickets, self.busy = {}, set()
-
-    def submit(self, slots, pcm, want_logprobs=False):
-        slots = [int(x) for x in slots]
-        assert len(self.tickets) < 2, "more than two steps in flight"
-        assert not (self.busy & set(slots)), "a session was submitted again before its previous chunk was collected"
-        self.busy |= set(slots)
-        t = len(self.calls)
-        self.tickets[t] = (slots, self.step(slots, pcm, want_logprobs))
-        return t
-
-    def collect(self, t):
-        slots, out = self.tickets.pop(t)
-        self.busy -= set(slots)
-        return out
-
-
 def test_pipelined_ticks_equal_synchronous_ticks():
     """Two ticks in flight with a backlog larger than max_batch: per session the decoded tokens, endpoints and counters must be
     exactly those of synchronous ticking, and no session may ride two in-flight steps."""
@@ -388,7 +379,7 @@ def test_pipelined_ticks_equal_synchronous_ticks():
     audio[:, cfg.segment_length - 1::cfg.segment_length] = lasts
 
     def run(pipelined):
-        eng = PipelinedTokenEngine(cfg)
+        eng = TokenEngine(cfg)
         sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules(), backlog_chunks=n_chunks + 1)
         ss = [sch.open() for _ in range(n_sess)]
         for i, s in enumerate(ss):
@@ -546,3 +537,182 @@ def test_weights_from_checkpoint_reads_the_reference_layout(tmp_path, oracle_wei
         d.load_state_dict(dec, strict=True)
         torch.save({"hyper_parameters": {}, "state_dict": {"encoder": e.state_dict(), "decoder": d.state_dict()}}, path)
         assert np.array_equal(A.weights_from_checkpoint(str(path), A.ModelConfig()), blob)
+
+
+# ------------------------------------------------------------------------------------------------ update_stream / endpoint goldens of the live reference
+class ScriptedIdsEngine(FakeEngine):
+    """Replays per-frame argmax ids through the bookkeeping ctc_greedy_kernel does on the device (layers.cu): unique_consecutive +
+    blank drop with a carry across chunks, last frame with id > 1, and `has_text` = an id outside the silent set was seen."""
+
+    def __init__(self, cfg, scripts):
+        super().__init__(cfg)
+        self.scripts, self.pos, self.carry = scripts, {}, {}
+
+    def reset_sessions(self, slots):
+        super().reset_sessions(slots)
+        for s in slots:
+            self.carry.pop(int(s), None)
+
+    def step(self, slots, pcm, want_logprobs=False):
+        slots = [int(s) for s in slots]
+        self.calls.append((slots, pcm.copy()))
+        n, S = len(slots), self.cfg.seg_rows
+        nnew, newtok = np.zeros(n, np.int32), np.zeros((n, S), np.int32)
+        blank, has, text = np.zeros(n, np.int32), np.zeros(n, bool), np.zeros(n, bool)
+        for i, s in enumerate(slots):
+            k = self.pos.get(s, 0)
+            self.pos[s] = k + 1
+            c = self.carry.setdefault(s, dict(prev=-1, nf=0, lt=-1, ht=False))
+            for tid in self.scripts[s][k]:
+                if tid != c["prev"] and tid != 0:
+                    newtok[i, nnew[i]] = tid
+                    nnew[i] += 1
+                if tid > 1:
+                    c["lt"] = c["nf"]
+                c["ht"] |= tid not in self.silent
+                c["prev"] = tid
+                c["nf"] += 1
+            has[i], text[i] = c["lt"] >= 0, c["ht"]
+            blank[i] = c["nf"] - 1 - c["lt"] if has[i] else c["nf"]
+        return A.StepResult(np.zeros((n, S), np.int32), None, blank, has, None, n_new=nnew, new_tokens_padded=newtok, has_text=text)
+
+
+def test_update_stream_and_endpoints_match_live_reference_goldens():
+    """tests/golden/stream_update.json (oracle/make_stream_goldens.py: the unmodified greedy_search + Stream.update_stream +
+    Stream.endpoint_detected) vs the native scheduler: segments whose only tokens are '<<' / '>>' have an id > 1 but empty text, so
+    trailing_blank_duration keeps growing by 0.64 and is_contain_token stays False (stream.py:121-125)."""
+    import json
+    import os
+    from asr_streaming_b200.endpoint import EndpointRules
+    from asr_streaming_b200.recognition import silent_ids
+    with open(os.path.join(os.path.dirname(__file__), "golden", "stream_update.json")) as f:
+        G = json.load(f)
+    vocab = ["-", "|"] + [f"t{i}" for i in range(2, G["vocab_size"])]
+    vocab[792], vocab[793] = "<<", ">>"
+    assert silent_ids(vocab) == G["silent_ids"]
+    cfg = A.ModelConfig(max_batch=8, max_sessions=8)
+    names = list(G["cases"])
+    eng = ScriptedIdsEngine(cfg, {i: [r["ids"] for r in G["cases"][nm]] for i, nm in enumerate(names)})
+    sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules(), vocab=vocab)
+    ss = [sch.open() for _ in names]
+    assert [s.slot for s in ss] == list(range(len(names)))
+    for k in range(max(len(G["cases"][nm]) for nm in names)):
+        live = [s for s, nm in zip(ss, names) if k < len(G["cases"][nm])]
+        for s in live:
+            s.accept_waveform(np.ones(cfg.segment_length, np.int16))
+        res = sch.tick()
+        assert len(res) == len(live)
+        for j, s in enumerate(res.sessions):
+            g = G["cases"][names[ss.index(s)]][k]
+            assert bool(res.final[j]) == g["detected"], (names[ss.index(s)], k)
+            assert abs(s.trailing_blank_duration - g["trailing_after"]) < 1e-9, (names[ss.index(s)], k, s.trailing_blank_duration, g)
+            assert s.segment == g["segment"]
+            if not g["detected"]:
+                assert s.is_contain_token == g["contain"] and s.chunk_processed == g["chunk_processed"]
+            else:
+                assert abs(res.final_utt_length[s.id] - g["utt"]) < 1e-9
+
+
+def test_token_overflow_is_reported_not_silent():
+    """A segment longer than MAX_TOKENS: the tick says so (TickResult.overflow) instead of overwriting the last token."""
+    from asr_streaming_b200.scheduler import MAX_TOKENS
+    cfg = A.ModelConfig(max_batch=2, max_sessions=2)
+    S = cfg.seg_rows
+    n_chunks = MAX_TOKENS // S + 2
+    script = [[2 + (k * S + i) % 700 for i in range(S)] for k in range(n_chunks)]           # 16 distinct tokens per chunk, never blank
+    eng = ScriptedIdsEngine(cfg, {0: script})
+    sch = A.SessionScheduler(eng)                                                              # no endpoint rules: the segment never ends
+    s = sch.open()
+    seen = []
+    for k in range(n_chunks):
+        s.accept_waveform(np.ones(cfg.segment_length, np.int16))
+        res = sch.tick()
+        seen.append(bool(res.overflow[0]))
+    assert seen[:MAX_TOKENS // S] == [False] * (MAX_TOKENS // S) and all(seen[MAX_TOKENS // S:])
+    assert len(s.tokens) == MAX_TOKENS and s.tokens == [t for ch in script for t in ch][:MAX_TOKENS]
+    sch.reset(s)
+    s.accept_waveform(np.ones(cfg.segment_length, np.int16))
+    eng.pos[0] = 0
+    assert not sch.tick().overflow[0]
+
+
+def test_failed_step_releases_its_sessions_and_nothing_is_applied_before_submit():
+    cfg = A.ModelConfig(max_batch=4, max_sessions=4)
+
+    class Flaky(FakeEngine):
+        fail_submit = fail_collect = False
+
+        def submit(self, slots, pcm, want_logprobs=False):
+            if self.fail_submit:
+                raise RuntimeError("submit failed")
+            return super().submit(slots, pcm, want_logprobs)
+
+        def collect(self, t):
+            out = super().collect(t)
+            if self.fail_collect:
+                raise RuntimeError("device fault")
+            return out
+    eng = Flaky(cfg)
+    sch = A.SessionScheduler(eng)
+    a, b = sch.open(), sch.open()
+    for s in (a, b):
+        s.accept_waveform(np.ones(cfg.segment_length * 2, np.int16))
+    b.accept_waveform(np.zeros(1, np.int16))
+    eng.fail_submit = True
+    with pytest.raises(RuntimeError):
+        sch.tick(gate=lambda sess, chunk: sess is a)                 # b would be VAD-skipped: must not be applied when the submit fails
+    assert a.chunk_processed == 0 and b.chunk_processed == 0 and b.trailing_blank_duration == 0.0 and not sch.inflight.any()
+    assert a.length_of_segment == cfg.buffer_length + 2 * cfg.segment_length
+    eng.fail_submit, eng.fail_collect = False, True
+    with pytest.raises(RuntimeError):
+        sch.tick()
+    assert not sch.inflight.any()                                    # the sessions of the lost step are eligible again
+    eng.fail_collect = False
+    assert len(sch.tick()) == 2
+    sch.close(a)                                                     # close / reset no longer raise forever
+
+
+def test_relative_cost_callback_reaches_the_rules():
+    """rule1.2 (trailing silence >= 0.9 s, relative cost < 8) can only fire when a language model supplies the cost (utils.py:126-139)."""
+    from asr_streaming_b200.endpoint import EndpointRules
+    cfg = A.ModelConfig(max_batch=2, max_sessions=2)
+    script = [[5] + [0] * 15, [0] * 16, [0] * 16]                    # token at frame 0: last_blank 0.6, 1.24 after the next chunk
+    fired = {}
+    for cost in (10.0, 3.0):
+        eng = ScriptedIdsEngine(cfg, {0: [[5] + [0] * 9 + [0] * 6, [0] * 7 + [0] * 9, [0] * 16]})
+        sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules(), cost_fn=lambda sc, rows, c=cost: np.full(len(rows), c))
+        s = sch.open()
+        out = []
+        for k in range(2):
+            s.accept_waveform(np.ones(cfg.segment_length, np.int16))
+            res = sch.tick()
+            out.append(res.final_rule[0])
+        fired[cost] = out
+    # chunk 0: last_blank = 15 frames = 0.6 s: no rule.  chunk 1: 31 frames = 1.24 s >= 1.0: rule1.1 for any cost
+    assert fired[10.0] == [None, "rule1.1"] and fired[3.0] == [None, "rule1.1"]
+    for cost, want in ((10.0, None), (3.0, "rule1.3")):              # 0.84 s of trailing silence: only cost < 5 ends the utterance (rule1.3: >= 0.8 s)
+        eng = ScriptedIdsEngine(cfg, {0: [[0] * 10 + [5] + [0] * 5, [0] * 16]})
+        sch = A.SessionScheduler(eng, endpoint_rules=EndpointRules(), cost_fn=lambda sc, rows, c=cost: np.full(len(rows), c))
+        s = sch.open()
+        for k in range(2):
+            s.accept_waveform(np.ones(cfg.segment_length, np.int16))
+            res = sch.tick()
+        assert res.final_rule[0] == want, (cost, res.final_rule, s.trailing_blank_duration)
+
+
+def test_step_less_ticks_do_not_consume_a_pipeline_slot():
+    """A tick whose ready sessions were all VAD-skipped has nothing to collect: it must not use up one of the two in-flight slots."""
+    cfg = A.ModelConfig(max_batch=1, max_sessions=4)
+    eng = FakeEngine(cfg)
+    sch = A.SessionScheduler(eng)
+    a, b, c = sch.open(), sch.open(), sch.open()
+    loud, quiet = np.full(cfg.segment_length, 900, np.int16), np.zeros(cfg.segment_length, np.int16)
+    a.accept_waveform(loud); b.accept_waveform(quiet); c.accept_waveform(loud)
+    gate = lambda sess, chunk: bool(np.abs(chunk).max() > 0)
+    p1 = sch.submit_tick(gate=gate)                                  # a runs (max_batch 1)
+    p2 = sch.submit_tick(gate=gate)                                  # b: skipped only
+    assert [s.id for s in p1.res.sessions] == [a.id] and p2.rows.size == 0 and [s.id for s in p2.res.skipped] == [b.id]
+    p3 = sch.submit_tick(gate=gate)                                  # c runs: second slot, while p1 is still in flight
+    assert [s.id for s in p3.res.sessions] == [c.id]
+    assert len(sch.collect_tick(p1)) == 1 and len(sch.collect_tick(p2)) == 0 and len(sch.collect_tick(p3)) == 1
+    assert b.chunk_processed == 1 and abs(b.trailing_blank_duration - 0.64) < 1e-9 and not sch.inflight.any()

@@ -278,7 +278,7 @@ def test_prefix_beam_kernel_matches_oracle(packed_weights, golden):
             states[0] = B.BeamState()
         r = e.step([slots[i] for i in idx], np.stack([chunks[i][tick] for i in idx]), want_logprobs=True)
         for j, i in enumerate(idx):
-            states[i] = B.beam_step(states[i], r.logprobs[j].astype(np.float64), beam=10, cand_k=8, max_len=255)
+            states[i] = B.beam_step(states[i], r.logprobs[j].astype(np.float64), beam=10, cand_k=8, max_len=1023)
             pre, score = B.best(states[i])
             assert list(r.beam_tokens[j]) == pre, f"{names[i]} tick {tick}"
             assert abs(float(r.beam_score[j]) - score) < 1e-3 * max(1.0, abs(score))
@@ -327,7 +327,7 @@ def test_scheduler_ticks_match_reference_texts(engines, golden, meta, device_gat
     e = engines(engines.EXACT)
     names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale", "edge_dc"]
     cases = [golden(n) for n in names]
-    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, device_gather=device_gather)   # device: asr_submit_rings reads the pinned rings
+    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, device_gather=device_gather, vocab=meta["vocab"])   # device: the GPU gathers out of pinned rings
     rng = np.random.default_rng(5)
     sess = [sch.open() for _ in names]
     pos = [0] * len(names)
@@ -349,8 +349,9 @@ def test_scheduler_ticks_match_reference_texts(engines, golden, meta, device_gat
             i = sess.index(s)
             mc = meta["cases"][names[i]]
             j = done_chunks[i]
-            assert ids_to_text(s.tokens, meta["vocab"]) == mc["texts"][j], (names[i], j)
-            assert abs(s.trailing_blank_duration - (cases[i]["last_blank"][j] if s.tokens else 0.64 * (j + 1))) < 1e-6
+            text = ids_to_text(s.tokens, meta["vocab"])
+            assert text == mc["texts"][j], (names[i], j)
+            assert abs(s.trailing_blank_duration - (cases[i]["last_blank"][j] if text else 0.64 * (j + 1))) < 1e-6      # stream.py:121-125
             done_chunks[i] += 1
         if all(p >= c["pcm"].size for p, c in zip(pos, cases)) and not sch.ready_rows().size:
             break
@@ -479,20 +480,29 @@ def test_fused_feed_forward_kernel_is_bit_identical(packed_weights, golden, meta
     assert np.abs(em - case["emission"]).max() < FAST_TOL
 
 
-def test_a_resident_pair_gemm_is_bit_identical(packed_weights, monkeypatch):
-    """QKV and FFN1 at large batches through the A-resident cta_group::2 kernel (the 128 x 512 A tile stays in shared memory while
-    the unit's N tiles stream only B) against the streaming pair kernel: same MMA shapes and k order => bit-identical log-probs.
-    700 streams = 55 row blocks (the last one ragged), 110 units on 74 pairs: units of different blocks follow each other in a pair."""
+@pytest.mark.parametrize("low_latency", [False, True], ids=["chunk16", "chunk8"])
+def test_tma_store_gemms_are_bit_identical(packed_weights, monkeypatch, low_latency):
+    """QKV (stream-tiled M tiles, every destination a TMA box: q, the session's K/V ring block, the right-context scratch), FFN1 and
+    CTC1 (row tiles, one box per warp) through the TMA-store epilogues against the LSU epilogues (ASR_B200_NO_TMA_STORE=1): same MMA
+    shapes, k order and epilogue arithmetic => bit-identical log-probs over chained steps (the K/V ring wraps, sessions at mixed
+    progress after a partial reset).  700 / 1100 streams: the last segment tile / right-context tile of each kind is ragged."""
     from asr_streaming_b200 import Engine, PRECISION_FAST
     rng = np.random.default_rng(43)
-    n = 700
-    pcm = rng.integers(-4000, 4000, size=(3, n, O.CANONICAL.chunk_length)).astype(np.int16)
+    n = 1100 if low_latency else 700                                       # enough 256-row tiles for the cta_group::2 kernels
+    geo = O.LOW_LATENCY if low_latency else O.CANONICAL
+    pcm = rng.integers(-4000, 4000, size=(5, n, geo.chunk_length)).astype(np.int16)
     outs = []
-    for resident in (False, True):
-        monkeypatch.setenv("ASR_B200_PAIR_A", "1" if resident else "0")
-        with Engine(model_cfg(PRECISION_FAST, max_batch=n, max_sessions=n), packed_weights) as e:
-            sl = [e.open_session() for _ in range(n)]
-            outs.append(np.stack([e.step(sl, pcm[t], want_logprobs=True).logprobs for t in range(3)]))
+    for tma in (False, True):
+        monkeypatch.setenv("ASR_B200_NO_TMA_STORE", "0" if tma else "1")
+        with Engine(model_cfg(PRECISION_FAST, low_latency=low_latency, max_batch=n, max_sessions=n + 8), packed_weights) as e:
+            sl = [e.open_session() for _ in range(n + 8)][8:]              # slots != batch positions
+            got = []
+            for t in range(5):
+                if t == 2:
+                    e.reset_sessions(sl[50:120])
+                k = n if t != 3 else 333                                   # a smaller, ragged batch in between
+                got.append(e.step(sl[:k], pcm[t, :k], want_logprobs=True).logprobs[:333])
+            outs.append(np.stack(got))
     assert np.isfinite(outs[1]).all()
     assert np.array_equal(outs[0], outs[1])
 

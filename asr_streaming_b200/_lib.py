@@ -117,6 +117,7 @@ SIGNATURES = {
     "asr_sched_close": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_sched_reset_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "asr_sched_accept": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "asr_sched_accept_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "asr_sched_ready": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "asr_sched_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(AsrSchedPlanC)]),
     "asr_sched_commit": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(AsrSchedResultC)]),

@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <mutex>
 #include <numeric>
+#include <stdlib.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/asr_b200.h"
@@ -320,10 +322,9 @@ int asr_sched_reset_rows(AsrScheduler* s, int32_t n, const int32_t* rows) {
   return 0;
 }
 
-/* stream.py:78-87: append int16 samples (messages of <= 100 samples are dropped); the unread tail moves to the front when the ring is full. */
-int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
-  if (!s || (n > 0 && !pcm)) { set_error("null argument"); return -1; }
-  std::lock_guard<std::mutex> lk(s->mu);
+namespace {
+// stream.py:78-87 for one session (lock held): messages of <= 100 samples are dropped; the unread tail moves to the front when the ring is full
+int accept_locked(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
   if (check_row(s, row)) return -1;
   if (n <= 100) return 0;
   int16_t* a = s->audio + (size_t)row * s->CAP;
@@ -336,6 +337,41 @@ int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n
   }
   memcpy(a + s->wr[row], pcm, sizeof(int16_t) * (size_t)n);
   s->wr[row] += n;
+  return 0;
+}
+}  // namespace
+
+/* stream.py:78-87: append int16 samples (messages of <= 100 samples are dropped); returns 1 when the backlog does not fit. */
+int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
+  if (!s || (n > 0 && !pcm)) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(s->mu);
+  return accept_locked(s, row, pcm, n);
+}
+
+/* The same for many sessions at once: block[i * samples .. + samples) is appended to session rows[i]. */
+int asr_sched_accept_block(AsrScheduler* s, int32_t n, const int32_t* rows, const int16_t* block, int64_t samples) {
+  if (!s || (n > 0 && (!rows || !block))) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int i = 0; i < n; ++i) {                             // validate first: the parallel part below cannot fail half way
+    if (check_row(s, rows[i])) return -1;
+    if (samples > 100 && s->wr[rows[i]] - s->rd[rows[i]] + samples > s->CAP) {
+      set_error("session row %d: backlog of %lld samples exceeds the %d-sample buffer", rows[i], (long long)(s->wr[rows[i]] - s->rd[rows[i]] + samples), s->CAP);
+      return 1;
+    }
+  }
+  static const int env_cap = [] { const char* v = getenv("ASR_B200_HOST_THREADS"); return v ? std::max(1, atoi(v)) : 8; }();
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nt = std::max(1, std::min({8, env_cap, hw > 0 ? hw : 1, n / 64 + 1}));
+  std::vector<int> rcs(nt, 0);
+  std::vector<std::thread> th;
+  auto work = [&](int t) {
+    for (int i = (int)((long long)n * t / nt); i < (int)((long long)n * (t + 1) / nt); ++i)
+      if (int rc = accept_locked(s, rows[i], block + (size_t)i * samples, samples)) { rcs[t] = rc; return; }
+  };
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  for (int rc : rcs) if (rc) return rc;
   return 0;
 }
 

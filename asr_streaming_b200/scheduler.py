@@ -330,17 +330,14 @@ class SessionScheduler:
         _lib.check(self.lib, rc, "asr_sched_accept")
 
     def accept_block(self, rows: np.ndarray, block: np.ndarray) -> None:
-        """Bulk ingest: ``block[i]`` (int16, equal lengths) is appended to session row ``rows[i]`` (no compaction: must fit)."""
-        rows = np.asarray(rows, np.int64)
-        block = np.asarray(block)
+        """Bulk ingest: ``block[i]`` (int16, equal lengths) is appended to session row ``rows[i]`` with accept()'s semantics, in one native call."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        block = np.ascontiguousarray(block)
         assert block.dtype == np.int16 and block.ndim == 2 and block.shape[0] == rows.size
-        n = block.shape[1]
-        if (self.wr[rows] + n > self.CAP).any():
-            raise BufferError(f"accept_block: {n} samples do not fit behind the write pointer of every session (CAP {self.CAP})")
-        for w in np.unique(self.wr[rows]):
-            m = self.wr[rows] == w
-            self.audio[rows[m], w:w + n] = block[m]
-        self.wr[rows] += n
+        rc = self.lib.asr_sched_accept_block(self._h, int(rows.size), rows.ctypes.data, block.ctypes.data, int(block.shape[1]))
+        if rc == 1:
+            raise BufferError((self.lib.asr_last_error() or b"").decode("utf-8", "replace"))
+        _lib.check(self.lib, rc, "asr_sched_accept_block")
 
     # ------------------------------------------------------------------ the tick
     def ready_rows(self, max_rows: Optional[int] = None) -> np.ndarray:

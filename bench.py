@@ -41,6 +41,8 @@ WORKLOADS = {
     "realtime": (10240, "north-star operating point: N real-time 16 kHz streams (default 10,240; --streams N) delivering 640 ms of audio every 640 ms "
                         "at random phases, served by SessionScheduler ticks (two in flight, greedy CTC); reports per-chunk latency p50 / p99"),
     "lowlat4096": (4096, "configs[4] per-GPU share: 4096 concurrent streams per GPU, chunk_size=8 low-latency mode (320 ms chunks), greedy CTC"),
+    "longform": (4096, "configs[4] long form: 4096 concurrent streams per GPU (32k on 8 GPUs), chunk_size=8 low-latency mode, 10 minutes of audio per stream "
+                       "(1875 chunks of 320 ms; --long-chunks), SessionScheduler with two ticks in flight, energy-gate VAD, endpoint rules (forced rule4 endpoints at 40 s)"),
 }
 FLOP_PER_STREAM_CHUNK = 2_583_363_584          # SURVEY.md §8a (L_valid = 32)
 
@@ -355,6 +357,286 @@ def run_realtime(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------ rooflines per kernel family
+def ncu_traffic_table():
+    """dram bytes per launch per kernel family from the committed ncu --set full captures (profiles/r02_roofline_traffic.json)."""
+    for name in ("r02_roofline_traffic.json", "r01_roofline_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+                d["_file"] = name
+                return d
+        except (OSError, ValueError):
+            continue
+    return {}
+
+
+def family_rooflines(fam, cfg, streams, precision_exact, pk, workload):
+    """Per kernel family: algorithmic FLOPs (tensor-bound GEMMs) or algorithmic HBM bytes (memory-bound kernels) per launch divided by the
+    mean launch time measured live with CUDA events on the engine stream (asr_profile_*), against the measured peaks.  The per-unit
+    figures are DESIGN.md section 4's: M = rows * streams GEMM rows; attention reads each stream's left-context K and V ring rows + q and
+    writes its rows of the out_proj operand; fbank reads the int16 chunk and writes the bf16 operand."""
+    M, d, f, V = streams * cfg.rows, cfg.d_model, cfg.ffn_dim, cfg.vocab
+    esz = 4 if precision_exact else 2                   # bytes per K/V / q element (EXACT: pre-split hi|lo bf16 rows, fp32 q)
+    traffic = ncu_traffic_table().get(workload, {})
+    tens = {"gemm_qkv": 2 * M * 3 * d * d, "gemm_out_proj": 2 * M * d * d, "gemm_ffn1": 2 * M * f * d, "gemm_ffn2": 2 * M * d * f,
+            "gemm_input_linear": 2 * streams * cfg.frames * (d // cfg.stride) * cfg.n_mels,
+            "gemm_ctc1": 2 * streams * cfg.seg_rows * d * cfg.ctc_hidden, "gemm_ctc2": 2 * streams * cfg.seg_rows * cfg.ctc_hidden * V}
+    # attention: the left-context K and V rows of every stream (written a step ago: 8 GB of rings never survive in L2) + q in + out_proj operand
+    # out; the segment / right-context K and V rows come straight from the QKV kernel before it and are not counted (SURVEY section 8d)
+    hbm = {"attention": streams * (2 * cfg.left_context * d * esz + cfg.rows * d * esz + cfg.rows * d * (4 if precision_exact else 2)),
+           "fbank": streams * (cfg.chunk_length * 2 + cfg.frames * cfg.n_mels * (4 if precision_exact else 2)),
+           "layernorm": M * d * (4 + esz), "ctc_greedy": streams * cfg.seg_rows * V * 4,
+           "beam": streams * cfg.seg_rows * V * 4}
+    out = {}
+    for k, v in fam.items():
+        if not v["launches_per_step"]:
+            continue
+        t = v["ms_per_step"] / v["launches_per_step"] / 1e3
+        if k in tens:
+            ach = tens[k] / t / 1e12
+            out[k] = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                      "us_per_launch": 1e6 * t, "traffic": traffic.get(k), "executed_flops_multiplier": 3 if precision_exact else 1}
+        elif k in hbm:
+            ach = hbm[k] / t / 1e9
+            out[k] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "us_per_launch": 1e6 * t,
+                      "traffic": traffic.get(k), "algorithmic_bytes_per_launch": hbm[k]}
+    return out
+
+
+def device_leg(local, blob, streams, precision, low_latency, steps, warmup, beam=0):
+    """Device-resident throughput of `streams` steady-state streams per step on a fresh engine: W warm-up + K timed steps, CUDA events on
+    the engine stream, then the per-family profile.  Returns (audio-s/s, ms/step, families, cfg, launches)."""
+    import torch
+    from asr_streaming_b200 import Engine, ModelConfig
+    cfg = ModelConfig(precision=precision, max_batch=streams, max_sessions=streams, segment_size=32 if low_latency else 64)
+    eng = Engine(cfg, blob, local)
+    try:
+        if beam:
+            eng.set_beam(beam, 8)
+        ext = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
+        sl = [eng.open_session() for _ in range(streams)]
+        eng.stage(sl, synth_pcm(streams, cfg.chunk_length))
+        for _ in range(max(warmup, 3)):
+            eng.run_staged(streams)
+        eng.sync()
+        l0 = eng.stats()["kernel_launches"]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ext)
+        for _ in range(steps):
+            eng.run_staged(streams)
+        b.record(ext)
+        eng.sync()
+        ms = a.elapsed_time(b) / steps
+        launches = eng.stats()["kernel_launches"] - l0
+        eng.profile_enable(True)
+        ps = min(steps, 3)
+        for _ in range(ps):
+            eng.run_staged(streams)
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        fam = {k: {"ms_per_step": v[0] / ps, "launches_per_step": v[1] / ps} for k, v in prof.items() if v[1]}
+        return streams * (cfg.segment_length / cfg.sample_rate) / (ms / 1e3), ms, fam, cfg, launches
+    finally:
+        eng.close()
+
+
+def fbank_cpu_baseline(threads: int, sample_streams: int = 64):
+    """BASELINE.md section 3, configs[1]: the reference's own front-ends on the host — extract_filterbank (audio.py:9-30: MelSpectrogram
+    rebuilt every call, as there) and torchaudio.compliance.kaldi.fbank(num_mel_bins=80, dither=0) — batch 1 per stream, 640 ms each."""
+    import torch
+    import torchaudio
+    torch.set_num_threads(threads)
+    pcm = synth_pcm(sample_streams, 10240 + 240).astype(np.float32)
+    x = [torch.from_numpy(pcm[i])[None] for i in range(sample_streams)]
+
+    def kaldi():
+        for xi in x:
+            torchaudio.compliance.kaldi.fbank(xi, num_mel_bins=80, dither=0.0, sample_frequency=16000.0)
+
+    def melspec():
+        for xi in x:
+            tr = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=800, win_length=400, hop_length=160, n_mels=128, center=False)
+            torch.transpose(tr(xi / 32768.0).clamp(1e-5).log(), 2, 1)
+    out = {}
+    for name, fn in (("kaldi80", kaldi), ("melspec128", melspec)):
+        fn()
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 3.0:
+            fn()
+            reps += 1
+        out[name] = reps * sample_streams * 0.64 / (time.perf_counter() - t0)
+    return out
+
+
+def fbank_leg(local, blob, pk, streams=1024, steps=50):
+    """BASELINE configs[1]: 80-bin Kaldi fbank of 1024 streams x 640 ms (10,240 new samples + 240 of framing history), PCM resident in HBM."""
+    import torch
+    from asr_streaming_b200 import Engine, ModelConfig, PRECISION_FAST
+    cfg = ModelConfig(precision=PRECISION_FAST, max_batch=streams, max_sessions=streams)
+    eng = Engine(cfg, blob, local)
+    try:
+        ext = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
+        n_samples = 10240 + 240
+        pcm = synth_pcm(streams, n_samples)
+        eng.stage_raw(pcm)
+        for _ in range(5):
+            eng.fbank_staged(1, streams, 0, n_samples)
+        eng.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ext)
+        for _ in range(steps):
+            eng.fbank_staged(1, streams, 0, n_samples)
+        b.record(ext)
+        eng.sync()
+        us = 1e3 * a.elapsed_time(b) / steps
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.fbank(pcm, kind=1)
+        e2e = 10 * streams * 0.64 / (time.perf_counter() - t0)
+        alg = pcm.nbytes + streams * 64 * 80 * 4
+        ach = alg / (us / 1e6) / 1e9
+        traffic = ncu_traffic_table().get("fbank1024", {}).get("fbank")
+        return {"workload": WORKLOADS["fbank1024"][1], "value": streams * 0.64 / (us / 1e6), "unit": "audio-s/s", "us_per_launch": us,
+                "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": streams * 64 * 80 * 4},
+                "roofline": {"kernel": "fbank_kernel<256,int16,kaldi>", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                             "traffic": traffic, "algorithmic_bytes_per_launch": alg, "peak_source": pk["source"]}}
+    finally:
+        eng.close()
+
+
+def run_longform(args):
+    """BASELINE configs[4], long form.  Every stream delivers `--long-chunks` chunks of 320 ms (default 1875 = 10 minutes); the timed region is
+    the whole run through the public API (ready scan -> gate -> gather -> H2D -> kernels -> D2H -> bookkeeping -> endpoint rules), audio
+    arriving from host memory pass by pass.  `value` is the device-resident low-latency step for the same stream count."""
+    import torch
+    from asr_streaming_b200 import Engine, ModelConfig, PRECISION_FAST, SessionScheduler, pack_weights, random_weights
+    from asr_streaming_b200.endpoint import EndpointRules
+    from asr_streaming_b200.scheduler import native_energy_gate
+    rank, world, local = dist_env()
+    if world > 1:
+        os.environ.setdefault("ASR_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 8) // world)))
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    n = args.streams or WORKLOADS["longform"][0]
+    chunks = args.long_chunks
+    pk = peaks()
+    cfg0 = ModelConfig(segment_size=32)
+    blob = pack_weights(random_weights(WEIGHT_SEED, cfg0), cfg0)
+    value, ms_step, fam, cfg, _ = device_leg(local, blob, n, PRECISION_FAST, True, 10, 3)
+    eng = Engine(ModelConfig(precision=PRECISION_FAST, max_batch=n, max_sessions=n, segment_size=32), blob, local)
+    dev_gather = world > 1 and (os.cpu_count() or 8) // world < 8
+    sch = SessionScheduler(eng, capacity=n, backlog_chunks=3, endpoint_rules=EndpointRules(), device_gather=dev_gather)
+    for _ in range(n):
+        sch.open()
+    seg = cfg.segment_length
+    P = 64
+    pool = synth_pcm(32, P * seg + seg, first_id=rank * 32)
+    rng = np.random.Generator(np.random.PCG64(5 + rank))
+    speech = rng.random((n, P)) < 0.8                          # periodic speech / silence pattern (P chunks), sticky
+    for k in range(1, P):
+        speech[:, k] = np.where(rng.random(n) < 0.85, speech[:, k - 1], speech[:, k])
+    src = np.arange(n) % 32                                    # 32 distinct audio sources fanned out over the streams
+    shift = rng.integers(0, seg, size=32)
+    rows = np.arange(n)
+    # what "arrives" every 320 ms, prepared up front for one period of the pattern (the websocket receive path is not the measured path;
+    # handing a block to the scheduler — asr_sched_accept_block: ring compaction + copy — is, and it is timed)
+    blocks = []
+    for kk in range(min(P, chunks)):
+        base = np.stack([pool[j, shift[j] + kk * seg: shift[j] + kk * seg + seg] for j in range(32)])
+        block = base[src]
+        block[~speech[:, kk]] = 0
+        blocks.append(block)
+    gate = native_energy_gate()
+    lat = []
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    def run(n_chunks, timed):
+        prev, done, ends, skips = None, 0, 0, 0
+        for k in range(n_chunks):
+            sch.accept_block(rows, blocks[k % len(blocks)])
+            while True:
+                t0 = time.perf_counter()
+                p = sch.submit_tick(gate=gate, max_rows=n // 2)
+                if prev is not None:
+                    res = sch.collect_tick(prev[0])
+                    if timed:
+                        lat.append(1e3 * (time.perf_counter() - prev[1]))
+                    done += len(res)
+                    ends += len(res.final_tokens)
+                    prev = None
+                skips += int(p.res.skipped_rows.size)
+                ends += len(p.res.final_tokens) if not p.rows.size else 0
+                if p.rows.size:
+                    prev = (p, t0)
+                elif not sch.ready_rows().size:
+                    break
+        if prev is not None:
+            res = sch.collect_tick(prev[0])
+            done += len(res)
+            ends += len(res.final_tokens)
+        return done, ends, skips
+    run(4, False)                                              # warm-up: left context filled, kernels warm
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    done, ends, skips = run(chunks, True)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.result()
+    if world > 1:
+        t = torch.tensor([wall, -float(done), -float(ends), -float(skips)], dtype=torch.float64, device=f"cuda:{local}")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        wall = float(t[0].item())
+        tot = torch.tensor([float(done), float(ends), float(skips)], dtype=torch.float64, device=f"cuda:{local}")
+        torch.distributed.all_reduce(tot)
+        done_all, ends_all, skips_all = (float(x) for x in tot.tolist())
+    else:
+        done_all, ends_all, skips_all = float(done), float(ends), float(skips)
+    chunk_s = seg / cfg.sample_rate
+    if rank == 0:
+        lat_a = np.asarray(lat)
+        line = {"metric": "audio-sec/sec", "value": value * world, "unit": "audio-s/s", "n_gpus": world, "steps": chunks, "warmup": 4, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOADS["longform"][1], "streams_per_gpu": n, "chunk_ms": 320, "chunks_per_stream": chunks,
+                           "audio_minutes_per_stream": chunks * chunk_s / 60.0, "weights": f"random-init seed {WEIGHT_SEED}",
+                           "parallelism": f"sessions partitioned per GPU x{world}, no collective"},
+                "clocks": clocks,
+                "e2e": {"value": done_all * chunk_s / wall, "unit": "audio-s/s", "h2d_bytes_per_step": int(done / max(chunks, 1) * (cfg.chunk_length * 2 + 4)),
+                        "d2h_bytes_per_step": int(done / max(chunks, 1) * (cfg.seg_rows * 8 + 20)), "wall_s": wall,
+                        "decoded_chunks": done_all, "vad_skipped_chunks": skips_all, "endpoints": ends_all,
+                        "realtime_factor_per_stream": (chunks * chunk_s) / wall,
+                        "what": "decoded audio-seconds of all streams / wall time of the whole long-form run (VAD-skipped chunks not counted)"},
+                "gpu_launches": None,
+                "chunk_latency_ms": {"p50": float(np.percentile(lat_a, 50)), "p99": float(np.percentile(lat_a, 99)), "max": float(lat_a.max()),
+                                     "what": "submit_tick -> collect_tick of one half-size tick (two in flight)"},
+                "kernel_rooflines": family_rooflines(fam, cfg, n, False, pk, "lowlat4096")}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    sch.close_scheduler()
+    eng.close()
+    return 0
+
+
 def run_ours(args):
     import torch
     from asr_streaming_b200 import Engine, ModelConfig, PRECISION_EXACT, PRECISION_FAST, pack_weights, random_weights
@@ -544,29 +826,18 @@ def run_ours(args):
     value = world * args.steps * audio_per_step / (dev_ms / 1e3)
     e2e_value = world * args.steps * (e2e_audio_per_step if ragged else audio_per_step) / e2e_s
 
-    # ---- larger batches on the same GPU (device-resident leg only; explains where the headline sits on the curve)
+    # ---- other batch sizes on the same GPU (device-resident leg only; explains where the headline sits on the curve)
     sweep = []
-    if world == 1 and not fbank_only and not args.no_sweep:
+    extra_legs = world == 1 and not fbank_only and not args.no_sweep
+    if extra_legs:
+        if ragged:
+            wl.sch.close_scheduler()
+        eng.close()
         for s_n in (256, 1024, 4096):
-            if s_n == streams:
+            if s_n == streams and not ragged:
                 continue
-            eng.close()
-            cfg2 = ModelConfig(precision=precision, max_batch=s_n, max_sessions=s_n, segment_size=cfg.segment_size)
-            eng = Engine(cfg2, blob, local)
-            ext2 = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
-            sl = [eng.open_session() for _ in range(s_n)]
-            eng.stage(sl, synth_pcm(s_n, cfg2.chunk_length))
-            for _ in range(3):
-                eng.run_staged(s_n)
-            eng.sync()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(ext2)
-            for _ in range(5):
-                eng.run_staged(s_n)
-            b.record(ext2)
-            eng.sync()
-            ms = a.elapsed_time(b) / 5
-            sweep.append({"streams": s_n, "ms_per_step": ms, "audio_s_per_s": s_n * (cfg.segment_length / cfg.sample_rate) / (ms / 1e3)})
+            v_, ms_, _, _, _ = device_leg(local, blob, s_n, precision, low_latency, 5, 3)
+            sweep.append({"streams": s_n, "ms_per_step": ms_, "audio_s_per_s": v_})
 
     if rank == 0:
         fam = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items() if v[1]}
@@ -604,6 +875,7 @@ def run_ours(args):
             extra["path_roofline"] = {"flop_per_stream_chunk": flop_sc,
                                       "achieved_tflops": streams * flop_sc * world * args.steps / (dev_ms / 1e3) / 1e12,
                                       "frac_of_tensor_peak": streams * flop_sc * args.steps / (dev_ms / 1e3) / 1e12 / pk["bf16_tflops"]}
+            extra["kernel_rooflines"] = family_rooflines(fam, cfg, streams, precision == PRECISION_EXACT, pk, args.workload if not args.streams else "")
         line = {
             "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -625,26 +897,57 @@ def run_ours(args):
             "realtime_streams_per_gpu": (int(e2e_value / world) if not fbank_only else None),
         }
         line.update(extra)
-        if world == 1 and not fbank_only and not args.no_sweep:
+        if extra_legs:
             line["stream_sweep"] = sweep
-        if world == 1 and ragged and not args.no_sweep:
+        if extra_legs and ragged:
             # the second half of the metric, measured directly: 10,240 real-time streams (the north-star count), per-chunk latency
-            eng.close()
             _, _, _, line["realtime_10240_streams"] = realtime_measure(local, rank, 10240, 6)
+            # ---- the parity-conformant precision at the same size: EXACT = split-bf16 operands, three tensor-core passes per product,
+            # token-exact against the reference (tests/test_parity_gpu.py); FAST is token-exact on peaked posteriors, see DESIGN.md
+            ev, ems, efam, ecfg, _ = device_leg(local, blob, streams, PRECISION_EXACT, False, 5, 3, beam=10)
+            eroof = family_rooflines(efam, ecfg, streams, True, pk, "exact4096")
+            edom = max((k for k in eroof if eroof[k]["bound"] == "tensor"), key=lambda k: efam[k]["ms_per_step"])
+            line["exact"] = {"value": ev, "unit": "audio-s/s", "ms_per_step": ems, "dtype": "bf16x3-split (fp32-equivalent), token-exact vs the reference",
+                             "streams_per_gpu": streams, "prefix_beam": 10,
+                             "roofline": dict(eroof[edom], kernel=edom, note="algorithmic FLOPs; the kernel executes 3x that on the tensor pipe"),
+                             "path_frac_of_tensor_peak": streams * flop_sc / (ems / 1e3) / 1e12 / pk["bf16_tflops"],
+                             "kernel_families_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in efam.items()}}
+            # ---- the other BASELINE configs, each on its own engine (device-resident; parity of every one is a GPU test)
+            confs = {}
+            v2, ms2, fam2, cfg2, _ = device_leg(local, blob, 256, PRECISION_FAST, False, 20, 5)
+            confs["streams256"] = {"workload": WORKLOADS["streams256"][1], "value": v2, "unit": "audio-s/s", "ms_per_step": ms2,
+                                   "kernel_families_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in fam2.items()}}
+            v4, ms4, fam4, cfg4, _ = device_leg(local, blob, 4096, PRECISION_FAST, True, 10, 3)
+            r4 = family_rooflines(fam4, cfg4, 4096, False, pk, "lowlat4096")
+            confs["lowlat4096"] = {"workload": WORKLOADS["lowlat4096"][1], "value": v4, "unit": "audio-s/s", "ms_per_step": ms4, "chunk_ms": 320,
+                                   "kernel_rooflines": {k: {"frac": round(v["frac"], 4), "bound": v["bound"], "us_per_launch": round(v["us_per_launch"], 2)} for k, v in r4.items()}}
+            confs["fbank1024"] = fbank_leg(local, blob, pk)
+            line["configs"] = confs
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, ms, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=args.ref_streams, threads=threads)
-            v2, _, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=4, threads=2)      # the reference's deployment setting (TORCH_THREAD=2, docker-compose.yml:22)
-            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.ref_streams} streams x 2 steps of the same workload, batch 1 per stream, {threads} torch threads",
-                                    "value_2_threads": v2}
+            if fbank_only:
+                fb = fbank_cpu_baseline(threads)
+                line["cpu_baseline"] = {"value": fb["kaldi80"], "unit": "audio-s/s", "cores": threads, "kind": "reference",
+                                        "sample": f"torchaudio.compliance.kaldi.fbank(num_mel_bins=80, dither=0) on 64 streams x 640 ms, batch 1 per stream, ~3 s, {threads} torch threads",
+                                        "melspec128_extract_filterbank": fb["melspec128"]}
+            else:
+                v, ms, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=args.ref_streams, threads=threads)
+                v2t, _, _ = cpu_reference_run(steps=2, warmup=1, sample_streams=4, threads=2)      # the reference's deployment setting (TORCH_THREAD=2, docker-compose.yml:22)
+                line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                        "sample": f"{args.ref_streams} streams x 2 steps of the same workload, batch 1 per stream, {threads} torch threads",
+                                        "value_2_threads": v2t}
+                if extra_legs and ragged:
+                    fb = fbank_cpu_baseline(threads)
+                    line["configs"]["fbank1024"]["cpu_baseline"] = {"value": fb["kaldi80"], "unit": "audio-s/s", "cores": threads, "kind": "reference",
+                                                                    "sample": "torchaudio.compliance.kaldi.fbank on 64 streams x 640 ms, batch 1 per stream, ~3 s",
+                                                                    "melspec128_extract_filterbank": fb["melspec128"]}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
         torch.distributed.destroy_process_group()
-    eng.close()
+    eng.close()                                              # (idempotent)
     return 0
 
 
@@ -659,10 +962,13 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--ref-streams", type=int, default=16, help="streams per step in the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the extra legs of the default line (batch-size sweep, real-time leg, exact leg, configs legs)")
+    ap.add_argument("--long-chunks", type=int, default=1875, help="chunks per stream of the longform workload (1875 x 320 ms = 10 minutes)")
     args = ap.parse_args()
     if args.impl == "reference":
         sys.exit(run_reference_arm(args))
+    if args.workload == "longform":
+        sys.exit(run_longform(args))
     sys.exit(run_realtime(args) if args.workload == "realtime" else run_ours(args))
 
 

@@ -249,6 +249,7 @@ ASR_API int asr_sched_open(AsrScheduler* s, int32_t row, int32_t slot /* < 0: op
 ASR_API int asr_sched_close(AsrScheduler* s, int32_t row);
 ASR_API int asr_sched_reset_rows(AsrScheduler* s, int32_t n, const int32_t* rows);
 ASR_API int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n);      /* returns 1 when the backlog does not fit */
+ASR_API int asr_sched_accept_block(AsrScheduler* s, int32_t n, const int32_t* rows, const int16_t* block, int64_t samples_per_row);
 ASR_API int asr_sched_ready(AsrScheduler* s, int32_t max_rows, const int32_t** rows, int32_t* n);
 /* gate_threshold >= 0: energy gate (peak of the chunk's new samples) for sessions without text in their segment; keep != NULL: the
  * caller's own decision for the rows asr_sched_ready returned. */

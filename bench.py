@@ -565,37 +565,53 @@ def run_longform(args):
         if world > 1:
             torch.distributed.barrier()
 
+    state = {"prev": None}
+
     def run(n_chunks, timed):
-        prev, done, ends, skips = None, 0, 0, 0
+        """n_chunks x 320 ms for every session; ticks of <= n / 2 sessions, two in flight, never draining between passes."""
+        done = ends = skips = 0
+
+        def collect():
+            nonlocal done, ends
+            p, t0 = state["prev"]
+            res = sch.collect_tick(p)
+            if timed:
+                lat.append(1e3 * (time.perf_counter() - t0))
+            done += len(res)
+            ends += len(res.final_tokens)
+            state["prev"] = None
         for k in range(n_chunks):
             sch.accept_block(rows, blocks[k % len(blocks)])
             while True:
                 t0 = time.perf_counter()
                 p = sch.submit_tick(gate=gate, max_rows=n // 2)
-                if prev is not None:
-                    res = sch.collect_tick(prev[0])
-                    if timed:
-                        lat.append(1e3 * (time.perf_counter() - prev[1]))
-                    done += len(res)
-                    ends += len(res.final_tokens)
-                    prev = None
                 skips += int(p.res.skipped_rows.size)
-                ends += len(p.res.final_tokens) if not p.rows.size else 0
-                if p.rows.size:
-                    prev = (p, t0)
-                elif not sch.ready_rows().size:
-                    break
-        if prev is not None:
-            res = sch.collect_tick(prev[0])
-            done += len(res)
-            ends += len(res.final_tokens)
+                if p.rows.size == 0:
+                    ends += len(p.res.final_tokens)
+                    if p.res.skipped_rows.size == 0:
+                        break                                   # nothing left to launch in this pass; the tick in flight stays in flight
+                    continue
+                if state["prev"] is not None:
+                    collect()
+                state["prev"] = (p, t0)
         return done, ends, skips
+
+    def drain():
+        if state["prev"] is not None:
+            p, _ = state["prev"]
+            res = sch.collect_tick(p)
+            state["prev"] = None
+            return len(res), len(res.final_tokens)
+        return 0, 0
     run(4, False)                                              # warm-up: left context filled, kernels warm
+    drain()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     t0 = time.perf_counter()
     done, ends, skips = run(chunks, True)
+    d2, e2 = drain()
+    done, ends = done + d2, ends + e2
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.result()

@@ -126,6 +126,7 @@ SIGNATURES = {
     "asr_sched_abort": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_sched_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(AsrSchedResultC), C.POINTER(C.c_int32)]),
     "asr_sched_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AsrSchedResultC)]),
+    "asr_sched_prestage": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "asr_debug_gemm_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int]),
 }
 

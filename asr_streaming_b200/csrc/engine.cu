@@ -160,6 +160,9 @@ struct AsrEngine {
   size_t h_out_off = 0;
   DevBuf d_pcm2, d_slots2;
   DevBuf d_src_off[2];          // asr_submit_rings: element offsets of the step's chunks inside the pinned session rings
+  DevBuf d_row_index[2];        // pre-staged batches: staged row of every batch element
+  int prestaged_rows[2] = {-1, -1};   // rows gathered + copied ahead of the decision which of them run (engine_prestage)
+  const int* act_row_index = nullptr;
   void* act_pcm = nullptr;      // input buffers the kernels of the step being enqueued read
   int* act_slots = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -478,7 +481,7 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
   const FbankPlan& pl = e->mel128;
   FbankParams P;
   memset(&P, 0, sizeof(P));
-  P.pcm = e->act_pcm; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
+  P.pcm = e->act_pcm; P.row_index = e->act_row_index; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
   P.n_frames = g.frames; P.hop = g.hop; P.frame_len = g.win; P.frame_off = (g.n_fft - g.win) / 2; P.nc = pl.nc; P.kaldi = 0;
   P.in_scale = P.pcm_is_f32 ? 1.0f : 1.0f / 32768.0f;                                  // streaming_server.py:362-363
   P.preemph = 0.f; P.log_floor = 1e-5f;                                                // audio.py:25 clamp(1e-5)
@@ -542,7 +545,7 @@ int run_step_chain(AsrEngine* e, int n, int pcm_format, bool want_logprobs) {
   if (!e->use_graphs || e->prof_on || n > e->graph_max_streams) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
   const char* asm_env = getenv("ASR_B200_ATTN_STREAM_MIN");           // read per launch by the attention dispatch: part of what a graph froze
   const uint64_t key = ((uint64_t)n << 8) | ((uint64_t)(e->act_slots == e->d_slots2.as<int>()) << 0) | ((uint64_t)(pcm_format == ASR_PCM_F32) << 1) |
-                       ((uint64_t)want_logprobs << 2) | ((uint64_t)(e->beam > 0) << 3) | ((uint64_t)((asm_env ? atoi(asm_env) : 148) & 0xffff) << 32);
+                       ((uint64_t)want_logprobs << 2) | ((uint64_t)(e->beam > 0) << 3) | ((uint64_t)(e->act_row_index != nullptr) << 4) | ((uint64_t)((asm_env ? atoi(asm_env) : 148) & 0xffff) << 32);
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     if ((int)e->graphs.size() >= e->graph_max_entries) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
@@ -609,7 +612,7 @@ size_t pcm_bytes(const AsrEngine* e, int n, int fmt) { return (size_t)n * e->geo
 size_t slots_off(const AsrEngine* e) { return round_up(pcm_bytes(e, e->cfg.max_batch, ASR_PCM_F32), 256); }
 void* dev_pcm(AsrEngine* e, int b) { return b ? e->d_pcm2.p : e->d_pcm.p; }
 int* dev_slots(AsrEngine* e, int b) { return b ? e->d_slots2.as<int>() : e->d_slots.as<int>(); }
-void use_buffer(AsrEngine* e, int b) { e->act_pcm = dev_pcm(e, b); e->act_slots = dev_slots(e, b); }
+void use_buffer(AsrEngine* e, int b) { e->act_pcm = dev_pcm(e, b); e->act_slots = dev_slots(e, b); e->act_row_index = nullptr; }
 
 // host -> pinned (skipped when the caller assembled the batch in the pinned buffer) -> device, on `st`
 int stage_inputs(AsrEngine* e, int b, int n, const int32_t* slots, const void* pcm, int fmt, cudaStream_t st) {
@@ -694,6 +697,7 @@ void deliver(AsrEngine* e, int b, int n, bool want_lp, const AsrStepOut* out) {
 int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int fmt, bool want_lp, int* ticket) {
   const int b = e->cur_buf;
   if (e->pend[b].active) { set_error("two steps are already in flight: asr_collect the oldest ticket first"); return -1; }
+  e->prestaged_rows[b] = -1;
   const auto t0 = std::chrono::steady_clock::now();
   if (stage_inputs(e, b, n, slots, pcm, fmt, e->copy_stream)) return -1;
   if (n) {
@@ -813,7 +817,7 @@ void destroy_engine(AsrEngine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   e->graphs.clear();
-  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
+  DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->d_row_index[0], &e->d_row_index[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->h_scratch, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->seg_has_text, &e->silent_mask, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_hastext, &e->d_flags, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
@@ -930,7 +934,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     // ---- activations
     const int B = cfg->max_batch, M = B * g.rows, Mc = B * g.seg_rows;
     const size_t esz = g.split ? 4 : 2;
-    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->d_src_off[0].alloc(8 * (size_t)B) || e->d_src_off[1].alloc(8 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
+    if (e->d_pcm.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots.alloc(4 * (size_t)B) || e->d_pcm2.alloc(pcm_bytes(e, B, ASR_PCM_F32)) || e->d_slots2.alloc(4 * (size_t)B) || e->d_src_off[0].alloc(8 * (size_t)B) || e->d_src_off[1].alloc(8 * (size_t)B) || e->d_row_index[0].alloc(4 * (size_t)B) || e->d_row_index[1].alloc(4 * (size_t)B) || e->x.alloc(4 * (size_t)M * d) || e->x1.alloc(4 * (size_t)M * d) ||
         e->x2.alloc(4 * (size_t)M * d) || e->q.alloc(4 * (size_t)M * d) || e->rc_kv.alloc(esz * (size_t)B * 2 * g.rc_rows * d) ||
         e->logits.alloc(4 * (size_t)Mc * g.vocab) || e->d_logprobs.alloc(4 * (size_t)Mc * g.vocab) || e->d_argmax.alloc(4 * (size_t)Mc) ||
         e->d_newtok.alloc(4 * (size_t)Mc) || e->d_nnew.alloc(4 * (size_t)B) || e->d_blank.alloc(4 * (size_t)B) || e->d_hastok.alloc(4 * (size_t)B) ||
@@ -1087,6 +1091,67 @@ int engine_submit_gather(AsrEngine* e, int n, const int32_t* slots, const int16_
     for (int i = a; i < b; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
   });
   return submit_step(e, n, slots, dst, ASR_PCM_I16, want_lp, ticket);
+}
+
+// Pre-staging: gather `n_rows` chunks into the pinned staging buffer of the NEXT step and start their H2D copy now — before the caller
+// knows which of them will run (that depends on the results of the step still in flight: VAD gate, endpoints).  The copy overlaps the
+// kernels of the running step; engine_submit_prestaged later launches the chain on a subset through a row-index indirection.
+int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int b = e->cur_buf;
+  if (n_rows < 0 || n_rows > e->cfg.max_batch) { set_error("prestage: %d rows outside [0, max_batch]", n_rows); return -1; }
+  if (e->pend[b].active) { set_error("prestage: the next staging buffer still belongs to a step in flight"); return -1; }
+  e->prestaged_rows[b] = -1;
+  if (!n_rows) return 0;
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[b]);
+  const size_t L = e->geo.chunk_len;
+  parallel_rows(n_rows, 8, [&](int a, int c) {
+    for (int i = a; i < c; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
+  });
+  ASR_CUDA_OK(cudaMemcpyAsync(dev_pcm(e, b), dst, pcm_bytes(e, n_rows, ASR_PCM_I16), cudaMemcpyHostToDevice, e->copy_stream));
+  e->prestaged_rows[b] = n_rows;
+  return 0;
+}
+
+// The step over batch elements i < n: session slots[i], audio = pre-staged row staged_index[i].
+int engine_submit_prestaged(AsrEngine* e, int n, const int32_t* slots, const int32_t* staged_index, bool want_lp, int* ticket) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int b = e->cur_buf;
+  if (e->pend[b].active) { set_error("two steps are already in flight: collect the oldest ticket first"); return -1; }
+  if (e->prestaged_rows[b] < 0) { set_error("submit_prestaged: nothing was pre-staged for this step"); return -1; }
+  if (check_step_args(e, n, slots)) return -1;
+  for (int i = 0; i < n; ++i)
+    if (staged_index[i] < 0 || staged_index[i] >= e->prestaged_rows[b]) { set_error("submit_prestaged: staged row %d out of range", staged_index[i]); return -1; }
+  const auto t0 = std::chrono::steady_clock::now();
+  e->prestaged_rows[b] = -1;
+  if (n) {
+    ASR_CUDA_OK(cudaSetDevice(e->device));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_buf[b]);
+    int32_t* h_slots = reinterpret_cast<int32_t*>(hs + slots_off(e));
+    memcpy(h_slots, slots, 4 * (size_t)n);
+    ASR_CUDA_OK(cudaMemcpyAsync(dev_slots(e, b), h_slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->copy_stream));
+    // the index list travels in the (unused) float32 half of the PCM staging area: int16 batches fill at most the first half
+    int32_t* h_index = reinterpret_cast<int32_t*>(hs + pcm_bytes(e, e->cfg.max_batch, ASR_PCM_I16));
+    memcpy(h_index, staged_index, 4 * (size_t)n);
+    ASR_CUDA_OK(cudaMemcpyAsync(e->d_row_index[b].p, h_index, 4 * (size_t)n, cudaMemcpyHostToDevice, e->copy_stream));
+    ASR_CUDA_OK(cudaEventRecord(e->ev_in[b], e->copy_stream));
+    ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+    use_buffer(e, b);
+    e->act_row_index = e->d_row_index[b].as<int>();
+    if (e->ev_t0[b]) cudaEventRecord(e->ev_t0[b], e->stream);
+    const int rc = run_step_chain(e, n, ASR_PCM_I16, want_lp);
+    e->act_row_index = nullptr;
+    if (rc) return -1;
+    if (enqueue_d2h(e, b, n, want_lp)) return -1;
+    if (e->ev_t1[b]) cudaEventRecord(e->ev_t1[b], e->stream);
+    ASR_CUDA_OK(cudaEventRecord(e->ev_done[b], e->stream));
+  }
+  e->pend[b].n = n; e->pend[b].want_lp = want_lp; e->pend[b].active = 1; e->pend[b].t0 = t0;
+  mark_inflight(e, b, n, slots);
+  e->cur_buf ^= 1;
+  if (ticket) *ticket = b;
+  return 0;
 }
 
 int engine_collect_view(AsrEngine* e, int ticket, StepView* v) {

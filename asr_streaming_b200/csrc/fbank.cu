@@ -70,11 +70,12 @@ __global__ void __launch_bounds__(kWarps * 32, KALDI ? 3 : 2) fbank_kernel(Fbank
   {
     // 16-byte vectorised, coalesced PCM stage-in (stream base is 16B aligned: pcm_stride * sizeof(PcmT) % 16 == 0)
     const int n_vec = (P.n_samples * (int)sizeof(PcmT)) / 16;
-    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const PcmT*>(P.pcm) + (size_t)b * P.pcm_stride);
+    const size_t srow = P.row_index ? (size_t)P.row_index[b] : (size_t)b;
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const PcmT*>(P.pcm) + srow * P.pcm_stride);
     int4* dst = reinterpret_cast<int4*>(s_pcm);
     for (int i = tid; i < n_vec; i += blockDim.x) dst[i] = __ldg(src + i);
     for (int i = n_vec * (16 / (int)sizeof(PcmT)) + tid; i < P.n_samples; i += blockDim.x)
-      s_pcm[i] = reinterpret_cast<const PcmT*>(P.pcm)[(size_t)b * P.pcm_stride + i];
+      s_pcm[i] = reinterpret_cast<const PcmT*>(P.pcm)[srow * P.pcm_stride + i];
   }
   __syncthreads();
   if (KALDI) {

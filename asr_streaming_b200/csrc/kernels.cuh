@@ -7,6 +7,7 @@ namespace asr {
 // ---------------------------------------------------------------- fbank
 struct FbankParams {
   const void* pcm;        // [n_streams, pcm_stride] int16 or float
+  const int* row_index;   // nullable: stream b reads row row_index[b] of `pcm` (batch assembled earlier than the batch was decided)
   int pcm_is_f32;
   int pcm_stride;         // samples between consecutive streams
   int n_samples;          // samples staged per stream

@@ -73,6 +73,11 @@ struct AsrScheduler {
   std::vector<int32_t> ready;      // scratch: the last ready scan
   std::vector<int32_t> scratch_rows;
   std::vector<int32_t> peaks;
+  // pre-staging (asr_sched_prestage): chunks gathered + copied to the device before the tick that runs them is decided
+  std::vector<int64_t> abs_rd;     // samples consumed per session since open (ring compaction moves rd, not this)
+  bool pre_valid = false;
+  std::vector<int32_t> pre_rows, pre_peaks, pre_index_of;     // staged sessions; gate peaks of their chunks; session row -> staged row (-1)
+  std::vector<int64_t> pre_abs;    // abs_rd of every staged chunk: a chunk consumed otherwise in the meantime (VAD skip) is not run from the stage
 };
 
 namespace {
@@ -88,6 +93,7 @@ void clear_segment(AsrScheduler* s, int r) {
 
 void advance(AsrScheduler* s, int r) {
   s->rd[r] += s->cfg.segment_length;                       // stream.py:159-160
+  s->abs_rd[r] += s->cfg.segment_length;
   s->last_served[r] = s->seq++;
 }
 
@@ -97,8 +103,15 @@ void ready_scan(AsrScheduler* s, int max_rows) {
   int lim = s->cfg.max_batch;
   if (max_rows > 0 && max_rows < lim) lim = max_rows;
   s->ready.clear();
-  for (int r = 0; r < cap; ++r)
-    if (s->active[r] && !s->inflight[r] && s->wr[r] - s->rd[r] >= s->cfg.chunk_length) s->ready.push_back(r);
+  if (s->pre_valid) {                                       // only chunks that are already on their way to the device
+    for (size_t i = 0; i < s->pre_rows.size(); ++i) {
+      const int r = s->pre_rows[i];
+      if (s->active[r] && !s->inflight[r] && s->abs_rd[r] == s->pre_abs[i] && s->wr[r] - s->rd[r] >= s->cfg.chunk_length) s->ready.push_back(r);
+    }
+  } else {
+    for (int r = 0; r < cap; ++r)
+      if (s->active[r] && !s->inflight[r] && s->wr[r] - s->rd[r] >= s->cfg.chunk_length) s->ready.push_back(r);
+  }
   if ((int)s->ready.size() > lim) {
     std::stable_sort(s->ready.begin(), s->ready.end(), [&](int a, int b) { return s->last_served[a] < s->last_served[b]; });
     s->ready.resize(lim);
@@ -139,7 +152,10 @@ int plan_tick(AsrScheduler* s, Tick& t, int max_rows, int gate_threshold, const 
   const int n_ready = (int)s->ready.size();
   std::vector<uint8_t> kp(n_ready, 1);
   if (keep) memcpy(kp.data(), keep, n_ready);
-  else if (gate_threshold >= 0 && n_ready) {
+  else if (gate_threshold >= 0 && n_ready && s->pre_valid && !s->pre_peaks.empty()) {
+    for (int i = 0; i < n_ready; ++i)
+      if (!s->contain[s->ready[i]]) kp[i] = s->pre_peaks[s->pre_index_of[s->ready[i]]] >= gate_threshold;
+  } else if (gate_threshold >= 0 && n_ready) {
     // the gate is consulted only for sessions without text in the current segment (stream.py:166-189, streaming_server.py:374-379)
     s->scratch_rows.clear();
     std::vector<int64_t> offs;
@@ -246,7 +262,7 @@ int asr_sched_create(const AsrSchedConfig* cfg, AsrEngine* engine, AsrScheduler*
   if (!s->audio) { if (!cfg->device_gather) set_error("asr_sched_create: cannot allocate %zu bytes of audio rings", audio_bytes); delete s; return -1; }
   memset(s->audio, 0, audio_bytes);
   s->rd.assign(n, 0); s->wr.assign(n, 0); s->n_frames.assign(n, 0); s->chunk_processed.assign(n, 0); s->chunk_total.assign(n, 0);
-  s->segment.assign(n, 0); s->last_served.assign(n, 0);
+  s->segment.assign(n, 0); s->last_served.assign(n, 0); s->abs_rd.assign(n, 0); s->pre_index_of.assign(n, -1);
   s->active.assign(n, 0); s->inflight.assign(n, 0); s->contain.assign(n, 0); s->overflow.assign(n, 0);
   s->slot.assign(n, -1); s->tok.assign(n * (size_t)cfg->max_tokens, 0); s->ntok.assign(n, 0);
   s->trailing.assign(n, 0.0); s->rel_cost.assign(n, cfg->relative_cost);
@@ -289,7 +305,7 @@ int asr_sched_open(AsrScheduler* s, int32_t row, int32_t slot) {
   if (s->eng && slot < 0 && engine_open_slot(s->eng, &slot)) return -1;
   s->slot[row] = slot;
   memset(s->audio + (size_t)row * s->CAP, 0, sizeof(int16_t) * (size_t)s->cfg.buffer_length);     // stream.py:23: buffer_length leading zeros
-  s->rd[row] = 0; s->wr[row] = s->cfg.buffer_length;
+  s->rd[row] = 0; s->wr[row] = s->cfg.buffer_length; s->abs_rd[row] = 0;
   s->active[row] = 1; s->inflight[row] = 0;
   clear_segment(s, row);
   s->chunk_total[row] = 0; s->segment[row] = 0; s->rel_cost[row] = s->cfg.relative_cost;
@@ -442,6 +458,37 @@ int asr_sched_abort(AsrScheduler* s, int32_t tick) {
   return 0;
 }
 
+/* Pre-staging for one-tick-per-pass pipelining: every session that has a full chunk buffered — INCLUDING the sessions of the tick still in
+ * flight, whose next chunk is already in their ring — is gathered into the next step's pinned staging buffer and its H2D copy starts now,
+ * overlapping the kernels of the running tick.  Which of the staged chunks run is decided by the next asr_sched_submit, after the running
+ * tick was collected (VAD gate, endpoint resets): it launches on a subset through a row-index indirection.  gate_threshold >= 0 also
+ * precomputes the energy-gate peaks of the staged chunks.  Returns the number of staged chunks (0: nothing staged, the next submit
+ * assembles its batch the usual way).  Host gather only. */
+int asr_sched_prestage(AsrScheduler* s, int32_t gate_threshold, int32_t* n_staged) {
+  if (!s) { set_error("null scheduler"); return -1; }
+  if (!s->eng) { set_error("asr_sched_prestage needs an engine"); return -1; }
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int r : s->pre_rows) s->pre_index_of[r] = -1;
+  s->pre_valid = false; s->pre_rows.clear(); s->pre_abs.clear(); s->pre_peaks.clear();
+  if (n_staged) *n_staged = 0;
+  if (s->pinned) return 0;
+  const int cap = s->cfg.capacity;
+  std::vector<int64_t> offs;
+  for (int r = 0; r < cap && (int)s->pre_rows.size() < s->cfg.max_batch; ++r)
+    if (s->active[r] && s->wr[r] - s->rd[r] >= s->cfg.chunk_length) { s->pre_rows.push_back(r); s->pre_abs.push_back(s->abs_rd[r]); offs.push_back(s->rd[r]); }
+  if (s->pre_rows.empty()) return 0;
+  const int n = (int)s->pre_rows.size();
+  if (engine_prestage(s->eng, n, s->audio, s->CAP, s->pre_rows.data(), offs.data())) { s->pre_rows.clear(); s->pre_abs.clear(); return -1; }
+  if (gate_threshold >= 0) {
+    s->pre_peaks.resize(n);
+    if (asr_pcm_peaks(n, s->audio, s->CAP, s->pre_rows.data(), offs.data(), s->cfg.buffer_length, s->cfg.chunk_length, s->pre_peaks.data())) return -1;
+  }
+  for (int i = 0; i < n; ++i) s->pre_index_of[s->pre_rows[i]] = i;
+  s->pre_valid = true;
+  if (n_staged) *n_staged = n;
+  return 0;
+}
+
 int asr_sched_submit(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, const uint8_t* keep, int32_t want_logprobs, AsrSchedResult* res, int32_t* tick_out) {
   if (!s || !tick_out) { set_error("null argument"); return -1; }
   if (!s->eng) { set_error("asr_sched_submit needs an engine (use plan / commit / update / endpoints with your own)"); return -1; }
@@ -450,10 +497,17 @@ int asr_sched_submit(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, 
   Tick& t = s->tick[id];
   if (t.active) { set_error("two ticks are already in flight: collect the oldest first"); return -1; }
   if (plan_tick(s, t, max_rows, gate_threshold, keep)) return -1;
+  const bool staged = s->pre_valid;
+  s->pre_valid = false;                                      // a stage serves one tick
   if (!t.rows.empty()) {
     // nothing of the tick is applied before the step is enqueued: a failure here leaves every session as it was
-    if (engine_submit_gather(s->eng, (int)t.rows.size(), t.slots.data(), s->audio, s->CAP, t.rows.data(), t.offsets.data(), s->pinned, want_logprobs != 0, &t.ticket)) return -1;
+    if (staged) {
+      std::vector<int32_t> idx(t.rows.size());
+      for (size_t i = 0; i < t.rows.size(); ++i) idx[i] = s->pre_index_of[t.rows[i]];
+      if (engine_submit_prestaged(s->eng, (int)t.rows.size(), t.slots.data(), idx.data(), want_logprobs != 0, &t.ticket)) return -1;
+    } else if (engine_submit_gather(s->eng, (int)t.rows.size(), t.slots.data(), s->audio, s->CAP, t.rows.data(), t.offsets.data(), s->pinned, want_logprobs != 0, &t.ticket)) return -1;
   }
+  if (staged) for (int r : s->pre_rows) s->pre_index_of[r] = -1;
   commit_tick(s, t);
   if (!t.rows.empty()) s->next_tick ^= 1;                    // a tick without a step has nothing to collect: its slot is reused by the next submit
   if (!t.fin_rows.empty()) {                      // endpoints of skipped sessions: reset their (idle) encoder state

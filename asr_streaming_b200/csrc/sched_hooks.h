@@ -19,6 +19,9 @@ struct StepView {          // pointers into the pinned result area of a collecte
 // pinned staging buffer of the step) or device gather (`base` pinned + mapped: a kernel reads the chunks over PCIe).
 int engine_submit_gather(AsrEngine* e, int n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
                          bool device_gather, bool want_logprobs, int* ticket);
+// Pre-staging (see engine.cu): gather + H2D of candidate chunks ahead of the decision which of them run; then the step over a subset.
+int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets);
+int engine_submit_prestaged(AsrEngine* e, int n, const int32_t* slots, const int32_t* staged_index, bool want_logprobs, int* ticket);
 int engine_collect_view(AsrEngine* e, int ticket, StepView* v);
 int engine_reset_async(AsrEngine* e, int n, const int32_t* slots);      // asr_session_reset_many without the argument checks' error text
 int engine_open_slot(AsrEngine* e, int32_t* slot);

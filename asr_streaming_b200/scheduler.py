@@ -388,6 +388,17 @@ class SessionScheduler:
     # the next tick (its endpoint decision needs the results first), which preserves the reference's per-stream order
     # chunk -> update_stream -> endpoint_detected -> next chunk exactly.  Nothing of a tick is applied before its step was
     # enqueued successfully; a step that fails at collect releases its sessions (their chunk is lost) and raises.
+    def prestage(self, gate: Optional[Callable] = None) -> int:
+        """One-tick-per-pass pipelining (real engine, host gather): every buffered chunk — also of the sessions whose previous chunk is still
+        in flight — is gathered and its H2D copy started now, overlapping the running tick; the next ``submit_tick`` (called after that tick
+        was collected) decides which of them run.  Returns the number of staged chunks."""
+        if not self._real:
+            return 0
+        n = C.c_int32()
+        thr = gate.threshold if (gate is not None and getattr(gate, "native", False)) else -1
+        _lib.check(self.lib, self.lib.asr_sched_prestage(self._h, thr, C.byref(n)), "asr_sched_prestage")
+        return n.value
+
     def submit_tick(self, want_logprobs: bool = False, gate: Optional[Callable] = None, max_rows: Optional[int] = None) -> PendingTick:
         res = TickResult(self)
         thr, keep = -1, None

@@ -207,6 +207,7 @@ class RaggedWorkload:
         self.run_chunks = self.skipped_chunks = self.endpoints = 0
         self.t_submit = self.t_collect = self.t_after = 0.0       # host seconds spent in submit_tick / collect_tick / scripted endpoints
         self.n_ticks = 0
+        self._prev = None
 
     def feed_pass(self):
         """The next 640 ms of every stream arrive (the samples are already in the rings; only the write pointers move)."""
@@ -253,6 +254,37 @@ class RaggedWorkload:
                     self._after(p.res)                              # VAD-skipped only: nothing to collect
         if prev is not None:
             self._after(self.sch.collect_tick(prev))
+
+    def run_prestaged(self, n_passes):
+        """n_passes x 640 ms for every session, ONE full-size tick per pass: as soon as a pass's audio is there its chunks are gathered and
+        their H2D copy starts (SessionScheduler.prestage) while the previous tick's kernels still run; that tick is then collected (its
+        bookkeeping, endpoint rules and resets decide which of the staged chunks run) and the next tick launches on the staged data."""
+        for _ in range(n_passes):
+            self.feed_pass()
+            t0 = time.perf_counter()
+            self.sch.prestage(self.gate)
+            self.t_submit += time.perf_counter() - t0
+            if self._prev is not None:
+                t0 = time.perf_counter()
+                res = self.sch.collect_tick(self._prev)
+                t1 = time.perf_counter()
+                self._after(res)
+                self.t_collect += t1 - t0
+                self.t_after += time.perf_counter() - t1
+                self._prev = None
+            t0 = time.perf_counter()
+            p = self.sch.submit_tick(gate=self.gate)
+            self.t_submit += time.perf_counter() - t0
+            self.n_ticks += 1
+            if p.rows.size:
+                self._prev = p
+            else:
+                self._after(p.res)
+
+    def drain(self):
+        if self._prev is not None:
+            self._after(self.sch.collect_tick(self._prev))
+            self._prev = None
 
     def run_sync(self):
         """One pass, one synchronous tick over every ready session: the per-chunk latency a session sees."""
@@ -582,7 +614,20 @@ def run_longform(args):
             state["prev"] = None
         for k in range(n_chunks):
             sch.accept_block(rows, blocks[k % len(blocks)])
-            while True:
+            if not dev_gather:
+                # one full-size tick per pass: gather + H2D of this pass start now, under the previous tick's kernels (SessionScheduler.prestage)
+                sch.prestage(gate)
+                if state["prev"] is not None:
+                    collect()
+                t0 = time.perf_counter()
+                p = sch.submit_tick(gate=gate)
+                skips += int(p.res.skipped_rows.size)
+                if p.rows.size:
+                    state["prev"] = (p, t0)
+                else:
+                    ends += len(p.res.final_tokens)
+                continue
+            while True:                                        # device gather: two ticks of <= n / 2 sessions per pass, two in flight
                 t0 = time.perf_counter()
                 p = sch.submit_tick(gate=gate, max_rows=n // 2)
                 skips += int(p.res.skipped_rows.size)
@@ -640,7 +685,7 @@ def run_longform(args):
                         "what": "decoded audio-seconds of all streams / wall time of the whole long-form run (VAD-skipped chunks not counted)"},
                 "gpu_launches": None,
                 "chunk_latency_ms": {"p50": float(np.percentile(lat_a, 50)), "p99": float(np.percentile(lat_a, 99)), "max": float(lat_a.max()),
-                                     "what": "submit_tick -> collect_tick of one half-size tick (two in flight)"},
+                                     "what": "submit_tick -> collect_tick of one tick (host gather: one full-size tick per pass, pre-staged; device gather: half-size ticks, two in flight)"},
                 "kernel_rooflines": family_rooflines(fam, cfg, n, False, pk, "lowlat4096")}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -787,17 +832,24 @@ def run_ours(args):
         for _ in range(lat_passes):
             dt, n_run = wl.run_sync()
             lat_ms.append(1e3 * dt)
-        # two ticks per pass (<= streams / 2 rows each, two in flight): the GPU is busy 97 % of the wall time (asr_pipeline_gpu_time: 15.8 of
-        # 16.3 ms per pass).  One tick per pass needs 7 % less GPU time (14.7 ms) but exposes the host side of the loop (feed + gather +
-        # bookkeeping of 3,275 sessions in one Python thread): 20.2 ms per pass, measured.  ASR_BENCH_E2E_ROWS overrides.
-        e2e_rows = int(os.environ.get("ASR_BENCH_E2E_ROWS", streams // 2))
-        wl.run_pipelined(2, e2e_rows)
+        # Host gather: ONE full-size tick per pass with pre-staging — the gather + H2D of pass k + 1 overlap the kernels of pass k; only the
+        # bookkeeping / endpoint rules between collect and the next launch are exposed.  Device gather (many ranks per host): two ticks of
+        # <= streams / 2 rows per pass, two in flight.  ASR_BENCH_E2E_ROWS=<rows> forces the two-tick form with that tick size.
+        forced = os.environ.get("ASR_BENCH_E2E_ROWS")
+        prestaged = not dev_gather and forced is None
+        e2e_rows = streams if prestaged else int(forced or streams // 2)
+        runner = wl.run_prestaged if prestaged else (lambda k: wl.run_pipelined(k, e2e_rows))
+        runner(2)
+        if prestaged:
+            wl.drain()
         barrier()
         c0 = (wl.run_chunks, wl.skipped_chunks, wl.endpoints)
         h0 = (wl.t_submit, wl.t_collect, wl.t_after, wl.n_ticks)
         eng.pipeline_gpu_time(reset=True)
         t0 = time.perf_counter()
-        wl.run_pipelined(e2e_steps, e2e_rows)
+        runner(e2e_steps)
+        if prestaged:
+            wl.drain()
         barrier()
         gpu_busy_ms, gpu_busy_n = eng.pipeline_gpu_time(reset=True)
         e2e_s = max_over_ranks(time.perf_counter() - t0) * (args.steps / e2e_steps)      # normalised to K steps (e2e_steps of them were run)
@@ -805,10 +857,12 @@ def run_ours(args):
         per_chunk_in = cfg.chunk_length * 2 + 4
         per_chunk_out = cfg.seg_rows * 4 * 2 + 3 * 4 + 4 * 256 + 8
         h2d, d2h = run_c * per_chunk_in // e2e_steps, run_c * per_chunk_out // e2e_steps
-        extra["ragged"] = {"sessions": streams, "batch_assembly": "device gather from pinned rings" if dev_gather else "host gather + DMA", "ticks_in_flight": 2, "max_rows_per_tick": e2e_rows, "e2e_steps_run": e2e_steps,
+        extra["ragged"] = {"sessions": streams, "batch_assembly": "device gather from pinned rings" if dev_gather else "host gather + DMA",
+                           "pipelining": ("one full-size tick per pass, gather + H2D pre-staged under the previous tick's kernels" if prestaged else "two ticks per pass, two in flight"),
+                           "max_rows_per_tick": e2e_rows, "e2e_steps_run": e2e_steps,
                            "decoded_chunks_per_pass": run_c / e2e_steps, "vad_skipped_chunks_per_pass": skip_c / e2e_steps,
                            "endpoints_per_pass": end_c / e2e_steps,
-                           "host_ms_per_tick": {"submit_tick (ready + gate + gather + enqueue)": 1e3 * (wl.t_submit - h0[0]) / max(1, wl.n_ticks - h0[3]),
+                           "host_ms_per_tick": {"prestage + submit_tick (ready + gate + gather + enqueue)": 1e3 * (wl.t_submit - h0[0]) / max(1, wl.n_ticks - h0[3]),
                                                 "collect_tick (wait + bookkeeping + rules)": 1e3 * (wl.t_collect - h0[1]) / max(1, wl.n_ticks - h0[3]),
                                                 "scripted endpoints": 1e3 * (wl.t_after - h0[2]) / max(1, wl.n_ticks - h0[3])},
                            "gpu_busy_ms_per_pass": gpu_busy_ms / e2e_steps, "gpu_steps_per_pass": gpu_busy_n / e2e_steps,

@@ -261,6 +261,9 @@ ASR_API int asr_sched_abort(AsrScheduler* s, int32_t tick);
 ASR_API int asr_sched_submit(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, const uint8_t* keep, int32_t want_logprobs, AsrSchedResult* res,
                              int32_t* tick);
 ASR_API int asr_sched_collect(AsrScheduler* s, int32_t tick, int32_t run_endpoints, AsrSchedResult* res);
+/* One-tick-per-pass pipelining: gather + H2D of every buffered chunk (also of the sessions still in flight) NOW, overlapping the running
+ * tick; the next asr_sched_submit decides which of them run and launches on that subset.  See csrc/sched.cu. */
+ASR_API int asr_sched_prestage(AsrScheduler* s, int32_t gate_threshold, int32_t* n_staged);
 
 /* ---- diagnostics used by tests (not part of the serving path) ---- */
 /* Runs the step but stops after `n_layers` encoder layers (no CTC, no state advance); buffers readable below. */

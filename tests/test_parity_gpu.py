@@ -750,3 +750,55 @@ def test_exact_precision_full_size_batch_equals_small_batch(packed_weights):
         worst = float(np.abs(r.logprobs - ref[T - 1].logprobs[which]).max())
         assert worst < EXACT_TOL
     report(f"EXACT 4096-stream step vs batch of 8: greedy ids identical on {T} x 4096 x 16 frames, log-prob max-abs {worst:.3e}")
+
+
+def test_prestaged_ticks_match_reference_texts(engines, golden, meta):
+    """One-tick-per-pass pipelining: every buffered chunk — also of the sessions still in flight — is gathered and copied to the device
+    (SessionScheduler.prestage) BEFORE the running tick is collected; the next tick then launches on a subset of the staged rows through
+    the fbank kernel's row-index indirection.  Same fixtures, same expectations as the plain scheduler test, plus a VAD-skip in between
+    (a staged chunk that was consumed otherwise must not be run from the stage)."""
+    from asr_streaming_b200 import SessionScheduler, ids_to_text
+    e = engines(engines.EXACT)
+    names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale", "edge_dc", "edge_silence"]
+    cases = [golden(n) for n in names]
+    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, vocab=meta["vocab"])
+    rng = np.random.default_rng(6)
+    sess = [sch.open() for _ in names]
+    pos, start, done_chunks = [0] * len(names), [0, 3, 1, 5, 2, 0], [0] * len(names)
+    prev, staged_total = None, 0
+
+    def check(res):
+        for s in res.sessions:
+            i = sess.index(s)
+            j = done_chunks[i]
+            text = ids_to_text(s.tokens, meta["vocab"])
+            assert text == meta["cases"][names[i]]["texts"][j], (names[i], j)
+            assert abs(s.trailing_blank_duration - (cases[i]["last_blank"][j] if text else 0.64 * (j + 1))) < 1e-6
+            done_chunks[i] += 1
+    for rnd in range(400):
+        for i, c in enumerate(cases):
+            if rnd < start[i] or pos[i] >= c["pcm"].size:
+                continue
+            room = sch.CAP - sess[i].length_of_segment
+            n = int(min(rng.integers(101, 9000), c["pcm"].size - pos[i], room))
+            if n > 100:
+                sess[i].accept_waveform(c["pcm"][pos[i]:pos[i] + n].astype(np.int16))
+                pos[i] += n
+            elif c["pcm"].size - pos[i] <= 100:
+                pos[i] = c["pcm"].size
+        staged_total += sch.prestage()                                   # while `prev` is still in flight
+        if prev is not None:
+            check(sch.collect_tick(prev))
+            prev = None
+        p = sch.submit_tick()
+        if p.rows.size:
+            prev = p
+        if all(q >= c["pcm"].size for q, c in zip(pos, cases)) and prev is None and not sch.ready_rows().size:
+            break
+    if prev is not None:
+        check(sch.collect_tick(prev))
+    for i, n in enumerate(names):
+        assert done_chunks[i] == meta["cases"][n]["n_chunks"], n
+    assert staged_total >= sum(done_chunks)
+    for s in sess:
+        sch.close(s)

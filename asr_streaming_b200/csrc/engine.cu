@@ -111,9 +111,6 @@ struct AsrEngine {
   struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int seen = 0; };
   std::unordered_map<uint64_t, StepGraph> graphs;
   int use_graphs = 0, graph_max_streams = 128, graph_max_entries = 256;
-  int mlp_fused = 0;            // ASR_B200_MLP_FUSED=1: the feed-forward block as ONE kernel at large batches (measured 9.4 vs 8.5 ms per step at
-                                // 4096 streams: both forms are bound by the epilogue warps, not by the 670 MB of hidden-activation traffic the fusion saves)
-  int mlp_min_tiles = 34;       // 256-row tiles needed before the feed-forward block runs as the one fused kernel (ASR_B200_MLP_MIN_TILES)
   int pair_ln_min_tiles = 34;   // 256-row tiles needed before gemm_ln takes the cta_group::2 shape (34 clusters of 4 fit on 148 SMs)
   int quad_ln_max_tiles = 34;   // 128-row tiles up to which gemm_ln takes the four-column-quarter shape: more would need a second wave of clusters (measured: 3200 rows 11.7 vs 15.2 us, 5120 rows 16.6 vs 15.9 us)
   int fused_ln = 1;             // LayerNorm fused into the out_proj / FFN2 epilogues (gemm_ln.cu); ASR_B200_NO_FUSED_LN=1 -> separate passes
@@ -134,9 +131,6 @@ struct AsrEngine {
   DevBuf d_pcm, d_slots, x, x1, x2, q, rc_kv, logits, fb_f32;
   Operand a_fb, a_ln, a_attn, a_h, a_enc, a_ctc;
   // per-session state
-  DevBuf h_scratch;             // fused feed-forward: [clusters * 256, ffn] bf16 hidden activations, L2-resident
-  CUtensorMap tm_h;
-  bool mlp_ready = false;
   DevBuf kv_cache, past_len, prev_id, n_frames, last_tok, seg_has_text, silent_mask;
   CUtensorMap tm_kv, tm_rc;      // head-major 3D views of the K/V cache / right-context scratch for the streaming attention kernel (bf16 only)
   bool attn_tma = false;
@@ -428,11 +422,8 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
       // out_proj + residual (pre-LN input) + LN_ff -> x1 (fp32) and the FFN1 operand
       LnEpilogue eo{L.bo, e->x.as<float>(), L.ln_ff_g, L.ln_ff_b, nullptr, nullptr, e->x1.as<float>(), e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, 0, 0, 0};
       if (run_gemm_ln(e, ASR_PROF_GEMM_OUT, e->a_attn, L.o, M, eo)) return -1;
-      const bool mlp = e->mlp_ready && e->mlp_fused && (M + 255) / 256 >= e->mlp_min_tiles;
-      if (!mlp) {
-        EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
-        if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1, &L.ts_ffn1)) return -1;
-      }
+      EpiOperand e1{e->a_h.buf.as<bf16>(), L.b1, e->a_h.ld, e->a_h.lo_off, ACT_GELU};
+      if (run_gemm(e, ASR_PROF_GEMM_FFN1, e->a_ln, L.w1, M, e1, &L.ts_ffn1)) return -1;
       // FFN2 + residual + LN_out -> x (fp32) and LN_in of the next layer -> QKV operand (last layer: segment rows -> CTC operand)
       LnEpilogue e2{L.b2, e->x1.as<float>(), L.ln_out_g, L.ln_out_b, nullptr, nullptr, e->x.as<float>(), nullptr, 0, 0, 0, 0, 0};
       if (last) {
@@ -443,15 +434,6 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
         e2.g2 = Nx.ln_in_g; e2.b2 = Nx.ln_in_b;
         e2.y_consts = e->no_fuse2 ? nullptr : L.ln_out_consts;
         e2.out_op = e->a_ln.buf.as<bf16>(); e2.op_ld = e->a_ln.ld; e2.op_lo_off = e->a_ln.lo_off;
-      }
-      if (mlp) {
-        // the whole feed-forward block in one kernel: the [M, ffn] hidden activations never leave L2 (gemm_ln.cu, MLP form)
-        MlpFuse mf;
-        mf.h = e->h_scratch.as<bf16>(); mf.b1 = L.b1; mf.ffn = g.ffn; mf.n_htiles = g.ffn / 256; mf.kb1 = d / 64;
-        const GemmProblem p2 = make_problem(M, L.w2.N, L.w2.K, 0);
-        ProfScope ps(e, ASR_PROF_GEMM_FFN2);
-        if (mlp_ln(e->tm_h, L.w2.tm[1], e->a_ln.tm, L.w1.tm[1], p2, e2, mf, e->num_sms, e->stream)) return -1;
-        continue;
       }
       if (run_gemm_ln(e, ASR_PROF_GEMM_FFN2, e->a_h, L.w2, M, e2)) return -1;
       continue;
@@ -818,7 +800,7 @@ void destroy_engine(AsrEngine* e) {
   for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   e->graphs.clear();
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->d_row_index[0], &e->d_row_index[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
-                    &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->h_scratch, &e->past_len,
+                    &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->seg_has_text, &e->silent_mask, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_hastext, &e->d_flags, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
   for (DevBuf* b : bufs) b->free();
@@ -859,11 +841,9 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* pl = getenv("ASR_B200_NO_PAIR_LN")) e->no_pair_ln = pl[0] == '1';
   if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
   if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
-  if (const char* mf = getenv("ASR_B200_MLP_FUSED")) e->mlp_fused = mf[0] == '1';
   if (const char* nt = getenv("ASR_B200_NO_TMA_STORE")) e->tma_store = !(nt[0] == '1');
   if (const char* ug = getenv("ASR_B200_GRAPHS")) e->use_graphs = ug[0] == '1';
   if (const char* gm = getenv("ASR_B200_GRAPH_MAX_STREAMS")) e->graph_max_streams = atoi(gm);
-  if (const char* mt = getenv("ASR_B200_MLP_MIN_TILES")) e->mlp_min_tiles = atoi(mt);
   if (const char* qt = getenv("ASR_B200_QUAD_LN_MAX_TILES")) e->quad_ln_max_tiles = atoi(qt);
   if (const char* fm = getenv("ASR_B200_FUSED_LN_MIN_STREAMS")) e->fused_ln_min_streams = atoi(fm);
   if (const char* pm = getenv("ASR_B200_PDL_MAX_STREAMS")) e->pdl_max_streams = atoi(pm);
@@ -998,14 +978,6 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
         host_bias(L.b1, f, &L.ts_ffn1);
       }
     }
-    if (e->mlp_fused && !g.split && d == 512 && g.ffn % 512 == 0 && g.ffn <= 2048 && (size_t)B * g.rows >= (size_t)256 * e->mlp_min_tiles) {
-      // fused feed-forward block for large batches: one 256-row slab of hidden activations per resident cluster (37 MB at most)
-      const int clusters = mlp_ln_clusters(e->num_sms);
-      if (clusters > 0 && !e->h_scratch.alloc((size_t)2 * clusters * 256 * g.ffn) &&
-          cudaMemsetAsync(e->h_scratch.p, 0, e->h_scratch.bytes, e->stream) == cudaSuccess &&
-          !make_tmap_bf16_2d(&e->tm_h, e->h_scratch.p, g.ffn, (uint64_t)clusters * 256, g.ffn, 128)) e->mlp_ready = true;
-      else fprintf(stderr, "asr_b200: fused feed-forward kernel disabled: %s\n", asr_last_error());
-    }
     if (fill_i32(e->past_len.as<int>(), 0, S, e->stream) || fill_i32(e->n_frames.as<int>(), 0, S, e->stream) ||
         fill_i32(e->prev_id.as<int>(), -1, S, e->stream) || fill_i32(e->last_tok.as<int>(), -1, S, e->stream) || fill_i32(e->seg_has_text.as<int>(), 0, S, e->stream)) break;
     e->slot_open.assign(S, 0);
@@ -1096,7 +1068,7 @@ int engine_submit_gather(AsrEngine* e, int n, const int32_t* slots, const int16_
 // Pre-staging: gather `n_rows` chunks into the pinned staging buffer of the NEXT step and start their H2D copy now — before the caller
 // knows which of them will run (that depends on the results of the step still in flight: VAD gate, endpoints).  The copy overlaps the
 // kernels of the running step; engine_submit_prestaged later launches the chain on a subset through a row-index indirection.
-int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets) {
+int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets, bool device_gather) {
   std::lock_guard<std::mutex> lk(e->mu);
   const int b = e->cur_buf;
   if (n_rows < 0 || n_rows > e->cfg.max_batch) { set_error("prestage: %d rows outside [0, max_batch]", n_rows); return -1; }
@@ -1104,12 +1076,25 @@ int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_s
   e->prestaged_rows[b] = -1;
   if (!n_rows) return 0;
   ASR_CUDA_OK(cudaSetDevice(e->device));
-  int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[b]);
-  const size_t L = e->geo.chunk_len;
-  parallel_rows(n_rows, 8, [&](int a, int c) {
-    for (int i = a; i < c; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
-  });
-  ASR_CUDA_OK(cudaMemcpyAsync(dev_pcm(e, b), dst, pcm_bytes(e, n_rows, ASR_PCM_I16), cudaMemcpyHostToDevice, e->copy_stream));
+  if (device_gather) {                                      // the rings are pinned + mapped: a kernel on the copy stream reads the chunks over PCIe
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, base) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      set_error("prestage: device gather needs the audio rings in pinned host memory (asr_host_alloc)"); return -1;
+    }
+    long long* h_off = reinterpret_cast<long long*>(e->h_buf[b]);
+    for (int i = 0; i < n_rows; ++i) h_off[i] = (long long)rows[i] * row_stride + offsets[i];
+    ASR_CUDA_OK(cudaMemcpyAsync(e->d_src_off[b].p, h_off, 8 * (size_t)n_rows, cudaMemcpyHostToDevice, e->copy_stream));
+    if (gather_rings_launch(reinterpret_cast<const int16_t*>(pa.devicePointer), e->d_src_off[b].as<long long>(), reinterpret_cast<int16_t*>(dev_pcm(e, b)), n_rows,
+                            e->geo.chunk_len, e->copy_stream)) return -1;
+  } else {
+    int16_t* dst = reinterpret_cast<int16_t*>(e->h_buf[b]);
+    const size_t L = e->geo.chunk_len;
+    parallel_rows(n_rows, 8, [&](int a, int c) {
+      for (int i = a; i < c; ++i) memcpy(dst + (size_t)i * L, base + (size_t)rows[i] * row_stride + offsets[i], L * sizeof(int16_t));
+    });
+    ASR_CUDA_OK(cudaMemcpyAsync(dev_pcm(e, b), dst, pcm_bytes(e, n_rows, ASR_PCM_I16), cudaMemcpyHostToDevice, e->copy_stream));
+  }
   e->prestaged_rows[b] = n_rows;
   return 0;
 }

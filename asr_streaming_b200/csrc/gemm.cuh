@@ -64,18 +64,6 @@ struct LnEpilogue {
 int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap& tmB128, const GemmProblem& p, const LnEpilogue& ep, int shape,
             int num_sms, cudaStream_t st);
 
-// Fused feed-forward block: FFN1 (+ bias + GELU) -> L2-resident scratch -> FFN2 + residual + LayerNorm(s) in one persistent kernel.
-struct MlpFuse {
-  bf16* h = nullptr;          // scratch [clusters * 256, ffn] bf16 (mlp_ln_clusters() slabs)
-  const float* b1 = nullptr;  // [ffn] FFN1 bias
-  int n_htiles = 0;           // ffn / 256
-  int kb1 = 0;                // d_model / 64
-  int ffn = 0;
-};
-int mlp_ln_clusters(int num_sms);
-int mlp_ln(const CUtensorMap& tmH, const CUtensorMap& tmW2_128, const CUtensorMap& tmX, const CUtensorMap& tmW1_128, const GemmProblem& p,
-           const LnEpilogue& ep, const MlpFuse& mf, int num_sms, cudaStream_t st);
-
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t rows, uint32_t n_heads, uint32_t box_rows);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows);
 // general bf16 map, rank <= 4, 128B swizzle, innermost box 64 elements: dims / strides (bytes, for dims 1 ..) / box given innermost first

@@ -33,7 +33,6 @@ __device__ unsigned long long g_ln_clk[8];                  // [0] tiles, [1] wa
 #else
 #define LN_T(var)
 #endif
-constexpr int kMaxHiddenTiles = 8;                         // MLP form: ffn <= 8 * 256
 constexpr int L_STATS4_BYTES = 4 * BM * 16 + 2 * BM * 16;      // float4 payload of the derived second-LN statistics (PAIR shape only)
 // Three shapes of the same kernel (SHAPE):
 //   0  cluster of 2: CTA r = columns [256 r, +256) of the same 128 rows; 1-CTA MMA 128 x 256; stage = A 16 KB + B 32 KB, 3 stages
@@ -223,46 +222,9 @@ __device__ __forceinline__ ChunkMoments chunk_moments(const float (&v)[32], cons
   return r;
 }
 
-// cluster-scope acquire / release on an mbarrier that orders GLOBAL-memory data between CTAs of the cluster (MLP form: the hidden
-// activations travel through an L2-resident scratch)
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (int it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (it == 64) t0 = clock64();
-    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000ll) asm volatile("trap;");
-  }
-}
-__device__ __forceinline__ void mbar_arrive_rlx_cluster(uint32_t bar, uint32_t cta_rank) {      // the caller has fenced (fence.acq_rel.cluster)
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(cta_rank) : "memory");
-}
-
-// MLP = true (PAIR shape only): the whole feed-forward block in one persistent kernel.  Per 256-row tile a cluster first runs the
-// FFN1 tiles (pair n: hidden-column tiles n, n + 2, ... of 256 columns, K = d_model; epilogue bias + GELU -> bf16 into the cluster's
-// private [256, ffn] scratch, which never leaves L2) and then the FFN2 tile with the LayerNorm epilogue above, whose A operand is
-// that scratch (TMA, gated per hidden tile by an mbarrier the writer CTA's 16 epilogue warps arrive on with release.cluster after a
-// fence.proxy.async: generic-proxy stores -> async-proxy loads of another CTA).  All three roles walk the same tile list, the two
-// TMEM accumulators alternate over FFN1 and FFN2 tiles alike.  Versus the two separate kernels the [M, ffn] bf16 hidden activations
-// (335 MB written + 335 MB read per layer at 4096 streams) stay on chip.  Re-use of the scratch by the next row tile is ordered by
-// the LayerNorm statistics exchange: a CTA's next FFN1 epilogue runs after its LN epilogue, which needed the other pair's
-// statistics, which that pair sends only after its FFN2 accumulator — hence all its scratch loads — completed.
-template <int SHAPE, bool MLP>
+template <int SHAPE>
 __global__ void __launch_bounds__(L_THREADS, 1)
-gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX,
-               const __grid_constant__ CUtensorMap tmW1, GemmProblem p, LnEpilogue ep, MlpFuse mf) {
-  static_assert(!MLP || SHAPE == 1, "the fused feed-forward form exists for the cta_group::2 shape only");
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmProblem p, LnEpilogue ep) {
   using Cfg = LnCfg<SHAPE>;
   constexpr bool PAIR = Cfg::PAIR;
   constexpr int L_STAGES = Cfg::STAGES, L_STAGE_BYTES = Cfg::STAGE_BYTES, CLUSTER = Cfg::CLUSTER, LBN = Cfg::BN, NSPLIT = Cfg::NSPLIT;
@@ -279,8 +241,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * L_STAGES + 2 + s); };
   auto xq_bar = [&](int set, int q) { return bar_base + 8u * (2 * L_STAGES + 4 + 4 * set + q); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * L_STAGES + 12);
-  auto hfull_bar = [&](int t) { return bar_base + 8u * (2 * L_STAGES + 13 + t); };      // MLP: hidden tile t of the scratch is written (cluster-visible)
-  auto hdone_bar = [&](int t) { return bar_base + 8u * (2 * L_STAGES + 13 + kMaxHiddenTiles + t); };   // MLP: this CTA's 16 epilogue warps stored tile t
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -299,11 +259,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < L_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), PAIR ? 2 * L_EW : L_EW); }
     for (int q = 0; q < 8; ++q) mbar_init(xq_bar(q >> 2, q & 3), 32);       // the 32 lanes of the quarter's warp 0 arm 8 bytes each
-    if (MLP) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
-      for (int t = 0; t < kMaxHiddenTiles; ++t) { mbar_init(hfull_bar(t), 1); mbar_init(hdone_bar(t), L_EW); }
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -326,34 +281,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      uint32_t it_par = 0;
-      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, it_par ^= 1u) {
-        // MLP: the FFN2 A operand is the cluster's scratch, not rows of a global [M, K] matrix
-        const int row_a = (MLP ? cluster_id : m_blk) * TILE_M + (int)mrank * BM;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        const int row_a = m_blk * TILE_M + (int)mrank * BM;
         const int row_b = (int)nrank * LBN + (PAIR ? (int)mrank * (LBN / 2) : 0);
-        if constexpr (MLP) {
-          const int row_x = m_blk * TILE_M + (int)mrank * BM;
-          for (int g = 0; g < mf.n_htiles / 2; ++g) {
-            const int row_w1 = (2 * g + (int)nrank) * LBN + (int)mrank * (LBN / 2);
-            for (int kb = 0; kb < mf.kb1; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
-              const uint32_t lbar = full_bar(stage) & kPeerBitMask;
-              if (mrank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)L_STAGE_BYTES);
-              tma_load_2d_pair(sa, &tmX, kb * BK, row_x, lbar);
-              tma_load_2d_pair(sa + BM * BK * 2, &tmW1, kb * BK, row_w1, lbar);
-              if (++stage == L_STAGES) { stage = 0; phase ^= 1u; }
-            }
-          }
-        }
         for (int ps = 0; ps < p.passes; ++ps) {
           for (int kb = 0; kb < kb_per_pass; ++kb) {
-            if constexpr (MLP) {
-              if ((kb & 3) == 0) {                            // 4 k-blocks = one 256-column hidden tile of the scratch
-                mbar_wait_acq_cluster(hfull_bar(kb >> 2), it_par);
-                asm volatile("fence.proxy.async;" ::: "memory");
-              }
-            }
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
             const uint32_t sb = sa + BM * BK * 2;
@@ -379,10 +311,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (!PAIR || mrank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const int sub_tiles = MLP ? mf.n_htiles / 2 + 1 : 1;   // MLP: this pair's FFN1 tiles, then the FFN2 tile
-      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters)
-      for (int sub = 0; sub < sub_tiles; ++sub) {
-        const int n_kb = (MLP && sub + 1 < sub_tiles) ? mf.kb1 : total_kb;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        const int n_kb = total_kb;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * LBN);
@@ -450,68 +380,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int col_cta = (int)nrank * LBN;
     int acc = 0; uint32_t acc_phase = 0;
     int round = 0;
-    uint32_t it_epi = 0;
-    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++it_epi) {
-      if constexpr (MLP) {
-        // ---------------- FFN1 tiles of this pair: bias + GELU -> bf16 rows of the cluster's scratch (thread = row, 64 B per chunk)
-        bf16* hrow_q = mf.h + (size_t)(cluster_id * TILE_M + (int)mrank * BM + quarter * 32) * mf.ffn;      // first row of this warp's TMEM lane quarter
-        for (int g = 0; g < mf.n_htiles / 2; ++g) {
-          const int t = 2 * g + (int)nrank;
-          const uint32_t ta1 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * LBN);
-          mbar_wait(tfull_bar(acc), acc_phase);
-          tc_fence_after();
-          float hv[32];
-          uint32_t* xw = reinterpret_cast<uint32_t*>(xpose);        // [32 rows][16 words] bf16 staging, 16-byte pieces XOR-swizzled
-#pragma unroll 1
-          for (int h = 0; h < CHUNKS; ++h) {
-            const int cc = wq + 4 * h;
-            const int col0 = t * LBN + cc * 32;
-            tmem_ld32(ta1 + (uint32_t)(cc * 32), hv);
-            tmem_ld_wait();
-            if (h == CHUNKS - 1) {                             // accumulator drained: the MMA warp may refill it while we finish
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (mrank == 0) mbar_arrive(tempty_bar(acc));
-                else mbar_arrive_cta(tempty_bar(acc), rank & ~1u);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(mf.b1 + col0 + j)), bb = __ldg(reinterpret_cast<const float4*>(mf.b1 + col0 + j + 4));
-              hv[j] += ba.x; hv[j + 1] += ba.y; hv[j + 2] += ba.z; hv[j + 3] += ba.w;
-              hv[j + 4] += bb.x; hv[j + 5] += bb.y; hv[j + 6] += bb.z; hv[j + 7] += bb.w;
-              gelu_erf2(hv[j], hv[j + 1]); gelu_erf2(hv[j + 2], hv[j + 3]); gelu_erf2(hv[j + 4], hv[j + 5]); gelu_erf2(hv[j + 6], hv[j + 7]);
-              uint4 o;
-              o.x = pack_bf16x2(hv[j], hv[j + 1]); o.y = pack_bf16x2(hv[j + 2], hv[j + 3]);
-              o.z = pack_bf16x2(hv[j + 4], hv[j + 5]); o.w = pack_bf16x2(hv[j + 6], hv[j + 7]);
-              *reinterpret_cast<uint4*>(xw + lane * 16 + 4 * ((j >> 3) ^ ((lane >> 1) & 3))) = o;      // row = lane
-            }
-            __syncwarp();
-            // 8 rows x 64 B per instruction: every 32-byte sector is written whole
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = 8 * i + (lane >> 2), pc = lane & 3;
-              const uint4 o = *reinterpret_cast<const uint4*>(xw + r * 16 + 4 * (pc ^ ((r >> 1) & 3)));
-              *reinterpret_cast<uint4*>(hrow_q + (size_t)r * mf.ffn + col0 + 8 * pc) = o;
-            }
-            __syncwarp();
-          }
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // my generic-proxy stores before any async-proxy (TMA) read of them
-          __syncwarp();
-          if (lane == 0) mbar_arrive(hdone_bar(t));           // CTA scope: cheap.  One warp per tile pays for the cluster-scope release:
-          if (ew == ((g + (int)(it_epi & 3u) * 4) & 15)) {    // (rotating, so that no warp is always the one that waits)
-            mbar_wait(hdone_bar(t), it_epi & 1u);             // all 16 warps' stores of this hidden tile are ordered before ...
-            if (lane == 0) {
-              asm volatile("fence.acq_rel.cluster;" ::: "memory");   // ... this fence, which publishes them to the cluster (cumulativity)
-              mbar_arrive_rlx_cluster(hfull_bar(t), rank);          // readers of rows `mrank` of hidden tile t: this CTA ...
-              mbar_arrive_rlx_cluster(hfull_bar(t), rank ^ 2u);     // ... and the CTA with the same rows in the other pair
-            }
-            __syncwarp();
-          }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        }
-      }
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
       const int row0 = m_blk * TILE_M + (int)mrank * BM + quarter * 32;
       const int my_row = row0 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * LBN);
@@ -701,7 +570,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 #ifdef ASR_EPI_TIMING
   if (blockIdx.x == 0 && threadIdx.x == 64 && g_ln_clk[0]) {
-    printf("gemm_ln<%d,%d> K %d epilogue warp 0 of CTA 0: %llu tiles, per tile: wait tfull %llu clk, R1 %llu, exchange %llu, R2 %llu\n", SHAPE, (int)MLP, p.K, g_ln_clk[0],
+    printf("gemm_ln<%d> K %d epilogue warp 0 of CTA 0: %llu tiles, per tile: wait tfull %llu clk, R1 %llu, exchange %llu, R2 %llu\n", SHAPE, p.K, g_ln_clk[0],
            g_ln_clk[1] / g_ln_clk[0], g_ln_clk[2] / g_ln_clk[0], g_ln_clk[3] / g_ln_clk[0], g_ln_clk[4] / g_ln_clk[0]);
     g_ln_clk[0] = g_ln_clk[1] = g_ln_clk[2] = g_ln_clk[3] = g_ln_clk[4] = 0;
   }
@@ -718,13 +587,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }  // namespace
 
 namespace {
-template <int SHAPE, bool MLP>
+template <int SHAPE>
 int ln_max_clusters(int num_sms, int* out) {
   constexpr int CL = LnCfg<SHAPE>::CLUSTER;
   static int max_clusters_dev[kMaxDevices] = {0};
   int& max_clusters = max_clusters_dev[current_device_index()];
   if (!max_clusters) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<SHAPE, MLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<SHAPE>()));
+    ASR_CUDA_OK(cudaFuncSetAttribute(gemm_ln_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<SHAPE>()));
     // how many clusters of this shape the device can hold at once (GPC boundaries: 148 SMs hold 74 pairs but only ~34 quads)
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(num_sms / CL * CL); q.blockDim = dim3(L_THREADS); q.dynamicSmemBytes = ln_smem_bytes<SHAPE>();
@@ -732,19 +601,18 @@ int ln_max_clusters(int num_sms, int* out) {
     a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CL; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel<SHAPE, MLP>, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel<SHAPE>, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
     max_clusters = n < num_sms / CL ? n : num_sms / CL;
   }
   *out = max_clusters;
   return 0;
 }
 
-template <int SHAPE, bool MLP>
-int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmW1, const GemmProblem& p, const LnEpilogue& ep,
-              const MlpFuse& mf, int num_sms, cudaStream_t st) {
+template <int SHAPE>
+int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmProblem& p, const LnEpilogue& ep, int num_sms, cudaStream_t st) {
   constexpr int CL = LnCfg<SHAPE>::CLUSTER, TILE_M = LnCfg<SHAPE>::PAIR ? 2 * BM : BM;
   int max_clusters = 0;
-  if (ln_max_clusters<SHAPE, MLP>(num_sms, &max_clusters)) return -1;
+  if (ln_max_clusters<SHAPE>(num_sms, &max_clusters)) return -1;
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int clusters = m_tiles < max_clusters ? m_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -753,7 +621,7 @@ int launch_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_kernel<SHAPE, MLP>, tmA, tmB, tmX, tmW1, p, ep, mf));
+  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_kernel<SHAPE>, tmA, tmB, p, ep));
   return 0;
 }
 }  // namespace
@@ -765,28 +633,9 @@ int gemm_ln(const CUtensorMap& tmA, const CUtensorMap& tmB256, const CUtensorMap
   if (p.M <= 0) return 0;
   if (p.N != LN_N) { set_error("gemm_ln: N = %d, the fused LayerNorm epilogue is built for d_model = %d", p.N, LN_N); return -1; }
   if (p.K % BK != 0) { set_error("gemm_ln: K=%d not a multiple of %d", p.K, BK); return -1; }
-  const MlpFuse none{};
-  if (shape == 1) return launch_ln<1, false>(tmA, tmB128, tmA, tmB128, p, ep, none, num_sms, st);
-  if (shape == 2) return launch_ln<2, false>(tmA, tmB128, tmA, tmB128, p, ep, none, num_sms, st);
-  return launch_ln<0, false>(tmA, tmB256, tmA, tmB256, p, ep, none, num_sms, st);
-}
-
-// How many clusters (= 256-row scratch slabs) the fused feed-forward kernel runs at once on this device.
-int mlp_ln_clusters(int num_sms) {
-  int n = 0;
-  return ln_max_clusters<1, true>(num_sms, &n) ? -1 : n;
-}
-
-// Fused feed-forward block (see gemm_ln_kernel, MLP form).  tmH: [clusters * 256, ffn] scratch, tmW2_128: [512, ffn] weight, tmX: the
-// [M, d] FFN1 operand, tmW1_128: [ffn, d] weight — all bf16 with 128-row boxes.  p describes FFN2 (M, N = 512, K = ffn, one pass).
-int mlp_ln(const CUtensorMap& tmH, const CUtensorMap& tmW2_128, const CUtensorMap& tmX, const CUtensorMap& tmW1_128, const GemmProblem& p,
-           const LnEpilogue& ep, const MlpFuse& mf, int num_sms, cudaStream_t st) {
-  if (p.M <= 0) return 0;
-  if (p.N != LN_N || p.passes != 1 || p.K != mf.ffn || mf.ffn % 512 != 0 || mf.n_htiles != mf.ffn / 256 || mf.n_htiles > kMaxHiddenTiles || mf.kb1 <= 0 || !mf.h || !mf.b1) {
-    set_error("mlp_ln: unsupported geometry (N %d passes %d K %d ffn %d)", p.N, p.passes, p.K, mf.ffn);
-    return -1;
-  }
-  return launch_ln<1, true>(tmH, tmW2_128, tmX, tmW1_128, p, ep, mf, num_sms, st);
+  if (shape == 1) return launch_ln<1>(tmA, tmB128, p, ep, num_sms, st);
+  if (shape == 2) return launch_ln<2>(tmA, tmB128, p, ep, num_sms, st);
+  return launch_ln<0>(tmA, tmB256, p, ep, num_sms, st);
 }
 
 }  // namespace asr

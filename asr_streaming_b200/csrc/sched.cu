@@ -76,6 +76,7 @@ struct AsrScheduler {
   // pre-staging (asr_sched_prestage): chunks gathered + copied to the device before the tick that runs them is decided
   std::vector<int64_t> abs_rd;     // samples consumed per session since open (ring compaction moves rd, not this)
   bool pre_valid = false;
+  bool ring_reads_pending = false;   // device gather: a gather kernel may still be reading the pinned rings (compaction must wait for it)
   std::vector<int32_t> pre_rows, pre_peaks, pre_index_of;     // staged sessions; gate peaks of their chunks; session row -> staged row (-1)
   std::vector<int64_t> pre_abs;    // abs_rd of every staged chunk: a chunk consumed otherwise in the meantime (VAD skip) is not run from the stage
 };
@@ -339,6 +340,14 @@ int asr_sched_reset_rows(AsrScheduler* s, int32_t n, const int32_t* rows) {
 }
 
 namespace {
+// device gather: a gather kernel reads the chunks straight out of the pinned rings; moving ring contents must wait for it
+int wait_ring_reads(AsrScheduler* s) {
+  if (!s->pinned || !s->ring_reads_pending) return 0;
+  if (engine_wait_inputs(s->eng)) return -1;
+  s->ring_reads_pending = false;
+  return 0;
+}
+
 // stream.py:78-87 for one session (lock held): messages of <= 100 samples are dropped; the unread tail moves to the front when the ring is full
 int accept_locked(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
   if (check_row(s, row)) return -1;
@@ -347,7 +356,7 @@ int accept_locked(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
   if (s->wr[row] + n > s->CAP) {
     const int64_t live = s->wr[row] - s->rd[row];
     if (live + n > s->CAP) { set_error("session row %d: backlog of %lld samples exceeds the %d-sample buffer", row, (long long)(live + n), s->CAP); return 1; }
-    if (s->pinned && s->inflight[row] && engine_wait_inputs(s->eng)) return -1;      // the GPU may still be reading this session's chunk out of the ring
+    // (device gather: the caller has waited for pending ring reads before any compaction, see wait_ring_reads)
     memmove(a, a + s->rd[row], sizeof(int16_t) * (size_t)live);
     s->rd[row] = 0; s->wr[row] = live;
   }
@@ -361,6 +370,7 @@ int accept_locked(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
 int asr_sched_accept(AsrScheduler* s, int32_t row, const int16_t* pcm, int64_t n) {
   if (!s || (n > 0 && !pcm)) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(s->mu);
+  if (row >= 0 && row < s->cfg.capacity && s->wr[row] + n > s->CAP && wait_ring_reads(s)) return -1;
   return accept_locked(s, row, pcm, n);
 }
 
@@ -375,6 +385,8 @@ int asr_sched_accept_block(AsrScheduler* s, int32_t n, const int32_t* rows, cons
       return 1;
     }
   }
+  for (int i = 0; i < n; ++i)
+    if (s->wr[rows[i]] + samples > s->CAP) { if (wait_ring_reads(s)) return -1; break; }      // some ring will be compacted
   static const int env_cap = [] { const char* v = getenv("ASR_B200_HOST_THREADS"); return v ? std::max(1, atoi(v)) : 8; }();
   const int hw = (int)std::thread::hardware_concurrency();
   const int nt = std::max(1, std::min({8, env_cap, hw > 0 ? hw : 1, n / 64 + 1}));
@@ -463,7 +475,7 @@ int asr_sched_abort(AsrScheduler* s, int32_t tick) {
  * overlapping the kernels of the running tick.  Which of the staged chunks run is decided by the next asr_sched_submit, after the running
  * tick was collected (VAD gate, endpoint resets): it launches on a subset through a row-index indirection.  gate_threshold >= 0 also
  * precomputes the energy-gate peaks of the staged chunks.  Returns the number of staged chunks (0: nothing staged, the next submit
- * assembles its batch the usual way).  Host gather only. */
+ * assembles its batch the usual way).  With device gather (pinned rings) the gather kernel is what gets pre-issued. */
 int asr_sched_prestage(AsrScheduler* s, int32_t gate_threshold, int32_t* n_staged) {
   if (!s) { set_error("null scheduler"); return -1; }
   if (!s->eng) { set_error("asr_sched_prestage needs an engine"); return -1; }
@@ -471,14 +483,14 @@ int asr_sched_prestage(AsrScheduler* s, int32_t gate_threshold, int32_t* n_stage
   for (int r : s->pre_rows) s->pre_index_of[r] = -1;
   s->pre_valid = false; s->pre_rows.clear(); s->pre_abs.clear(); s->pre_peaks.clear();
   if (n_staged) *n_staged = 0;
-  if (s->pinned) return 0;
   const int cap = s->cfg.capacity;
   std::vector<int64_t> offs;
   for (int r = 0; r < cap && (int)s->pre_rows.size() < s->cfg.max_batch; ++r)
     if (s->active[r] && s->wr[r] - s->rd[r] >= s->cfg.chunk_length) { s->pre_rows.push_back(r); s->pre_abs.push_back(s->abs_rd[r]); offs.push_back(s->rd[r]); }
   if (s->pre_rows.empty()) return 0;
   const int n = (int)s->pre_rows.size();
-  if (engine_prestage(s->eng, n, s->audio, s->CAP, s->pre_rows.data(), offs.data())) { s->pre_rows.clear(); s->pre_abs.clear(); return -1; }
+  if (s->pinned) s->ring_reads_pending = true;
+  if (engine_prestage(s->eng, n, s->audio, s->CAP, s->pre_rows.data(), offs.data(), s->pinned)) { s->pre_rows.clear(); s->pre_abs.clear(); return -1; }
   if (gate_threshold >= 0) {
     s->pre_peaks.resize(n);
     if (asr_pcm_peaks(n, s->audio, s->CAP, s->pre_rows.data(), offs.data(), s->cfg.buffer_length, s->cfg.chunk_length, s->pre_peaks.data())) return -1;
@@ -505,7 +517,10 @@ int asr_sched_submit(AsrScheduler* s, int32_t max_rows, int32_t gate_threshold, 
       std::vector<int32_t> idx(t.rows.size());
       for (size_t i = 0; i < t.rows.size(); ++i) idx[i] = s->pre_index_of[t.rows[i]];
       if (engine_submit_prestaged(s->eng, (int)t.rows.size(), t.slots.data(), idx.data(), want_logprobs != 0, &t.ticket)) return -1;
-    } else if (engine_submit_gather(s->eng, (int)t.rows.size(), t.slots.data(), s->audio, s->CAP, t.rows.data(), t.offsets.data(), s->pinned, want_logprobs != 0, &t.ticket)) return -1;
+    } else {
+      if (s->pinned) s->ring_reads_pending = true;
+      if (engine_submit_gather(s->eng, (int)t.rows.size(), t.slots.data(), s->audio, s->CAP, t.rows.data(), t.offsets.data(), s->pinned, want_logprobs != 0, &t.ticket)) return -1;
+    }
   }
   if (staged) for (int r : s->pre_rows) s->pre_index_of[r] = -1;
   commit_tick(s, t);

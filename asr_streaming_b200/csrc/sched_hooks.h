@@ -20,7 +20,7 @@ struct StepView {          // pointers into the pinned result area of a collecte
 int engine_submit_gather(AsrEngine* e, int n, const int32_t* slots, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets,
                          bool device_gather, bool want_logprobs, int* ticket);
 // Pre-staging (see engine.cu): gather + H2D of candidate chunks ahead of the decision which of them run; then the step over a subset.
-int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets);
+int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_stride, const int32_t* rows, const int64_t* offsets, bool device_gather);
 int engine_submit_prestaged(AsrEngine* e, int n, const int32_t* slots, const int32_t* staged_index, bool want_logprobs, int* ticket);
 int engine_collect_view(AsrEngine* e, int ticket, StepView* v);
 int engine_reset_async(AsrEngine* e, int n, const int32_t* slots);      // asr_session_reset_many without the argument checks' error text

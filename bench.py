@@ -590,6 +590,7 @@ def run_longform(args):
         blocks.append(block)
     gate = native_energy_gate()
     lat = []
+    two_ticks = os.environ.get("ASR_BENCH_E2E_ROWS") is not None
 
     def barrier():
         eng.sync()
@@ -614,7 +615,7 @@ def run_longform(args):
             state["prev"] = None
         for k in range(n_chunks):
             sch.accept_block(rows, blocks[k % len(blocks)])
-            if not dev_gather:
+            if not two_ticks:
                 # one full-size tick per pass: gather + H2D of this pass start now, under the previous tick's kernels (SessionScheduler.prestage)
                 sch.prestage(gate)
                 if state["prev"] is not None:
@@ -627,7 +628,7 @@ def run_longform(args):
                 else:
                     ends += len(p.res.final_tokens)
                 continue
-            while True:                                        # device gather: two ticks of <= n / 2 sessions per pass, two in flight
+            while True:                                        # ASR_BENCH_E2E_ROWS: two ticks of <= n / 2 sessions per pass, two in flight
                 t0 = time.perf_counter()
                 p = sch.submit_tick(gate=gate, max_rows=n // 2)
                 skips += int(p.res.skipped_rows.size)
@@ -685,7 +686,7 @@ def run_longform(args):
                         "what": "decoded audio-seconds of all streams / wall time of the whole long-form run (VAD-skipped chunks not counted)"},
                 "gpu_launches": None,
                 "chunk_latency_ms": {"p50": float(np.percentile(lat_a, 50)), "p99": float(np.percentile(lat_a, 99)), "max": float(lat_a.max()),
-                                     "what": "submit_tick -> collect_tick of one tick (host gather: one full-size tick per pass, pre-staged; device gather: half-size ticks, two in flight)"},
+                                     "what": "submit_tick -> collect_tick of one full-size tick (one per pass, batch pre-staged under the previous tick)"},
                 "kernel_rooflines": family_rooflines(fam, cfg, n, False, pk, "lowlat4096")}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -832,11 +833,11 @@ def run_ours(args):
         for _ in range(lat_passes):
             dt, n_run = wl.run_sync()
             lat_ms.append(1e3 * dt)
-        # Host gather: ONE full-size tick per pass with pre-staging — the gather + H2D of pass k + 1 overlap the kernels of pass k; only the
-        # bookkeeping / endpoint rules between collect and the next launch are exposed.  Device gather (many ranks per host): two ticks of
-        # <= streams / 2 rows per pass, two in flight.  ASR_BENCH_E2E_ROWS=<rows> forces the two-tick form with that tick size.
+        # ONE full-size tick per pass with pre-staging — the gather + H2D (or the device gather out of pinned rings) of pass k + 1 overlap the
+        # kernels of pass k; only the bookkeeping / endpoint rules between collect and the next launch are exposed.
+        # ASR_BENCH_E2E_ROWS=<rows> forces the older form: two ticks of that size per pass, two in flight.
         forced = os.environ.get("ASR_BENCH_E2E_ROWS")
-        prestaged = not dev_gather and forced is None
+        prestaged = forced is None
         e2e_rows = streams if prestaged else int(forced or streams // 2)
         runner = wl.run_prestaged if prestaged else (lambda k: wl.run_pipelined(k, e2e_rows))
         runner(2)
@@ -924,9 +925,6 @@ def run_ours(args):
             keys = cfg.rc_rows + cfg.left_context + cfg.seg_rows
             flop_sc = (20 * sum(gemm_flops.values()) // streams + 2 * cfg.frames * 128 * 128 + 2 * cfg.seg_rows * (512 * 512 + 512 * 804)
                        + 20 * 8 * 2 * 2 * cfg.rows * keys * 64)
-            mlp_fused = "gemm_ffn1" not in fam and "gemm_ffn2" in fam      # the feed-forward block ran as one kernel (timed under gemm_ffn2)
-            if mlp_fused:
-                gemm_flops["gemm_ffn2"] += gemm_flops.pop("gemm_ffn1")
             dom = max(gemm_flops, key=lambda k: fam[k]["ms_per_step"])
             t = fam[dom]["ms_per_step"] / fam[dom]["launches_per_step"]
             mult = 3 if precision == PRECISION_EXACT else 1
@@ -936,9 +934,7 @@ def run_ours(args):
             fused = streams >= 96 and dom in ("gemm_out_proj", "gemm_ffn2") and not os.environ.get("ASR_B200_NO_FUSED_LN")
             kname = "gemm_ln_kernel" if fused else "gemm_tc_kernel"
             dom_name = dom
-            if mlp_fused and dom == "gemm_ffn2":
-                kname, dom_name = "gemm_ln_kernel<pair, MLP>", "gemm_mlp"
-            roof = {"kernel": f"{kname} ({'fused FFN1 + GELU + FFN2 + residual + LayerNorms' if dom_name == 'gemm_mlp' else dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            roof = {"kernel": f"{kname} ({dom}, M={M})", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(args.workload if not args.streams else "", dom_name), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                     "algorithmic_flops_per_launch": gemm_flops[dom], "executed_flops_multiplier": mult,
                     "all_gemms": {"ms_per_step": all_gemm_ms, "tflops": all_gemm_flop / (all_gemm_ms / 1e3) / 1e12}}

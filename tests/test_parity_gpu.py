@@ -449,37 +449,6 @@ def test_fused_layernorm_large_ragged_batch(packed_weights):
             assert np.array_equal(r, got[t][perm])                       # same kernels, different positions: bit-exact
 
 
-def test_fused_feed_forward_kernel_is_bit_identical(packed_weights, golden, meta, monkeypatch):
-    """The feed-forward block as ONE kernel (FFN1 + GELU -> L2-resident scratch -> FFN2 + residual + LayerNorms; taken from 34
-    256-row tiles per step on) forced for a 200-stream batch (15 full row tiles + a partial one, several tiles per cluster only when
-    clusters are scarce) against the two-kernel path: same MMA shapes and k order, same GELU => bit-identical log-probs and ids over
-    four chained steps; and a golden case against the reference's emission."""
-    from asr_streaming_b200 import Engine, PRECISION_FAST
-    rng = np.random.default_rng(41)
-    n = 200
-    pcm = rng.integers(-4000, 4000, size=(4, n, O.CANONICAL.chunk_length)).astype(np.int16)
-    monkeypatch.setenv("ASR_B200_FUSED_LN_MIN_STREAMS", "1")
-    monkeypatch.setenv("ASR_B200_PAIR_LN_MIN_TILES", "1")
-    outs = []
-    for fused in (False, True):
-        monkeypatch.setenv("ASR_B200_MLP_FUSED", "1" if fused else "0")
-        monkeypatch.setenv("ASR_B200_MLP_MIN_TILES", "1")
-        with Engine(model_cfg(PRECISION_FAST, max_batch=256, max_sessions=256), packed_weights) as e:
-            sl = [e.open_session() for _ in range(n)]
-            got = []
-            for t in range(4):
-                if t == 2:
-                    e.reset_sessions(sl[50:120])
-                got.append(e.step(sl, pcm[t], want_logprobs=True).logprobs)
-            outs.append(np.stack(got))
-    assert np.isfinite(outs[1]).all()
-    assert np.array_equal(outs[0], outs[1])
-    case, mc = golden("synth_noise"), meta["cases"]["synth_noise"]
-    with Engine(model_cfg(PRECISION_FAST, max_batch=16, max_sessions=16), packed_weights) as e:      # one stream: a 20-row partial tile
-        em, _, _ = _run_case(e, case, mc, O.CANONICAL)
-    assert np.abs(em - case["emission"]).max() < FAST_TOL
-
-
 @pytest.mark.parametrize("low_latency", [False, True], ids=["chunk16", "chunk8"])
 def test_tma_store_gemms_are_bit_identical(packed_weights, monkeypatch, low_latency):
     """QKV (stream-tiled M tiles, every destination a TMA box: q, the session's K/V ring block, the right-context scratch), FFN1 and
@@ -752,7 +721,8 @@ def test_exact_precision_full_size_batch_equals_small_batch(packed_weights):
     report(f"EXACT 4096-stream step vs batch of 8: greedy ids identical on {T} x 4096 x 16 frames, log-prob max-abs {worst:.3e}")
 
 
-def test_prestaged_ticks_match_reference_texts(engines, golden, meta):
+@pytest.mark.parametrize("device_gather", [False, True], ids=["host_gather", "device_gather"])
+def test_prestaged_ticks_match_reference_texts(engines, golden, meta, device_gather):
     """One-tick-per-pass pipelining: every buffered chunk — also of the sessions still in flight — is gathered and copied to the device
     (SessionScheduler.prestage) BEFORE the running tick is collected; the next tick then launches on a subset of the staged rows through
     the fbank kernel's row-index indirection.  Same fixtures, same expectations as the plain scheduler test, plus a VAD-skip in between
@@ -761,7 +731,7 @@ def test_prestaged_ticks_match_reference_texts(engines, golden, meta):
     e = engines(engines.EXACT)
     names = ["synth_noise", "testwav", "synth_tone", "edge_fullscale", "edge_dc", "edge_silence"]
     cases = [golden(n) for n in names]
-    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, vocab=meta["vocab"])
+    sch = SessionScheduler(e, capacity=16, backlog_chunks=3, vocab=meta["vocab"], device_gather=device_gather)
     rng = np.random.default_rng(6)
     sess = [sch.open() for _ in names]
     pos, start, done_chunks = [0] * len(names), [0, 3, 1, 5, 2, 0], [0] * len(names)

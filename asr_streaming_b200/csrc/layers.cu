@@ -1088,7 +1088,7 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
     return -1;
   }
   if constexpr (sizeof(T) == 2) {
-    if (P.n_heads == AM_WARPS && P.d == 512 && P.lo_off == 0 && !getenv("ASR_B200_DEBUG_SIMT_ATTENTION")) {
+    if (P.n_heads == AM_WARPS && P.d == 512 && P.lo_off == 0) {
       const char* sm_env = getenv("ASR_B200_ATTN_STREAM_MIN");       // read per launch so a test can flip it inside one process
       const int stream_min = sm_env ? atoi(sm_env) : 148;       // measured on B200: wins from 256 streams per step on (1.98 vs 2.00 ms)
       int num_sms = 148;
@@ -1108,7 +1108,7 @@ int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st) {
     const int stream_min = sm_env ? atoi(sm_env) : 148;
     const bool tma_ok = P.h_tm_cache && P.h_tm_rc && P.n_heads == AM_WARPS && P.d == 512 && P.rc_rows == AS_RC_ROWS && P.rows == P.seg_rows + P.rc_rows &&
                         P.ring <= AS_RING_ROWS && P.ring % P.seg_rows == 0 && P.left % P.seg_rows == 0 && (P.seg_rows == 16 || P.seg_rows == 8);
-    if (n_streams >= stream_min && tma_ok && !getenv("ASR_B200_DEBUG_SIMT_ATTENTION")) {
+    if (n_streams >= stream_min && tma_ok) {
       int num_sms = 148;
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, current_device_index());
       if (P.rows == 20) return attention_exact_launch<20>(P, n_streams, num_sms, st);

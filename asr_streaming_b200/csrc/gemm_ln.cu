@@ -311,14 +311,30 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (!PAIR || mrank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+#ifdef ASR_MMA_TIMING
+      long long w_empty = 0, w_full = 0, n_t = 0;
+      const long long t_begin = clock64();
+#endif
       for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
         const int n_kb = total_kb;
+#ifdef ASR_MMA_TIMING
+        const long long ta = clock64();
+#endif
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+#ifdef ASR_MMA_TIMING
+        w_empty += clock64() - ta; ++n_t;
+#endif
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * LBN);
         for (int kb = 0; kb < n_kb; ++kb) {
+#ifdef ASR_MMA_TIMING
+          const long long tb = clock64();
+#endif
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+#ifdef ASR_MMA_TIMING
+          w_full += clock64() - tb;
+#endif
           if (lane == 0) {
             const uint32_t sa = smem_base + stage * L_STAGE_BYTES;
             const uint64_t adesc = make_smem_desc(sa);
@@ -341,6 +357,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+#ifdef ASR_MMA_TIMING
+      if (blockIdx.x == 0 && lane == 0)
+        printf("gemm_ln<%d> MMA thread of CTA 0 (K %d): %lld tiles, per tile %lld clk total, waiting for a free accumulator %lld, for operand stages %lld\n", SHAPE, p.K, n_t,
+               (clock64() - t_begin) / (n_t ? n_t : 1), w_empty / (n_t ? n_t : 1), w_full / (n_t ? n_t : 1));
+#endif
     }
   } else {
     // ===================== epilogue =====================

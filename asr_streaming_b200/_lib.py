@@ -96,6 +96,7 @@ SIGNATURES = {
     "asr_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "asr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "asr_debug_step_partial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "asr_debug_decode_logits": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(AsrStepOutC)]),
     "asr_debug_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]),
     "asr_debug_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "asr_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

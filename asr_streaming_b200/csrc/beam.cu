@@ -6,16 +6,22 @@
 //   stay(j)               : p_b' = p_tot(j) + lp[blank];  p_nb' = p_nb(j) + lp[last(j)]  (+ merged extensions that spell j)
 //   ext(i, k)             : p_nb' = (tok_k == last(i) ? p_b(i) : p_tot(i)) + lp[tok_k]
 //   next beam             = the `beam` best by logaddexp(p_b', p_nb'), ties to the lower enumeration index.
-// Prefix identity is a 64-bit rolling hash + length; token strings live in a per-session double buffer in HBM
-// ([2][16][1024] int16) and are copied warp-parallel, 16 bytes per lane, when a beam entry is (re)built.
+// What is serial per stream is only the recursion over the chunk's frames; everything that is not was moved out of it:
+//   * the cand_k best tokens of every frame come from ctc_greedy_kernel (parallel over rows), together with the row's (max, lse),
+//     so a frame costs one gathered logit per beam entry (lp[last(j)]) instead of a scan of the 804-wide row, and the
+//     [rows, vocab] log-prob array is neither written nor read;
+//   * hypotheses are not copied per frame: during the chunk an entry carries (origin = entry at chunk start, tokens appended
+//     since), and the token strings — per-session double buffer in HBM, [2][16][1024] int16 — are rebuilt ONCE per chunk,
+//     warp-parallel, 16 bytes per lane.
+// Prefix identity is a 64-bit rolling hash + length.
 #include "kernels.cuh"
 
 namespace asr {
 
 namespace {
 
-constexpr int BW = 4;          // warps (streams) per CTA
-constexpr int BV = 32;         // vocab <= 1024
+constexpr int BW = 4;            // warps (streams) per CTA
+constexpr int BSEG = 32;         // frames per chunk limit (seg_rows is 16, or 8 in the low-latency geometry)
 
 __device__ __forceinline__ float lae(float a, float b) {        // logaddexp with -inf handling
   const float m = fmaxf(a, b), n = fminf(a, b);
@@ -30,19 +36,20 @@ __device__ __forceinline__ unsigned long long hext(unsigned long long h, int c) 
   return h;
 }
 
-struct WarpState {
+__device__ __forceinline__ uint32_t bkey(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+
+struct __align__(16) WarpState {
+  int16_t app[BEAM_MAX][BSEG];                                    // tokens appended to the entry since the chunk began
   int len[BEAM_MAX], last[BEAM_MAX];
   float pb[BEAM_MAX], pnb[BEAM_MAX], ptot[BEAM_MAX];
   unsigned long long hash[BEAM_MAX];
-  // scratch
+  int org[BEAM_MAX], app_n[BEAM_MAX];                             // entry at chunk start this one descends from; tokens appended since
   float npb[BEAM_MAX], npnb[BEAM_MAX], ntot[BEAM_MAX];
-  int cand_tok[BEAM_CAND_MAX];
-  float cand_lp[BEAM_CAND_MAX];
   int dead[BEAM_MAX];
   int sel[BEAM_MAX];
-  int o_len[BEAM_MAX], o_last[BEAM_MAX];
-  float o_pb[BEAM_MAX], o_pnb[BEAM_MAX];
-  unsigned long long o_hash[BEAM_MAX];
+  int ctok[BSEG * BEAM_CAND_MAX];                                 // the chunk's extension candidates, all frames
+  float clp[BSEG * BEAM_CAND_MAX];
+  float rmax[BSEG], rlse[BSEG], lp_blank[BSEG];
 };
 
 __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
@@ -54,56 +61,44 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
   if (w >= P.n) return;
   WarpState& S = ws_all[warp];
   const int slot = P.slots[w];
-  const int B = P.beam, K = P.cand_k;
-  int nb = P.n_beam[slot], cur = P.cur[slot];
+  const int B = P.beam, K = P.cand_k, SR = P.seg_rows;
+  int nb = P.n_beam[slot];
+  const int cur = P.cur[slot];
+  const size_t row0 = (size_t)w * SR;
   if (lane < BEAM_MAX) {
     const size_t o = (size_t)slot * BEAM_MAX + lane;
     S.len[lane] = P.len[o]; S.last[lane] = P.last[o]; S.pb[lane] = P.pb[o]; S.pnb[lane] = P.pnb[o]; S.hash[lane] = P.hash[o];
+    S.org[lane] = lane; S.app_n[lane] = 0;
+  }
+  for (int i = lane; i < SR * BEAM_CAND_MAX; i += 32) { S.ctok[i] = P.cand_tok[row0 * BEAM_CAND_MAX + i]; S.clp[i] = P.cand_lp[row0 * BEAM_CAND_MAX + i]; }
+  if (lane < SR) {
+    const float m = P.row_stat[2 * (row0 + lane)], lse = P.row_stat[2 * (row0 + lane) + 1];
+    S.rmax[lane] = m; S.rlse[lane] = lse;
+    S.lp_blank[lane] = (P.logits[(row0 + lane) * P.vocab] - m) - lse;
   }
   __syncwarp();
-  int16_t* tok_base = P.tokens + (size_t)slot * 2 * BEAM_MAX * BEAM_MAX_LEN;
 
-  for (int r = 0; r < P.seg_rows; ++r) {
-    const float* row = P.logprobs + ((size_t)w * P.seg_rows + r) * P.vocab;
-    float v[BV];
-#pragma unroll
-    for (int i = 0; i < BV; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = (c < P.vocab && c != 0) ? row[c] : -INFINITY;       // blank (id 0) is never an extension candidate
-    }
-    // ---- the cand_k best non-blank tokens (ties: lower id)
-    for (int k = 0; k < K; ++k) {
-      float best = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < BV; ++i)
-        if (v[i] > best) { best = v[i]; bi = lane + 32 * i; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-#pragma unroll
-      for (int i = 0; i < BV; ++i)
-        if (bi == lane + 32 * i) v[i] = -INFINITY;
-      if (lane == 0) { S.cand_tok[k] = bi; S.cand_lp[k] = best; }
-    }
+  for (int r = 0; r < SR; ++r) {
+    const int* ct = S.ctok + r * BEAM_CAND_MAX;
+    const float* cl = S.clp + r * BEAM_CAND_MAX;
+    // log-prob of the entry's last token in this frame: the one value of the row that is not among the candidates in general
+    float lp_last = -INFINITY;
+    if (lane < nb && S.len[lane] > 0) lp_last = (P.logits[(row0 + r) * P.vocab + S.last[lane]] - S.rmax[r]) - S.rlse[r];
     if (lane < BEAM_MAX) { S.dead[lane] = 0; S.ptot[lane] = lane < nb ? lae(S.pb[lane], S.pnb[lane]) : -INFINITY; }
     __syncwarp();
     // ---- stay candidates (lane j), with the extensions that spell the same prefix merged in
     if (lane < nb) {
       const int j = lane;
-      const float lp_blank = row[0];
-      float pbn = S.ptot[j] + lp_blank;
-      float pnbn = S.len[j] > 0 ? S.pnb[j] + row[S.last[j]] : -INFINITY;
+      float pbn = S.ptot[j] + S.lp_blank[r];
+      float pnbn = S.len[j] > 0 ? S.pnb[j] + lp_last : -INFINITY;
       if (S.len[j] > 0) {
         int kk = -1;
         for (int k = 0; k < K; ++k)
-          if (S.cand_tok[k] == S.last[j]) kk = k;
+          if (ct[k] == S.last[j]) kk = k;
         if (kk >= 0) {
           for (int i = 0; i < nb; ++i) {
             if (S.len[i] + 1 == S.len[j] && S.len[i] < P.max_len && hext(S.hash[i], S.last[j]) == S.hash[j]) {
-              const float val = ((S.len[i] > 0 && S.last[i] == S.last[j]) ? S.pb[i] : S.ptot[i]) + S.cand_lp[kk];
+              const float val = ((S.len[i] > 0 && S.last[i] == S.last[j]) ? S.pb[i] : S.ptot[i]) + cl[kk];
               pnbn = lae(pnbn, val);
               atomicOr(&S.dead[i], 1 << kk);
             }
@@ -125,7 +120,7 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
       else if (q < nq) {
         const int i = (q - nb) / K, k = (q - nb) - i * K;
         if (!((S.dead[i] >> k) & 1) && S.len[i] < P.max_len)
-          s = ((S.len[i] > 0 && S.last[i] == S.cand_tok[k]) ? S.pb[i] : S.ptot[i]) + S.cand_lp[k];
+          s = ((S.len[i] > 0 && S.last[i] == ct[k]) ? S.pb[i] : S.ptot[i]) + cl[k];
       }
       sc[m] = s;
     }
@@ -136,71 +131,74 @@ __global__ void __launch_bounds__(BW * 32) beam_kernel(BeamParams P) {
 #pragma unroll
       for (int m = 0; m < QM; ++m)
         if (sc[m] > best) { best = sc[m]; bq = lane + 32 * m; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oq = __shfl_xor_sync(0xffffffffu, bq, o);
-        if (ob > best || (ob == best && oq < bq)) { best = ob; bq = oq; }
-      }
-      if (best == -INFINITY) break;
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, bkey(best));
+      if (mx == bkey(-INFINITY)) break;
+      const int wq = (int)__reduce_min_sync(0xffffffffu, (uint32_t)(bkey(best) == mx ? bq : 0x7fffffff));
 #pragma unroll
       for (int m = 0; m < QM; ++m)
-        if (bq == lane + 32 * m) sc[m] = -INFINITY;
-      if (lane == 0) S.sel[t] = bq;
+        if (wq == lane + 32 * m) sc[m] = -INFINITY;
+      if (lane == 0) S.sel[t] = wq;
       ++n_new;
     }
     __syncwarp();
-    // ---- rebuild the beam into the other token buffer
-    const int16_t* src_buf = tok_base + (size_t)cur * BEAM_MAX * BEAM_MAX_LEN;
-    int16_t* dst_buf = tok_base + (size_t)(cur ^ 1) * BEAM_MAX * BEAM_MAX_LEN;
-    for (int t = 0; t < n_new; ++t) {
-      const int q = S.sel[t];
-      int src, app = -1;
-      float pbn, pnbn;
-      if (q < nb) { src = q; pbn = S.npb[q]; pnbn = S.npnb[q]; }
+    // ---- the new beam, entry t on lane t: read the parent, then (after everyone has read) write in place
+    int n_len = 0, n_last = 0, n_org = 0, n_app = 0, app = -1;
+    float n_pb = 0.f, n_pnb = 0.f;
+    unsigned long long n_hash = 0;
+    uint4 a4[BSEG / 8];
+    if (lane < n_new) {
+      const int q = S.sel[lane];
+      int src;
+      if (q < nb) { src = q; n_pb = S.npb[q]; n_pnb = S.npnb[q]; }
       else {
         src = (q - nb) / K;
         const int k = (q - nb) - src * K;
-        app = S.cand_tok[k];
-        pbn = -INFINITY;
-        pnbn = ((S.len[src] > 0 && S.last[src] == app) ? S.pb[src] : S.ptot[src]) + S.cand_lp[k];
+        app = ct[k];
+        n_pb = -INFINITY;
+        n_pnb = ((S.len[src] > 0 && S.last[src] == app) ? S.pb[src] : S.ptot[src]) + cl[k];
       }
-      const int L = S.len[src];
-      {                                                            // rows are BEAM_MAX_LEN * 2 bytes apart and 16-byte aligned: whole uint4 pieces
-        const uint4* s4 = reinterpret_cast<const uint4*>(src_buf + src * BEAM_MAX_LEN);
-        uint4* d4 = reinterpret_cast<uint4*>(dst_buf + t * BEAM_MAX_LEN);
-        for (int i = lane; i * 8 < L; i += 32) d4[i] = s4[i];
-      }
-      __syncwarp();
-      if (lane == 0) {
-        if (app >= 0) dst_buf[t * BEAM_MAX_LEN + L] = (int16_t)app;
-        S.o_len[t] = L + (app >= 0); S.o_last[t] = app >= 0 ? app : S.last[src];
-        S.o_pb[t] = pbn; S.o_pnb[t] = pnbn; S.o_hash[t] = app >= 0 ? hext(S.hash[src], app) : S.hash[src];
-      }
+      n_len = S.len[src] + (app >= 0); n_last = app >= 0 ? app : S.last[src];
+      n_hash = app >= 0 ? hext(S.hash[src], app) : S.hash[src];
+      n_org = S.org[src]; n_app = S.app_n[src];
+      const uint4* s4 = reinterpret_cast<const uint4*>(S.app[src]);
+#pragma unroll
+      for (int i = 0; i < BSEG / 8; ++i) a4[i] = s4[i];
     }
     __syncwarp();
-    if (lane < BEAM_MAX && lane < n_new) {
-      S.len[lane] = S.o_len[lane]; S.last[lane] = S.o_last[lane]; S.pb[lane] = S.o_pb[lane]; S.pnb[lane] = S.o_pnb[lane]; S.hash[lane] = S.o_hash[lane];
+    if (lane < n_new) {
+      S.len[lane] = n_len; S.last[lane] = n_last; S.pb[lane] = n_pb; S.pnb[lane] = n_pnb; S.hash[lane] = n_hash; S.org[lane] = n_org;
+      uint4* d4 = reinterpret_cast<uint4*>(S.app[lane]);
+#pragma unroll
+      for (int i = 0; i < BSEG / 8; ++i) d4[i] = a4[i];
+      if (app >= 0) S.app[lane][n_app++] = (int16_t)app;
+      S.app_n[lane] = n_app;
     }
-    nb = n_new; cur ^= 1;
+    nb = n_new;
     __syncwarp();
+  }
+  // ---- rebuild the token strings once: new entry t = string of its origin (old buffer) + the tokens appended during the chunk
+  const int16_t* src_buf = P.tokens + ((size_t)slot * 2 + cur) * BEAM_MAX * BEAM_MAX_LEN;
+  int16_t* dst_buf = P.tokens + ((size_t)slot * 2 + (cur ^ 1)) * BEAM_MAX * BEAM_MAX_LEN;
+  int16_t* out0 = P.out_tokens + (size_t)w * BEAM_MAX_LEN;
+  for (int t = 0; t < nb; ++t) {
+    const int an = S.app_n[t], L0 = S.len[t] - an;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src_buf + S.org[t] * BEAM_MAX_LEN);   // rows are 16-byte aligned: whole uint4 pieces
+    uint4* d4 = reinterpret_cast<uint4*>(dst_buf + t * BEAM_MAX_LEN);
+    uint4* o4 = reinterpret_cast<uint4*>(out0);
+    for (int i = lane; i * 8 < L0; i += 32) { const uint4 x = s4[i]; d4[i] = x; if (t == 0) o4[i] = x; }
+    __syncwarp();
+    if (lane < an) { const int16_t x = S.app[t][lane]; dst_buf[t * BEAM_MAX_LEN + L0 + lane] = x; if (t == 0) out0[L0 + lane] = x; }
   }
   // ---- write back the state and the best hypothesis
   if (lane < BEAM_MAX) {
     const size_t o = (size_t)slot * BEAM_MAX + lane;
     P.len[o] = S.len[lane]; P.last[o] = S.last[lane]; P.pb[o] = S.pb[lane]; P.pnb[o] = S.pnb[lane]; P.hash[o] = S.hash[lane];
   }
-  if (lane == 0) { P.n_beam[slot] = nb; P.cur[slot] = cur; }
-  const int L0 = S.len[0];
-  {
-    const uint4* s4 = reinterpret_cast<const uint4*>(tok_base + (size_t)cur * BEAM_MAX * BEAM_MAX_LEN);
-    uint4* d4 = reinterpret_cast<uint4*>(P.out_tokens + (size_t)w * BEAM_MAX_LEN);
-    for (int i = lane; i * 8 < L0; i += 32) d4[i] = s4[i];
-  }
+  if (lane == 0) { P.n_beam[slot] = nb; P.cur[slot] = cur ^ 1; }
   int full = 0;                                                   // a hypothesis that can no longer be extended: the caller must know
   if (lane < nb) full = S.len[lane] >= P.max_len;
   full = __any_sync(0xffffffffu, full);
-  if (lane == 0) { P.out_len[w] = L0; P.out_score[w] = lae(S.pb[0], S.pnb[0]); if (full) P.out_flags[w] |= 1; }
+  if (lane == 0) { P.out_len[w] = S.len[0]; P.out_score[w] = lae(S.pb[0], S.pnb[0]); if (full) P.out_flags[w] |= 1; }
 }
 
 __global__ void beam_reset_kernel(BeamParams P, int slot) {
@@ -237,8 +235,8 @@ __global__ void beam_reset_all_kernel(BeamParams P, int n_slots) {
 
 int beam_launch(const BeamParams& P, cudaStream_t st) {
   if (P.n <= 0) return 0;
-  if (P.beam < 1 || P.beam > BEAM_MAX || P.cand_k < 1 || P.cand_k > BEAM_CAND_MAX || P.vocab > 32 * BV || P.max_len > BEAM_MAX_LEN - 1) {
-    set_error("beam: unsupported parameters (beam %d <= %d, cand_k %d <= %d, vocab %d)", P.beam, BEAM_MAX, P.cand_k, BEAM_CAND_MAX, P.vocab);
+  if (P.beam < 1 || P.beam > BEAM_MAX || P.cand_k < 1 || P.cand_k > BEAM_CAND_MAX || P.seg_rows > BSEG || P.max_len > BEAM_MAX_LEN - 1) {
+    set_error("beam: unsupported parameters (beam %d <= %d, cand_k %d <= %d, frames per chunk %d <= %d)", P.beam, BEAM_MAX, P.cand_k, BEAM_CAND_MAX, P.seg_rows, BSEG);
     return -1;
   }
   ASR_CUDA_OK(launch_pdl(beam_kernel, dim3((P.n + BW - 1) / BW), dim3(BW * 32), 0, st, P));

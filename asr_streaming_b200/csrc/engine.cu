@@ -146,6 +146,7 @@ struct AsrEngine {
   // prefix beam search (optional)
   int beam = 0, cand_k = 0;
   DevBuf bm_n, bm_cur, bm_len, bm_last, bm_pb, bm_pnb, bm_hash, bm_tokens, d_beam_tok, d_beam_len, d_beam_score;
+  DevBuf bm_cand_tok, bm_cand_lp, bm_row_stat;   // per row of the step: extension candidates and (max, lse), written by ctc_greedy_kernel
   // Double-buffered staging so that step k+1's H2D overlaps step k's kernels (asr_submit / asr_collect):
   // pinned host [pcm | slots | results] x 2, device pcm/slots x 2 (buffer 0 = d_pcm / d_slots above), a copy stream.
   void* h_stage = nullptr;      // == h_buf[0]
@@ -477,7 +478,8 @@ int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool 
 
 BeamParams beam_params(AsrEngine* e, int n) {
   BeamParams P;
-  P.logprobs = e->d_logprobs.as<float>(); P.slots = e->act_slots;
+  P.logits = e->logits.as<float>(); P.row_stat = e->bm_row_stat.as<float>(); P.cand_tok = e->bm_cand_tok.as<int>(); P.cand_lp = e->bm_cand_lp.as<float>();
+  P.slots = e->act_slots;
   P.n = n; P.seg_rows = e->geo.seg_rows; P.vocab = e->geo.vocab; P.beam = e->beam; P.cand_k = e->cand_k; P.max_len = BEAM_MAX_LEN - 1;
   P.n_beam = e->bm_n.as<int>(); P.cur = e->bm_cur.as<int>(); P.len = e->bm_len.as<int>(); P.last = e->bm_last.as<int>();
   P.pb = e->bm_pb.as<float>(); P.pnb = e->bm_pnb.as<float>(); P.hash = e->bm_hash.as<unsigned long long>(); P.tokens = e->bm_tokens.as<int16_t>();
@@ -485,8 +487,23 @@ BeamParams beam_params(AsrEngine* e, int n) {
   return P;
 }
 
+// log_softmax + argmax + incremental greedy collapse (+ the per-frame extension candidates) over e->logits, then the prefix beam search
+int run_decode(AsrEngine* e, int n, bool want_logprobs) {
+  const Geo& g = e->geo;
+  CtcParams cp;
+  cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->act_slots;
+  cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
+  cp.seg_has_text = e->seg_has_text.as<int>(); cp.silent_mask = e->silent_mask.as<uint32_t>();
+  cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
+  cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>(); cp.has_text = e->d_hastext.as<int>(); cp.flags = e->d_flags.as<int>();
+  cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
+  if (e->beam > 0) { cp.cand_k = e->cand_k; cp.cand_tok = e->bm_cand_tok.as<int>(); cp.cand_lp = e->bm_cand_lp.as<float>(); cp.row_stat = e->bm_row_stat.as<float>(); }
+  { ProfScope ps(e, ASR_PROF_CTC); if (ctc_greedy_launch(cp, n, e->stream)) return -1; }
+  if (e->beam > 0) { ProfScope ps(e, ASR_PROF_BEAM); if (beam_launch(beam_params(e, n), e->stream)) return -1; }
+  return 0;
+}
+
 int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool with_ctc, bool want_logprobs) {
-  if (e->beam > 0) want_logprobs = true;
   pdl_set_active(n <= e->pdl_max_streams);
   const Geo& g = e->geo;
   if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
@@ -504,16 +521,7 @@ int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool 
   if (run_gemm(e, ASR_PROF_GEMM_CTC1, e->a_enc, e->ctc1, Mc, ec1, &e->ts_ctc1)) return -1;
   EpiF32 ec2{e->logits.as<float>(), e->ctc_b2, nullptr, g.vocab, g.vocab};                        // decoder.py:68
   if (run_gemm(e, ASR_PROF_GEMM_CTC2, e->a_ctc, e->ctc2, Mc, ec2)) return -1;
-  CtcParams cp;
-  cp.logits = e->logits.as<float>(); cp.vocab = g.vocab; cp.seg_rows = g.seg_rows; cp.slots = e->act_slots;
-  cp.prev_id = e->prev_id.as<int>(); cp.n_frames = e->n_frames.as<int>(); cp.last_tok_frame = e->last_tok.as<int>(); cp.past_len = e->past_len.as<int>();
-  cp.seg_has_text = e->seg_has_text.as<int>(); cp.silent_mask = e->silent_mask.as<uint32_t>();
-  cp.argmax_ids = e->d_argmax.as<int>(); cp.new_tokens = e->d_newtok.as<int>(); cp.n_new = e->d_nnew.as<int>();
-  cp.blank_frames = e->d_blank.as<int>(); cp.has_token = e->d_hastok.as<int>(); cp.has_text = e->d_hastext.as<int>(); cp.flags = e->d_flags.as<int>();
-  cp.logprobs = want_logprobs ? e->d_logprobs.as<float>() : nullptr;
-  { ProfScope ps(e, ASR_PROF_CTC); if (ctc_greedy_launch(cp, n, e->stream)) return -1; }
-  if (e->beam > 0) { ProfScope ps(e, ASR_PROF_BEAM); if (beam_launch(beam_params(e, n), e->stream)) return -1; }
-  return 0;
+  return run_decode(e, n, want_logprobs);
 }
 
 void drop_step_graphs(AsrEngine* e) {
@@ -802,7 +810,7 @@ void destroy_engine(AsrEngine* e) {
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->d_row_index[0], &e->d_row_index[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
                     &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->seg_has_text, &e->silent_mask, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_hastext, &e->d_flags, &e->d_logprobs,
-                    &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score};
+                    &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score, &e->bm_cand_tok, &e->bm_cand_lp, &e->bm_row_stat};
   for (DevBuf* b : bufs) b->free();
   for (FbankPlan* pl : {&e->mel128, &e->kaldi80}) {
     pl->window.free(); pl->tw.free(); pl->w2.free(); pl->mel_start.free(); pl->mel_cnt.free(); pl->mel_off.free(); pl->mel_w.free();
@@ -1468,7 +1476,8 @@ int asr_set_beam(AsrEngine* e, int32_t beam, int32_t cand_k) {
     if (e->bm_n.alloc(4 * S) || e->bm_cur.alloc(4 * S) || e->bm_len.alloc(4 * S * BEAM_MAX) || e->bm_last.alloc(4 * S * BEAM_MAX) ||
         e->bm_pb.alloc(4 * S * BEAM_MAX) || e->bm_pnb.alloc(4 * S * BEAM_MAX) || e->bm_hash.alloc(8 * S * BEAM_MAX) ||
         e->bm_tokens.alloc(2 * S * 2 * BEAM_MAX * BEAM_MAX_LEN) || e->d_beam_tok.alloc(2 * B * BEAM_MAX_LEN) || e->d_beam_len.alloc(4 * B) ||
-        e->d_beam_score.alloc(4 * B)) return -1;
+        e->d_beam_score.alloc(4 * B) || e->bm_cand_tok.alloc(4 * B * e->geo.seg_rows * BEAM_CAND_MAX) ||
+        e->bm_cand_lp.alloc(4 * B * e->geo.seg_rows * BEAM_CAND_MAX) || e->bm_row_stat.alloc(8 * B * e->geo.seg_rows)) return -1;
   }
   e->beam = beam; e->cand_k = cand_k;
   if (beam > 0) {
@@ -1548,10 +1557,30 @@ int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const 
   return 0;
 }
 
+int asr_debug_decode_logits(AsrEngine* e, int32_t n, const int32_t* slots, const float* logits, const AsrStepOut* out) {
+  if (!e || (n > 0 && !logits)) { set_error("null argument"); return -1; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (ticket_pending(e)) { set_error("asr_debug_decode_logits while an asr_submit ticket is in flight"); return -1; }
+  if (check_step_args(e, n, slots)) return -1;
+  if (n == 0) return 0;
+  ASR_CUDA_OK(cudaSetDevice(e->device));
+  use_buffer(e, 0);
+  const bool want_lp = out && out->logprobs;
+  ASR_CUDA_OK(cudaMemcpyAsync(e->logits.p, logits, 4 * (size_t)n * e->geo.seg_rows * e->geo.vocab, cudaMemcpyHostToDevice, e->stream));
+  ASR_CUDA_OK(cudaMemcpyAsync(dev_slots(e, 0), slots, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  pdl_set_active(false);
+  if (run_decode(e, n, want_lp)) return -1;
+  if (enqueue_d2h(e, 0, n, want_lp)) return -1;
+  ASR_CUDA_OK(cudaStreamSynchronize(e->stream));
+  deliver(e, 0, n, want_lp, out);
+  return 0;
+}
+
 int asr_debug_read(AsrEngine* e, int32_t which, float* out, uint64_t n_floats) {
   if (!e || !out) { set_error("null argument"); return -1; }
   std::lock_guard<std::mutex> lk(e->mu);
-  const DevBuf* src = which == 0 ? &e->x : which == 1 ? &e->x1 : which == 2 ? &e->x2 : which == 3 ? &e->q : which == 4 ? &e->logits : nullptr;
+  const DevBuf* src = which == 0 ? &e->x : which == 1 ? &e->x1 : which == 2 ? &e->x2 : which == 3 ? &e->q : which == 4 ? &e->logits :
+                      which == 5 ? &e->bm_cand_lp : which == 6 ? &e->bm_cand_tok : which == 7 ? &e->bm_row_stat : nullptr;
   if (!src || n_floats * 4 > src->bytes) { set_error("asr_debug_read: bad buffer id %d or size", which); return -1; }
   ASR_CUDA_OK(cudaSetDevice(e->device));
   ASR_CUDA_OK(cudaStreamSynchronize(e->stream));

@@ -61,6 +61,9 @@ struct AttnParams {
 };
 template <typename T> int attention_launch(const AttnParams<T>& P, int n_streams, cudaStream_t st);
 
+constexpr int BEAM_MAX = 16;         // beam width limit
+constexpr int BEAM_CAND_MAX = 8;     // extension candidates per frame limit
+
 // ---------------------------------------------------------------- CTC log-softmax + argmax + incremental greedy
 struct CtcParams {
   const float* logits;     // [B*seg_rows, vocab]
@@ -82,16 +85,24 @@ struct CtcParams {
   int* has_text;           // [B]  the rendered text of the segment is non-empty (the `if text:` test of stream.py:121)
   int* flags;              // [B]  cleared here (ASR_FLAG_* bits are OR-ed in by later kernels of the step)
   float* logprobs;         // nullable [B*seg_rows, vocab]
+  // prefix beam search only (cand_k > 0): per row the cand_k best non-blank ids (value desc, id asc; BEAM_CAND_MAX entries per row) and
+  // the row's (max logit, log-sum-exp) so that the beam kernel evaluates log-probs of single ids as (logit - max) - lse: the same two
+  // fp32 operations as here, without the [rows, vocab] log-prob array ever being written
+  int cand_k = 0;
+  int* cand_tok = nullptr;       // [B*seg_rows, BEAM_CAND_MAX]
+  float* cand_lp = nullptr;      // [B*seg_rows, BEAM_CAND_MAX]
+  float* row_stat = nullptr;     // [B*seg_rows, 2]
 };
 int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st);
 
 // ---------------------------------------------------------------- CTC prefix beam search (warp per stream)
-constexpr int BEAM_MAX = 16;         // beam width limit
-constexpr int BEAM_CAND_MAX = 8;     // extension candidates per frame limit
 constexpr int BEAM_MAX_LEN = 1024;   // tokens per hypothesis: an utterance is force-ended at 40 s = 1000 frames (asr-online.yaml:103-107) and CTC emits
                                      // at most one token per frame, so the cap is never reached under the reference's rules; if it is, the step says so
 struct BeamParams {
-  const float* logprobs;   // [n*seg_rows, vocab] of the current step
+  const float* logits;     // [n*seg_rows, vocab] of the current step (CTC head output before log_softmax)
+  const float* row_stat;   // [n*seg_rows, 2]  (max logit, log-sum-exp) per row: log-prob(id) = (logit[id] - max) - lse
+  const int* cand_tok;     // [n*seg_rows, BEAM_CAND_MAX]  extension candidates per frame, from ctc_greedy_kernel
+  const float* cand_lp;    // [n*seg_rows, BEAM_CAND_MAX]
   const int* slots;        // [n]
   int n, seg_rows, vocab, beam, cand_k, max_len;
   // per-slot state

@@ -955,8 +955,14 @@ int attention_launch_rows(const AttnParams<T>& P, int n_streams, cudaStream_t st
 // ------------------------------------------------------------------------------------------
 constexpr int CTC_MAXV = 32;   // vocab <= 1024
 
-__global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
+// order-preserving float <-> uint32 (so redux.sync max works on log-probs); -inf maps below every finite value
+__device__ __forceinline__ uint32_t f2key(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
   __shared__ int s_ids[64];
+  __shared__ float s_clp[8][32];                                 // per warp: the row's elements that can be among its cand_k best
+  __shared__ int s_ctok[8][32];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
@@ -974,16 +980,19 @@ __global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
     m = warp_max(m);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < CTC_MAXV; ++i) s += (lane + 32 * i < P.vocab) ? expf(v[i] - m) : 0.f;
+    for (int i = 0; i < CTC_MAXV; ++i) s += (lane + 32 * i < P.vocab) ? __expf(v[i] - m) : 0.f;    // ex2.approx: 2e-7 relative per term, 1e-6 on the log-probs (bound 2e-4)
     const float lse = logf(warp_sum(s));
     float best = -INFINITY; int bi = 0x7fffffff;
+    float lm = -INFINITY;                                          // lane maximum over the non-blank ids
 #pragma unroll
     for (int i = 0; i < CTC_MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < P.vocab) {
         const float lp = (v[i] - m) - lse;                       // log_softmax(dim=2)
+        v[i] = lp;
         if (P.logprobs) P.logprobs[row * P.vocab + c] = lp;
         if (lp > best) { best = lp; bi = c; }                     // first max wins inside a lane (c increasing)
+        if (c != 0) lm = fmaxf(lm, lp);
       }
     }
 #pragma unroll
@@ -992,10 +1001,92 @@ __global__ void __launch_bounds__(256) ctc_greedy_kernel(CtcParams P) {
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
+    if (P.cand_k > 0) {
+      // ---- the cand_k best non-blank ids of the row (value desc, id asc) for the prefix beam search, found in parallel over rows here
+      // instead of serially per frame inside the beam kernel.  Threshold T = the cand_k-th largest of the 32 lane maxima: every
+      // member of the row's top cand_k is >= T, and usually only ~cand_k elements are; those are compacted into shared memory and ranked
+      // one per lane.  More than 32 elements >= T (ties on a flat row) take the plain selection over the registers.
+      if (lane == 0) { P.row_stat[2 * row] = m; P.row_stat[2 * row + 1] = lse; }
+      uint32_t w = f2key(lm);
+      for (int k = 0; k + 1 < P.cand_k; ++k) {
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, w);
+        const uint32_t bal = __ballot_sync(0xffffffffu, w == mx);
+        if (lane == __ffs(bal) - 1) w = 0u;
+      }
+      const float T = key2f(__reduce_max_sync(0xffffffffu, w));
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < CTC_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        const bool f = c < P.vocab && c != 0 && v[i] >= T && v[i] > -INFINITY;
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        if (bal) {                                                 // warp-uniform
+          const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+          if (f && pos < 32) { s_clp[warp][pos] = v[i]; s_ctok[warp][pos] = c; }
+          cnt += __popc(bal);
+        }
+      }
+      __syncwarp();
+      float my_lp = -INFINITY; int my_tok = 0;
+      if (cnt <= 32) {
+        float x = lane < cnt ? s_clp[warp][lane] : -INFINITY;
+        const int xc = lane < cnt ? s_ctok[warp][lane] : 0x7fffffff;
+        for (int k = 0; k < P.cand_k; ++k) {
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, f2key(x));
+          const int wc = (int)__reduce_min_sync(0xffffffffu, (uint32_t)(f2key(x) == mx ? xc : 0x7fffffff));
+          if (lane == k) { my_lp = key2f(mx); my_tok = mx == f2key(-INFINITY) ? 0x7fffffff : wc; }
+          if (xc == wc) x = -INFINITY;
+        }
+      } else {
+        for (int k = 0; k < P.cand_k; ++k) {
+          float cb = -INFINITY; int ci = 0x7fffffff;
+#pragma unroll
+          for (int i = 0; i < CTC_MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < P.vocab && c != 0 && v[i] > cb) { cb = v[i]; ci = c; }
+          }
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, f2key(cb));
+          const int wc = (int)__reduce_min_sync(0xffffffffu, (uint32_t)(f2key(cb) == mx ? ci : 0x7fffffff));
+          if (lane == k) { my_lp = key2f(mx); my_tok = mx == f2key(-INFINITY) ? 0x7fffffff : wc; }
+#pragma unroll
+          for (int i = 0; i < CTC_MAXV; ++i)
+            if (wc == lane + 32 * i) v[i] = -INFINITY;
+        }
+      }
+      __syncwarp();
+      if (lane < P.cand_k) {                                       // an exhausted row (fewer finite ids than cand_k) yields lp = -inf entries: never selected
+        P.cand_tok[row * BEAM_CAND_MAX + lane] = my_tok;
+        P.cand_lp[row * BEAM_CAND_MAX + lane] = my_lp;
+      }
+    }
     if (lane == 0) { s_ids[r] = bi; P.argmax_ids[row] = bi; }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0 && P.seg_rows <= 32) {
+    // the carry update of greedy_search, one lane per frame of the chunk (ballots instead of a serial scan by one thread)
+    const int slot = P.slots[b];
+    const int prev0 = P.prev_id[slot], nf = P.n_frames[slot];
+    int lt = P.last_tok_frame[slot], ht = P.seg_has_text[slot];
+    const bool in = lane < P.seg_rows;
+    const int id = in ? s_ids[lane] : 0;
+    const int prev = lane == 0 ? prev0 : (in ? s_ids[lane - 1] : 0);
+    const uint32_t is_new = __ballot_sync(0xffffffffu, in && id != prev && id != 0);        // unique_consecutive, then drop blank
+    const uint32_t is_tok = __ballot_sync(0xffffffffu, in && id > 1);                       // tokens_idx = indices > 1
+    const uint32_t is_txt = __ballot_sync(0xffffffffu, in && !((P.silent_mask[id >> 5] >> (id & 31)) & 1u));   // `if text:` (stream.py:121)
+    if ((is_new >> lane) & 1u) P.new_tokens[(size_t)b * P.seg_rows + __popc(is_new & ((1u << lane) - 1u))] = id;
+    if (lane == 0) {
+      if (is_tok) lt = nf + 31 - __clz(is_tok);
+      ht |= is_txt != 0u;
+      const int nf1 = nf + P.seg_rows;
+      P.prev_id[slot] = s_ids[P.seg_rows - 1]; P.n_frames[slot] = nf1; P.last_tok_frame[slot] = lt; P.seg_has_text[slot] = ht;
+      P.n_new[b] = __popc(is_new);
+      P.has_token[b] = lt >= 0;
+      P.has_text[b] = ht;
+      P.flags[b] = 0;
+      P.blank_frames[b] = lt >= 0 ? nf1 - 1 - lt : nf1;
+      P.past_len[slot] += P.seg_rows;                                                     // TA:emformer.py:413 (state[3] + update_length)
+    }
+  } else if (threadIdx.x == 0 && P.seg_rows > 32) {
     const int slot = P.slots[b];
     int prev = P.prev_id[slot], nf = P.n_frames[slot], lt = P.last_tok_frame[slot], ht = P.seg_has_text[slot], n_new = 0;
     for (int r = 0; r < P.seg_rows; ++r) {

@@ -336,6 +336,16 @@ class Engine:
         a, fmt = self._pcm(pcm, int(sl.size))
         _lib.check(self.lib, self.lib.asr_debug_step_partial(self._h, int(sl.size), sl.ctypes.data, a.ctypes.data, fmt, n_layers), "asr_debug_step_partial")
 
+    def debug_decode_logits(self, slots: Sequence[int], logits: np.ndarray, want_logprobs: bool = False) -> StepResult:
+        """The decode stage alone (log_softmax, greedy collapse, prefix beam) on caller-supplied CTC logits [n, seg_rows, vocab]."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        n = int(sl.size)
+        z = np.ascontiguousarray(logits, np.float32)
+        assert z.shape == (n, self.cfg.seg_rows, self.cfg.vocab), z.shape
+        bufs, o = self._alloc_out(n, want_logprobs)
+        _lib.check(self.lib, self.lib.asr_debug_decode_logits(self._h, n, sl.ctypes.data, z.ctypes.data, C.byref(o)), "asr_debug_decode_logits")
+        return self._result(bufs, n)
+
     def debug_read(self, which: int, shape) -> np.ndarray:
         out = np.empty(shape, np.float32)
         _lib.check(self.lib, self.lib.asr_debug_read(self._h, which, out.ctypes.data, out.size), "asr_debug_read")

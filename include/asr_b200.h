@@ -268,7 +268,12 @@ ASR_API int asr_sched_prestage(AsrScheduler* s, int32_t gate_threshold, int32_t*
 /* ---- diagnostics used by tests (not part of the serving path) ---- */
 /* Runs the step but stops after `n_layers` encoder layers (no CTC, no state advance); buffers readable below. */
 ASR_API int asr_debug_step_partial(AsrEngine* e, int32_t n, const int32_t* slots, const void* pcm, int32_t pcm_format, int32_t n_layers);
-/* which: 0 = x (layer output / input_linear output) [n*rows, d]; 1 = x1; 2 = x2; 3 = q; 4 = logits [n*S, vocab] */
+/* The decode stage alone on caller-supplied CTC logits [n*S, vocab] (host memory): log_softmax + argmax + incremental greedy collapse
+ * (+ the per-frame extension candidates and the prefix beam search when asr_set_beam enabled it), session carries advanced exactly as
+ * by asr_step.  Lets tests drive the decoders with peaked, tied or degenerate posteriors that the random-init encoder never produces. */
+ASR_API int asr_debug_decode_logits(AsrEngine* e, int32_t n, const int32_t* slots, const float* logits, const AsrStepOut* out);
+/* which: 0 = x (layer output / input_linear output) [n*rows, d]; 1 = x1; 2 = x2; 3 = q; 4 = logits [n*S, vocab]; with the prefix beam enabled
+ * also 5 = log-probs of the per-frame extension candidates [n*S, 8]; 6 = their ids (int32 bit patterns); 7 = (max logit, lse) per row [n*S, 2] */
 ASR_API int asr_debug_read(AsrEngine* e, int32_t which, float* out, uint64_t n_floats);
 /* Reads the K (which=0) / V (which=1) left context of `layer` of a session in the reference's layout
  * [left_context, d] (oldest row first, zero rows where past_length < left_context) and past_length. */

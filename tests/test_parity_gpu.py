@@ -287,6 +287,86 @@ def test_prefix_beam_kernel_matches_oracle(packed_weights, golden):
     e.close()
 
 
+def _rank_candidates(lp_row, k):
+    """The k best non-blank ids by (log-prob desc, id asc) — the rule of oracle/ctc_beam_oracle.top_candidates."""
+    ids = np.arange(1, lp_row.shape[0])
+    order = np.lexsort((ids, -lp_row[1:].astype(np.float64)))
+    return ids[order[:k]]
+
+
+def test_decode_stage_on_peaked_tied_and_flat_posteriors(packed_weights):
+    """The decode stage alone (asr_debug_decode_logits) on posteriors the random-init encoder never produces:
+    * peaked rows (a trained model's regime), rows of small integers (hundreds of exact ties: more than 32 elements reach the
+      candidate threshold, i.e. the plain-selection path of ctc_greedy_kernel) and completely flat rows;
+    * per row: log-probs vs float64 log_softmax, argmax = lowest index among equal maxima (torch.argmax), the beam's extension
+      candidates = the 8 best non-blank ids by (log-prob desc, id asc) with log-probs bit-equal to the log-prob array;
+    * greedy carry across chunks vs oracle.greedy_ids on the concatenated emission; prefix beam vs oracle/ctc_beam_oracle.py on the
+      peaked streams (parity unpinned vs the reference, see that file)."""
+    from asr_streaming_b200 import Engine, PRECISION_FAST
+    from oracle import ctc_beam_oracle as B
+    cfg = model_cfg(PRECISION_FAST, max_batch=8, max_sessions=8)
+    S, V = cfg.seg_rows, cfg.vocab
+    rng = np.random.default_rng(77)
+    n, T = 6, 4
+    kinds = ["peaked", "peaked", "peaked_repeats", "ints", "ints_wide", "flat"]
+
+    def make(kind, t):
+        if kind == "flat":
+            z = np.zeros((S, V), np.float32)
+            if t % 2:
+                z[:, 5] = 1.0
+            return z
+        if kind == "ints":
+            return rng.integers(0, 4, size=(S, V)).astype(np.float32)
+        if kind == "ints_wide":
+            return rng.integers(0, 40, size=(S, V)).astype(np.float32)
+        z = rng.standard_normal((S, V)).astype(np.float32)
+        toks = rng.integers(0, V, size=S)
+        toks[rng.random(S) < 0.45] = 0                               # blanks
+        if kind == "peaked_repeats":
+            toks[1::2] = toks[0::2]                                  # repeated frames of one token (collapse / p_b vs p_nb paths)
+        z[np.arange(S), toks] += 14.0
+        return z
+
+    with Engine(cfg, packed_weights) as e:
+        e.set_beam(10, 8)
+        slots = [e.open_session() for _ in range(n)]
+        states = [B.BeamState() for _ in range(n)]
+        emis = [[] for _ in range(n)]
+        toks = [[] for _ in range(n)]
+        n_rows = 0
+        for t in range(T):
+            z = np.stack([make(k, t) for k in kinds])
+            r = e.debug_decode_logits(slots, z, want_logprobs=True)
+            lp = r.logprobs
+            z64 = z.astype(np.float64)
+            ref = z64 - z64.max(2, keepdims=True)
+            ref = ref - np.log(np.exp(ref).sum(2, keepdims=True))
+            assert np.abs(lp - ref).max() < 2e-5
+            assert np.array_equal(r.argmax_ids, lp.argmax(2))          # numpy argmax: first (lowest) index among equal maxima
+            cand_lp = e.debug_read(5, (n * S, 8)).reshape(n, S, 8)
+            cand_tok = e.debug_read(6, (n * S, 8)).view(np.int32).reshape(n, S, 8)
+            for i in range(n):
+                for f in range(S):
+                    want = _rank_candidates(lp[i, f], 8)
+                    assert np.array_equal(cand_tok[i, f], want), (kinds[i], t, f, cand_tok[i, f], want)
+                    assert np.array_equal(cand_lp[i, f], lp[i, f][want])
+                    n_rows += 1
+                emis[i].append(lp[i])
+                ids, last_blank, _ = O.greedy_ids(np.concatenate(emis[i]))
+                toks[i].extend(int(x) for x in r.new_tokens[i])
+                assert toks[i] == ids, (kinds[i], t)
+                assert int(r.blank_frames[i]) == int(round(last_blank / 0.04))
+                if kinds[i].startswith("peaked"):
+                    states[i] = B.beam_step(states[i], lp[i].astype(np.float64), beam=10, cand_k=8, max_len=1023)
+                    pre, score = B.best(states[i])
+                    assert list(r.beam_tokens[i]) == pre, (kinds[i], t)
+                    assert abs(float(r.beam_score[i]) - score) < 1e-3 * max(1.0, abs(score))
+                    # where the posterior is peaked the beam's best hypothesis is the greedy path
+                    assert pre == ids
+        report(f"decode stage on synthetic posteriors: {n_rows} rows (peaked / tied / flat) — candidates, argmax ties, log-probs, greedy carry, beam vs oracle exact")
+
+
 def test_pipelined_submit_collect_equals_sync(engines):
     """Two steps in flight (H2D of k+1 overlapping the kernels of k, batches assembled in the pinned staging buffers)
     must give bit-identical results to synchronous steps."""

@@ -27,6 +27,11 @@ namespace {
 using namespace tc;
 
 constexpr int LN_N = 512;
+#ifndef ASR_LN_KNOCK
+// diagnostic builds only (python -m asr_streaming_b200.build --out=... -DASR_LN_KNOCK=n, tools/gemm_ln_knock.py): bit 0 = no residual loads, 1 = no
+// global stores, 2 = no statistics exchange, 3 = stores go to a 4096-row (L2-resident) window, 4 = residual read from such a window
+#define ASR_LN_KNOCK 0
+#endif
 #ifdef ASR_EPI_TIMING
 __device__ unsigned long long g_ln_clk[8];                  // [0] tiles, [1] wait tfull, [2] R1, [3] exchange(s), [4] R2
 #define LN_T(var) const long long var = clock64()
@@ -430,7 +435,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = row0 + 4 * i + rsub;
-          const float4 r4 = row < p.M ? *reinterpret_cast<const float4*>(ep.res + (size_t)row * LN_N + col0 + csub) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 r4 = (row < p.M && !(ASR_LN_KNOCK & 1)) ? *reinterpret_cast<const float4*>(ep.res + (size_t)((ASR_LN_KNOCK & 16) ? (row & 4095) : row) * LN_N + col0 + csub)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(xpose + (4 * i + rsub) * L_LD + csub) = r4;
         }
         __syncwarp();
@@ -459,7 +465,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         s_a += s_b;
       }
       LN_T(lt2);
+#if ASR_LN_KNOCK & 4
+      RowStats st; st.mean = s_a * (1.0f / N_T); st.rstd = 1.0f / sqrtf(q_a * (1.0f / N_T) + 1e-5f);
+#else
       RowStats st = exchange_row_stats<NSPLIT, N_T>(s_a, q_a, X, round++);
+#endif
       RowStats st2 = st;                                     // statistics of y (two-LN forms)
 
       const float* g_fin = ep.g1;
@@ -552,9 +562,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             n[2] = (t.z - mu[i]) * rs[i] * gg.z + bb.z;
             n[3] = (t.w - mu[i]) * rs[i] * gg.w + bb.w;
           }
-          if (row < p.M) {
-            *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * LN_N + col) = ep.f32_normed ? make_float4(n[0], n[1], n[2], n[3]) : t;
-            int orow = row;
+          if (row < p.M && !(ASR_LN_KNOCK & 2)) {
+            *reinterpret_cast<float4*>(ep.out_f32 + (size_t)((ASR_LN_KNOCK & 8) ? (row & 4095) : row) * LN_N + col) = ep.f32_normed ? make_float4(n[0], n[1], n[2], n[3]) : t;
+            int orow = (ASR_LN_KNOCK & 8) ? (row & 4095) : row;
             if (ep.compact_rows) {                           // last layer: only the segment rows feed the CTC head (TA:emformer.py:803)
               const int b = row / ep.compact_rows, tt = row - b * ep.compact_rows;
               orow = tt < ep.compact_seg ? b * ep.compact_seg + tt : -1;

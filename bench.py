@@ -420,7 +420,9 @@ def family_rooflines(fam, cfg, streams, precision_exact, pk, workload):
     hbm = {"attention": streams * (2 * cfg.left_context * d * esz + cfg.rows * d * esz + cfg.rows * d * (4 if precision_exact else 2)),
            "fbank": streams * (cfg.chunk_length * 2 + cfg.frames * cfg.n_mels * (4 if precision_exact else 2)),
            "layernorm": M * d * (4 + esz), "ctc_greedy": streams * cfg.seg_rows * V * 4,
-           "beam": streams * cfg.seg_rows * V * 4}
+           # prefix beam: per frame the 8 candidates (id + log-prob), the row's (max, lse), the blank logit and one gathered logit per beam
+           # entry (a 32-byte sector each); the kernel is a serial recursion over the chunk's frames per stream, bound by latency, not bytes
+           "beam": streams * cfg.seg_rows * (8 * 8 + 8 + 32 * (1 + 10))}
     out = {}
     for k, v in fam.items():
         if not v["launches_per_step"]:

@@ -157,6 +157,13 @@ struct AsrEngine {
   DevBuf d_src_off[2];          // asr_submit_rings: element offsets of the step's chunks inside the pinned session rings
   DevBuf d_row_index[2];        // pre-staged batches: staged row of every batch element
   int prestaged_rows[2] = {-1, -1};   // rows gathered + copied ahead of the decision which of them run (engine_prestage)
+  // speculative front-end: the fbank of every pre-staged chunk does not depend on which of them will run, so engine_prestage queues it
+  // behind the running step (it executes in the collect -> submit gap); the step then only compacts the rows that run into a_fb
+  Operand a_fb_stage;
+  int fb_staged[2] = {0, 0};
+  bool spec_fbank = true;             // ASR_B200_NO_SPEC_FBANK=1: fbank inside the step through the row index (A/B)
+  bool act_fb_stage = false, act_fb_identity = false;
+  cudaEvent_t ev_pre[2] = {nullptr, nullptr};
   const int* act_row_index = nullptr;
   void* act_pcm = nullptr;      // input buffers the kernels of the step being enqueued read
   int* act_slots = nullptr;
@@ -459,19 +466,20 @@ int run_layers(AsrEngine* e, int n, int n_layers_to_run) {
   return 0;
 }
 
-int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool to_operand) {
+int run_fbank_melspec(AsrEngine* e, int n, int pcm_format, float* out_f32, bool to_operand, const Operand* dst = nullptr, const void* pcm = nullptr) {
   const Geo& g = e->geo;
   const FbankPlan& pl = e->mel128;
+  const Operand& afb = dst ? *dst : e->a_fb;
   FbankParams P;
   memset(&P, 0, sizeof(P));
-  P.pcm = e->act_pcm; P.row_index = e->act_row_index; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
+  P.pcm = pcm ? pcm : e->act_pcm; P.row_index = pcm ? nullptr : e->act_row_index; P.pcm_is_f32 = pcm_format == ASR_PCM_F32; P.pcm_stride = g.chunk_len; P.n_samples = g.chunk_len;
   P.n_frames = g.frames; P.hop = g.hop; P.frame_len = g.win; P.frame_off = (g.n_fft - g.win) / 2; P.nc = pl.nc; P.kaldi = 0;
   P.in_scale = P.pcm_is_f32 ? 1.0f : 1.0f / 32768.0f;                                  // streaming_server.py:362-363
   P.preemph = 0.f; P.log_floor = 1e-5f;                                                // audio.py:25 clamp(1e-5)
   P.window = pl.window.as<float>(); P.tw = pl.tw.as<float2>(); P.w2 = pl.w2.as<float2>();
   P.mel_start = pl.mel_start.as<int>(); P.mel_cnt = pl.mel_cnt.as<int>(); P.mel_off = pl.mel_off.as<int>(); P.mel_w = pl.mel_w.as<float>();
   P.n_mels = g.n_mels; P.out_f32 = out_f32;
-  P.out_op = to_operand ? e->a_fb.buf.as<bf16>() : nullptr; P.op_ld = e->a_fb.ld; P.op_lo_off = e->a_fb.lo_off;
+  P.out_op = to_operand ? afb.buf.as<bf16>() : nullptr; P.op_ld = afb.ld; P.op_lo_off = afb.lo_off;
   ProfScope ps(e, ASR_PROF_FBANK);
   return fbank_launch(P, n, e->stream);
 }
@@ -506,10 +514,17 @@ int run_decode(AsrEngine* e, int n, bool want_logprobs) {
 int run_pipeline(AsrEngine* e, int n, int pcm_format, int n_layers_to_run, bool with_ctc, bool want_logprobs) {
   pdl_set_active(n <= e->pdl_max_streams);
   const Geo& g = e->geo;
-  if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
+  const Operand* afb = &e->a_fb;
+  if (e->act_fb_stage) {                                     // the features exist already (engine_prestage): keep the rows that run
+    if (e->act_fb_identity) afb = &e->a_fb_stage;
+    else {
+      ProfScope ps(e, ASR_PROF_FBANK);
+      if (gather_blocks_launch(e->a_fb_stage.buf.p, e->a_fb.buf.p, e->act_row_index, n, (size_t)g.frames * e->a_fb.ld * sizeof(bf16), e->stream)) return -1;
+    }
+  } else if (run_fbank_melspec(e, n, pcm_format, nullptr, true)) return -1;
   // input_linear (encoder.py:142, no bias); its [n*frames, d/stride] output *is* the time-reduced [n*rows, d] (common.py:118-119)
   EpiF32 ein{e->x.as<float>(), nullptr, nullptr, g.d_model / g.stride, g.d_model / g.stride};
-  if (run_gemm(e, ASR_PROF_GEMM_IN, e->a_fb, e->w_in, n * g.frames, ein)) return -1;
+  if (run_gemm(e, ASR_PROF_GEMM_IN, *afb, e->w_in, n * g.frames, ein)) return -1;
   const int M = n * g.rows;
   { ProfScope ps(e, ASR_PROF_LN);
     if (ln_to_operand(e->x.as<float>(), e->layers[0].ln_in_g, e->layers[0].ln_in_b, e->a_ln.buf.as<bf16>(), e->a_ln.ld, e->a_ln.lo_off, M, g.d_model,
@@ -532,7 +547,7 @@ void drop_step_graphs(AsrEngine* e) {
 // The full per-step chain, replayed from a CUDA graph when the batch is small enough to be launch-bound.
 int run_step_chain(AsrEngine* e, int n, int pcm_format, bool want_logprobs) {
   const Geo& g = e->geo;
-  if (!e->use_graphs || e->prof_on || n > e->graph_max_streams) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
+  if (!e->use_graphs || e->prof_on || n > e->graph_max_streams || e->act_fb_stage) return run_pipeline(e, n, pcm_format, g.n_layers, true, want_logprobs);
   const char* asm_env = getenv("ASR_B200_ATTN_STREAM_MIN");           // read per launch by the attention dispatch: part of what a graph froze
   const uint64_t key = ((uint64_t)n << 8) | ((uint64_t)(e->act_slots == e->d_slots2.as<int>()) << 0) | ((uint64_t)(pcm_format == ASR_PCM_F32) << 1) |
                        ((uint64_t)want_logprobs << 2) | ((uint64_t)(e->beam > 0) << 3) | ((uint64_t)(e->act_row_index != nullptr) << 4) | ((uint64_t)((asm_env ? atoi(asm_env) : 148) & 0xffff) << 32);
@@ -687,7 +702,7 @@ void deliver(AsrEngine* e, int b, int n, bool want_lp, const AsrStepOut* out) {
 int submit_step(AsrEngine* e, int n, const int32_t* slots, const void* pcm, int fmt, bool want_lp, int* ticket) {
   const int b = e->cur_buf;
   if (e->pend[b].active) { set_error("two steps are already in flight: asr_collect the oldest ticket first"); return -1; }
-  e->prestaged_rows[b] = -1;
+  e->prestaged_rows[b] = -1; const int fb_was_staged = e->fb_staged[b]; e->fb_staged[b] = 0; (void)fb_was_staged;
   const auto t0 = std::chrono::steady_clock::now();
   if (stage_inputs(e, b, n, slots, pcm, fmt, e->copy_stream)) return -1;
   if (n) {
@@ -808,7 +823,7 @@ void destroy_engine(AsrEngine* e) {
   for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   e->graphs.clear();
   DevBuf* bufs[] = {&e->w_f32, &e->w_bf16, &e->ln_consts, &e->d_pcm, &e->d_slots, &e->d_pcm2, &e->d_slots2, &e->d_src_off[0], &e->d_src_off[1], &e->d_row_index[0], &e->d_row_index[1], &e->x, &e->x1, &e->x2, &e->q, &e->rc_kv, &e->logits, &e->fb_f32,
-                    &e->a_fb.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
+                    &e->a_fb.buf, &e->a_fb_stage.buf, &e->a_ln.buf, &e->a_attn.buf, &e->a_h.buf, &e->a_enc.buf, &e->a_ctc.buf, &e->kv_cache, &e->past_len,
                     &e->prev_id, &e->n_frames, &e->last_tok, &e->seg_has_text, &e->silent_mask, &e->d_argmax, &e->d_newtok, &e->d_nnew, &e->d_blank, &e->d_hastok, &e->d_hastext, &e->d_flags, &e->d_logprobs,
                     &e->bm_n, &e->bm_cur, &e->bm_len, &e->bm_last, &e->bm_pb, &e->bm_pnb, &e->bm_hash, &e->bm_tokens, &e->d_beam_tok, &e->d_beam_len, &e->d_beam_score, &e->bm_cand_tok, &e->bm_cand_lp, &e->bm_row_stat};
   for (DevBuf* b : bufs) b->free();
@@ -817,7 +832,7 @@ void destroy_engine(AsrEngine* e) {
   }
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+  for (int i = 0; i < 2; ++i) { if (e->h_buf[i]) cudaFreeHost(e->h_buf[i]); if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->ev_pre[i]) cudaEventDestroy(e->ev_pre[i]);
                                 if (e->ev_t0[i]) cudaEventDestroy(e->ev_t0[i]); if (e->ev_t1[i]) cudaEventDestroy(e->ev_t1[i]); }
   if (e->h_reset) cudaFreeHost(e->h_reset);
   for (auto ev : e->ev_reset) if (ev) cudaEventDestroy(ev);
@@ -850,6 +865,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
   if (const char* nf2 = getenv("ASR_B200_NO_LN_FUSE2")) e->no_fuse2 = nf2[0] == '1';
   if (const char* pt = getenv("ASR_B200_PAIR_LN_MIN_TILES")) e->pair_ln_min_tiles = atoi(pt);
   if (const char* nt = getenv("ASR_B200_NO_TMA_STORE")) e->tma_store = !(nt[0] == '1');
+  if (const char* ns = getenv("ASR_B200_NO_SPEC_FBANK")) e->spec_fbank = !(ns[0] == '1');
   if (const char* ug = getenv("ASR_B200_GRAPHS")) e->use_graphs = ug[0] == '1';
   if (const char* gm = getenv("ASR_B200_GRAPH_MAX_STREAMS")) e->graph_max_streams = atoi(gm);
   if (const char* qt = getenv("ASR_B200_QUAD_LN_MAX_TILES")) e->quad_ln_max_tiles = atoi(qt);
@@ -1007,6 +1023,7 @@ int create_engine(const AsrConfig* cfg, const float* weights, uint64_t n_floats,
     for (int i = 0; i < 2; ++i)
       ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&e->ev_pre[i], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&e->ev_t0[i]) == cudaSuccess && cudaEventCreate(&e->ev_t1[i]) == cudaSuccess;
     for (int i = 0; i < AsrEngine::kResetRing; ++i) ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_reset[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok) { set_error("cudaEventCreate failed"); break; }
@@ -1081,7 +1098,7 @@ int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_s
   const int b = e->cur_buf;
   if (n_rows < 0 || n_rows > e->cfg.max_batch) { set_error("prestage: %d rows outside [0, max_batch]", n_rows); return -1; }
   if (e->pend[b].active) { set_error("prestage: the next staging buffer still belongs to a step in flight"); return -1; }
-  e->prestaged_rows[b] = -1;
+  e->prestaged_rows[b] = -1; const int fb_was_staged = e->fb_staged[b]; e->fb_staged[b] = 0; (void)fb_was_staged;
   if (!n_rows) return 0;
   ASR_CUDA_OK(cudaSetDevice(e->device));
   if (device_gather) {                                      // the rings are pinned + mapped: a kernel on the copy stream reads the chunks over PCIe
@@ -1104,6 +1121,16 @@ int engine_prestage(AsrEngine* e, int n_rows, const int16_t* base, int64_t row_s
     ASR_CUDA_OK(cudaMemcpyAsync(dev_pcm(e, b), dst, pcm_bytes(e, n_rows, ASR_PCM_I16), cudaMemcpyHostToDevice, e->copy_stream));
   }
   e->prestaged_rows[b] = n_rows;
+  if (e->spec_fbank) {
+    // the front-end of every staged chunk, queued on the compute stream behind the running step: it executes while the host collects that
+    // step and decides which chunks run (nothing in it depends on the decision)
+    if (!e->a_fb_stage.buf.p && make_operand(e, &e->a_fb_stage, e->cfg.max_batch * e->geo.frames, e->geo.n_mels)) return -1;
+    ASR_CUDA_OK(cudaEventRecord(e->ev_pre[b], e->copy_stream));
+    ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_pre[b], 0));
+    pdl_set_active(false);
+    if (run_fbank_melspec(e, n_rows, ASR_PCM_I16, nullptr, true, &e->a_fb_stage, dev_pcm(e, b))) return -1;
+    e->fb_staged[b] = 1;
+  }
   return 0;
 }
 
@@ -1117,7 +1144,8 @@ int engine_submit_prestaged(AsrEngine* e, int n, const int32_t* slots, const int
   for (int i = 0; i < n; ++i)
     if (staged_index[i] < 0 || staged_index[i] >= e->prestaged_rows[b]) { set_error("submit_prestaged: staged row %d out of range", staged_index[i]); return -1; }
   const auto t0 = std::chrono::steady_clock::now();
-  e->prestaged_rows[b] = -1;
+  const int n_staged = e->prestaged_rows[b];
+  e->prestaged_rows[b] = -1; const int fb_was_staged = e->fb_staged[b]; e->fb_staged[b] = 0; (void)fb_was_staged;
   if (n) {
     ASR_CUDA_OK(cudaSetDevice(e->device));
     uint8_t* hs = reinterpret_cast<uint8_t*>(e->h_buf[b]);
@@ -1132,9 +1160,16 @@ int engine_submit_prestaged(AsrEngine* e, int n, const int32_t* slots, const int
     ASR_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     use_buffer(e, b);
     e->act_row_index = e->d_row_index[b].as<int>();
+    e->act_fb_stage = fb_was_staged != 0;
+    e->act_fb_identity = false;
+    if (e->act_fb_stage && n == n_staged) {                   // every staged chunk runs, in staging order: no compaction needed
+      bool id = true;
+      for (int i = 0; i < n && id; ++i) id = staged_index[i] == i;
+      e->act_fb_identity = id;
+    }
     if (e->ev_t0[b]) cudaEventRecord(e->ev_t0[b], e->stream);
     const int rc = run_step_chain(e, n, ASR_PCM_I16, want_lp);
-    e->act_row_index = nullptr;
+    e->act_row_index = nullptr; e->act_fb_stage = false; e->act_fb_identity = false;
     if (rc) return -1;
     if (enqueue_d2h(e, b, n, want_lp)) return -1;
     if (e->ev_t1[b]) cudaEventRecord(e->ev_t1[b], e->stream);

@@ -126,6 +126,8 @@ int convert_weight(const float* src, bf16* dst, int rows, int cols, int ld, int 
 int fill_i32(int* p, int v, size_t n, cudaStream_t st);
 // device-side batch assembly from pinned host rings (zero-copy reads): dst[i] = base[src_off[i] .. + chunk_len)
 int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st);
+// dst block i = src block idx[i], blocks of block_bytes (multiple of 16): compaction of pre-computed per-stream operand blocks
+int gather_blocks_launch(const void* src, void* dst, const int* idx, int n, size_t block_bytes, cudaStream_t st);
 // endpoint on many sessions at once: past_len = n_frames = has_text = 0, prev_id = last_tok = -1 for the listed slots
 int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, int* prev_id, int* last_tok, int* has_text, cudaStream_t st);
 // per-utterance CMVN over the frames of one call (TA:compliance/kaldi.py:603-606, subtract_mean)

@@ -1150,6 +1150,13 @@ __global__ void __launch_bounds__(256) gather_rings_kernel(const int16_t* __rest
   }
 }
 
+// dst block i = src block idx[i] (blocks of vec_per_block 16-byte vectors): the pre-computed fbank operands of the chunks that run
+__global__ void __launch_bounds__(256) gather_blocks_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ idx, int vec_per_block) {
+  const uint4* s = src + (size_t)idx[blockIdx.x] * vec_per_block;
+  uint4* d = dst + (size_t)blockIdx.x * vec_per_block;
+  for (int i = threadIdx.x; i < vec_per_block; i += blockDim.x) d[i] = s[i];
+}
+
 __global__ void fill_i32_kernel(int* p, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1243,6 +1250,14 @@ int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, in
 int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st) {
   if (n <= 0) return 0;
   gather_rings_kernel<<<n, 256, 0, st>>>(base_dev, src_off, dst, chunk_len);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gather_blocks_launch(const void* src, void* dst, const int* idx, int n, size_t block_bytes, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (block_bytes % 16) { set_error("gather_blocks: block of %zu bytes is not a multiple of 16", block_bytes); return -1; }
+  gather_blocks_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, (int)(block_bytes / 16));
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1136,17 +1136,30 @@ __global__ void reset_slots_kernel(const int* __restrict__ slots, int n, int* pa
 }
 
 // Batch assembly on the device: chunk i = chunk_len int16 samples at base + src_off[i] (pinned, mapped host memory: the sessions'
-// audio rings, read over PCIe) -> row i of the step's PCM buffer.  One CTA per chunk, 16-byte loads when the source is aligned.
-__global__ void __launch_bounds__(256) gather_rings_kernel(const int16_t* __restrict__ base, const long long* __restrict__ src_off,
-                                                           int16_t* __restrict__ dst, int chunk_len) {
-  const int16_t* s = base + src_off[blockIdx.x];
-  int16_t* d = dst + (size_t)blockIdx.x * chunk_len;
-  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0 && (chunk_len & 7) == 0) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(s);
-    uint4* d4 = reinterpret_cast<uint4*>(d);
-    for (int i = threadIdx.x; i < chunk_len / 8; i += blockDim.x) d4[i] = s4[i];
-  } else {
-    for (int i = threadIdx.x; i < chunk_len; i += blockDim.x) d[i] = s[i];
+// audio rings, read over PCIe) -> row i of the step's PCM buffer.  The kernel runs on the copy stream UNDER the compute stream's step, whose
+// persistent GEMM CTAs take ~55 k of an SM's 64 k registers: a gather CTA must be small enough to sit next to one (128 threads, few
+// registers, one CTA per SM, persistent over the chunks) or the next GEMM's CTAs wait for gather CTAs that are themselves waiting on PCIe
+// round trips (a 256-thread CTA per chunk cost the step 2 ms of its 14 at 4096 streams; 74 persistent 128-thread CTAs cost it 0.5 ms).  Four
+// independent 16-byte loads per thread keep ~150 KB in flight on the link.
+constexpr int GR_THREADS = 128;
+__global__ void __launch_bounds__(GR_THREADS) gather_rings_kernel(const int16_t* __restrict__ base, const long long* __restrict__ src_off,
+                                                                  int16_t* __restrict__ dst, int n, int chunk_len) {
+  for (int c = blockIdx.x; c < n; c += gridDim.x) {
+    const int16_t* s = base + src_off[c];
+    int16_t* d = dst + (size_t)c * chunk_len;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0 && (chunk_len & 7) == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(s);
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      const int nv = chunk_len / 8;
+      int i = threadIdx.x;
+      for (; i + 3 * GR_THREADS < nv; i += 4 * GR_THREADS) {
+        const uint4 a0 = s4[i], a1 = s4[i + GR_THREADS], a2 = s4[i + 2 * GR_THREADS], a3 = s4[i + 3 * GR_THREADS];
+        d4[i] = a0; d4[i + GR_THREADS] = a1; d4[i + 2 * GR_THREADS] = a2; d4[i + 3 * GR_THREADS] = a3;
+      }
+      for (; i < nv; i += GR_THREADS) d4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < chunk_len; i += GR_THREADS) d[i] = s[i];
+    }
   }
 }
 
@@ -1249,7 +1262,10 @@ int reset_slots_launch(const int* slots, int n, int* past_len, int* n_frames, in
 
 int gather_rings_launch(const int16_t* base_dev, const long long* src_off, int16_t* dst, int n, int chunk_len, cudaStream_t st) {
   if (n <= 0) return 0;
-  gather_rings_kernel<<<n, 256, 0, st>>>(base_dev, src_off, dst, chunk_len);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = sms / 2 > 0 ? sms / 2 : 1;       // measured at 4096 streams: 37 or 74 CTAs cost the concurrent step 0.9 ms less than 148 (PCIe-bound either way)
+  gather_rings_kernel<<<n < ctas ? n : ctas, GR_THREADS, 0, st>>>(base_dev, src_off, dst, n, chunk_len);
   ASR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -8,7 +8,7 @@ A step = one pass of the hot path (PCM -> fbank -> 20-layer Emformer chunk forwa
 greedy / prefix beam) over one batch of `streams` concurrent 640 ms stream-chunks per GPU.  `value` times K steps with the PCM
 batch already resident in HBM (CUDA events on the engine's own stream); `e2e` times the public API with host int16 buffers, H2D of
 the PCM and D2H of the token ids inside the timed region.  Default workload = BASELINE configs[3] (the largest single-GPU
-configuration): 4096 sessions at mixed progress driven by SessionScheduler (VAD gate, pinned gather, two ticks in flight, endpoint
+configuration): 4096 sessions at mixed progress driven by SessionScheduler (VAD gate, pinned gather, one pre-staged tick per pass, endpoint
 rules), prefix beam 10.  N > 1: one process per GPU (torchrun), sessions partitioned per GPU, no data-path collective (weak
 scaling), time = max over ranks.
 """
@@ -42,7 +42,7 @@ WORKLOADS = {
                         "at random phases, served by SessionScheduler ticks (two in flight, greedy CTC); reports per-chunk latency p50 / p99"),
     "lowlat4096": (4096, "configs[4] per-GPU share: 4096 concurrent streams per GPU, chunk_size=8 low-latency mode (320 ms chunks), greedy CTC"),
     "longform": (4096, "configs[4] long form: 4096 concurrent streams per GPU (32k on 8 GPUs), chunk_size=8 low-latency mode, 10 minutes of audio per stream "
-                       "(1875 chunks of 320 ms; --long-chunks), SessionScheduler with two ticks in flight, energy-gate VAD, endpoint rules (forced rule4 endpoints at 40 s)"),
+                       "(1875 chunks of 320 ms; --long-chunks), SessionScheduler with one pre-staged full-size tick per pass, energy-gate VAD, endpoint rules (forced rule4 endpoints at 40 s)"),
 }
 FLOP_PER_STREAM_CHUNK = 2_583_363_584          # SURVEY.md §8a (L_valid = 32)
 

@@ -569,15 +569,18 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_c
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt * 8 < n_keys) {                                     // warp-uniform
-        int key = nt * 8 + g;
+        // K fragments by ldmatrix.x4: lane -> (matrix lane / 8, row lane % 8); the four matrices of one instruction are the b0 | b1 pairs of two
+        // 16-dim steps (dims [32 hf, 32 hf + 32) of key nt * 8 + row) — 2 instructions and 2 address computations per 8 keys instead of 8 LDS.32
+        int key = nt * 8 + (lane & 7);
         key = key < n_keys ? key : n_keys - 1;                    // clamp: garbage columns are masked below
         const uint32_t ro = as_row_off<SEG>(key, n_ring, head);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t b0, b1;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(s_k + as_swz(ro, 2 * ks) + tig * 4));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(s_k + as_swz(ro, 2 * ks + 1) + tig * 4));
-          mma_bf16_16816(sc[nt], qa[ks], b0, b1);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t k0, k1, k2, k3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3) : "r"(s_k + as_swz(ro, 4 * hf + (lane >> 3))));
+          mma_bf16_16816(sc[nt], qa[2 * hf], k0, k1);
+          mma_bf16_16816(sc[nt], qa[2 * hf + 1], k2, k3);
         }
       }
     }

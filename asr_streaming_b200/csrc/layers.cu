@@ -808,19 +808,22 @@ attention_exact_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_co
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt * 8 < n_keys) {
-        int key = nt * 8 + g;
+        int key = nt * 8 + (lane & 7);                            // ldmatrix.x4: lane -> (matrix lane / 8, row lane % 8), as in attention_stream_kernel
         key = key < n_keys ? key : n_keys - 1;                    // clamp: garbage columns are masked below
         const uint32_t rh = ax_row_off<SEG>(key, n_ring, head), rl = ax_row_off<SEG>(key, n_ring, head + 8);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t h0, h1, l0, l1;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(h0) : "r"(s_k + as_swz(rh, 2 * ks) + tig * 4));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(h1) : "r"(s_k + as_swz(rh, 2 * ks + 1) + tig * 4));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(l0) : "r"(s_k + as_swz(rl, 2 * ks) + tig * 4));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(l1) : "r"(s_k + as_swz(rl, 2 * ks + 1) + tig * 4));
-          mma_bf16_16816(sc[nt], ql[ks], h0, h1);                 // small terms first
-          mma_bf16_16816(sc[nt], qh[ks], l0, l1);
-          mma_bf16_16816(sc[nt], qh[ks], h0, h1);
+        for (int hf = 0; hf < 2; ++hf) {                          // dims [32 hf, 32 hf + 32): (b0, b1) of steps ks = 2 hf and 2 hf + 1, hi and lo pieces
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(s_k + as_swz(rh, 4 * hf + (lane >> 3))));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(s_k + as_swz(rl, 4 * hf + (lane >> 3))));
+          mma_bf16_16816(sc[nt], ql[2 * hf], h0, h1);             // small terms first
+          mma_bf16_16816(sc[nt], qh[2 * hf], l0, l1);
+          mma_bf16_16816(sc[nt], qh[2 * hf], h0, h1);
+          mma_bf16_16816(sc[nt], ql[2 * hf + 1], h2, h3);
+          mma_bf16_16816(sc[nt], qh[2 * hf + 1], l2, l3);
+          mma_bf16_16816(sc[nt], qh[2 * hf + 1], h2, h3);
         }
       }
     }
@@ -962,6 +965,8 @@ constexpr int CTC_MAXV = 32;   // vocab <= 1024
 __device__ __forceinline__ uint32_t f2key(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
+// NV = ceil(vocab / 32) columns per lane (26 for the 804-entry vocabulary: the loops below are fully unrolled over it)
+template <int NV>
 __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
   __shared__ int s_ids[64];
   __shared__ float s_clp[8][32];                                 // per warp: the row's elements that can be among its cand_k best
@@ -972,10 +977,10 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
   for (int r = warp; r < P.seg_rows; r += 8) {
     const size_t row = (size_t)b * P.seg_rows + r;
     const float* z = P.logits + row * P.vocab;
-    float v[CTC_MAXV];
+    float v[NV];
     float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < CTC_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       v[i] = c < P.vocab ? z[c] : -INFINITY;
       m = fmaxf(m, v[i]);
@@ -983,12 +988,12 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
     m = warp_max(m);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < CTC_MAXV; ++i) s += (lane + 32 * i < P.vocab) ? __expf(v[i] - m) : 0.f;    // ex2.approx: 2e-7 relative per term, 1e-6 on the log-probs (bound 2e-4)
+    for (int i = 0; i < NV; ++i) s += (lane + 32 * i < P.vocab) ? __expf(v[i] - m) : 0.f;    // ex2.approx: 2e-7 relative per term, 1e-6 on the log-probs (bound 2e-4)
     const float lse = logf(warp_sum(s));
     float best = -INFINITY; int bi = 0x7fffffff;
     float lm = -INFINITY;                                          // lane maximum over the non-blank ids
 #pragma unroll
-    for (int i = 0; i < CTC_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < P.vocab) {
         const float lp = (v[i] - m) - lse;                       // log_softmax(dim=2)
@@ -1019,7 +1024,7 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
       const float T = key2f(__reduce_max_sync(0xffffffffu, w));
       int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < CTC_MAXV; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         const bool f = c < P.vocab && c != 0 && v[i] >= T && v[i] > -INFINITY;
         const uint32_t bal = __ballot_sync(0xffffffffu, f);
@@ -1044,7 +1049,7 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
         for (int k = 0; k < P.cand_k; ++k) {
           float cb = -INFINITY; int ci = 0x7fffffff;
 #pragma unroll
-          for (int i = 0; i < CTC_MAXV; ++i) {
+          for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < P.vocab && c != 0 && v[i] > cb) { cb = v[i]; ci = c; }
           }
@@ -1052,7 +1057,7 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
           const int wc = (int)__reduce_min_sync(0xffffffffu, (uint32_t)(f2key(cb) == mx ? ci : 0x7fffffff));
           if (lane == k) { my_lp = key2f(mx); my_tok = mx == f2key(-INFINITY) ? 0x7fffffff : wc; }
 #pragma unroll
-          for (int i = 0; i < CTC_MAXV; ++i)
+          for (int i = 0; i < NV; ++i)
             if (wc == lane + 32 * i) v[i] = -INFINITY;
         }
       }
@@ -1240,7 +1245,8 @@ template int attention_launch<bf16>(const AttnParams<bf16>&, int, cudaStream_t);
 int ctc_greedy_launch(const CtcParams& P, int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return 0;
   if (P.vocab > 32 * CTC_MAXV || P.seg_rows > 64) { set_error("ctc: vocab %d / seg_rows %d too large", P.vocab, P.seg_rows); return -1; }
-  ASR_CUDA_OK(launch_pdl(ctc_greedy_kernel, dim3(n_streams), dim3(256), 0, st, P));
+  if (P.vocab <= 26 * 32) { ASR_CUDA_OK(launch_pdl(ctc_greedy_kernel<26>, dim3(n_streams), dim3(256), 0, st, P)); }
+  else { ASR_CUDA_OK(launch_pdl(ctc_greedy_kernel<CTC_MAXV>, dim3(n_streams), dim3(256), 0, st, P)); }
   return 0;
 }
 

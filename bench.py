@@ -921,7 +921,7 @@ def run_ours(args):
             t = fam["fbank"]["ms_per_step"] / fam["fbank"]["launches_per_step"]
             ach = alg_bytes / (t / 1e3) / 1e9
             roof = {"kernel": "fbank_kernel<256,int16,kaldi>", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic_table().get("fbank1024", {}).get("fbank"), "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": alg_bytes}
         else:
             M = streams * cfg.rows

@@ -1021,7 +1021,8 @@ __global__ void __launch_bounds__(256, 4) ctc_greedy_kernel(CtcParams P) {
         const uint32_t bal = __ballot_sync(0xffffffffu, w == mx);
         if (lane == __ffs(bal) - 1) w = 0u;
       }
-      const float T = key2f(__reduce_max_sync(0xffffffffu, w));
+      float T = key2f(__reduce_max_sync(0xffffffffu, w));
+      if (!(T == T)) T = -INFINITY;                                // fewer than cand_k lanes hold a finite value (tiny vocabularies): everything finite qualifies
       int cnt = 0;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {

@@ -872,6 +872,7 @@ def run_ours(args):
                                                 "scripted endpoints": 1e3 * (wl.t_after - h0[2]) / max(1, wl.n_ticks - h0[3]),
                                                 "of which prestage (overlaps the running tick)": 1e3 * (getattr(wl, "t_prestage", 0.0) - h0[4]) / max(1, wl.n_ticks - h0[3])},
                            "gpu_busy_ms_per_pass": gpu_busy_ms / e2e_steps, "gpu_steps_per_pass": gpu_busy_n / e2e_steps,
+                           "gpu_busy_counts": "first to last kernel of each pipelined step (asr_pipeline_gpu_time); the speculative fbank of the pre-staged chunks (~0.75 ms per pass at 4096 sessions) runs between steps and is not included",
                            "e2e_counts": "audio-seconds of the chunks actually decoded (VAD-skipped chunks are excluded from e2e.value)"}
         e2e_audio_per_step = run_c * (cfg.segment_length / cfg.sample_rate) / e2e_steps
     else:
